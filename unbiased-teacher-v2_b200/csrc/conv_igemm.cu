@@ -1,0 +1,465 @@
+// Implicit-GEMM convolution on the sm_100a tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces the cuDNN conv2d calls the reference reaches through Detectron2 / torch:
+//   ResNet bottlenecks + FPN          (ubteacher/modeling/backbone/fpn.py:59-78 -> [D2] ResNet/FPN)
+//   FCOS towers + prediction convs    (ubteacher/modeling/fcos/fcos.py:248-304, :338-376)
+//
+// Layouts (all bf16, fp32 accumulate):
+//   activations  NHWC  == row-major [M = N*P*Q, C]
+//   weights      [Cout, R, S, Cin]  == row-major [Cout, K = R*S*Cin]   (K-major B operand)
+// Forward:  Y[m, n] = sum_k im2col(X)[m, k] * W[n, k]   -> epilogue: *scale[n] + shift[n] (+res) (relu)
+// Dgrad  :  the same kernel on dY with the flipped/transposed filter (host packs it).
+// Wgrad  :  dW[n, tap, c] = sum_m dY[m, n] * im2col(X)[m, tap, c]  (both operands MN-major,
+//           reduction over pixels, split-K with fp32 red.global.add).
+//
+// The A operand never exists in memory: each k-block is one filter tap x 64 input channels and is
+// fetched by one im2col-mode TMA load (hardware halo zero-fill, stride handled by the descriptor).
+#include "sm100_ptx.cuh"
+#include "tmap.cuh"
+#include "ut2_internal.h"
+
+namespace ut2 {
+
+constexpr int BM = 128;          // output pixels per tile (UMMA M)
+constexpr int BK = 64;           // K elements per pipeline stage (128 B rows, SWIZZLE_128B)
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;        // 16 KiB
+constexpr int B_BYTES = 256 * BK * 2;       // 32 KiB (block_n <= 256)
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;            // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int TMEM_COLS = 512;              // 2 accumulator buffers x 256 fp32 columns
+
+struct ConvFwdArgs {
+  int M, Cout, ldo;
+  int block_n, n_tiles, m_tiles;
+  int P, Q, stride, pad;
+  int R, S, Cin;
+  int relu;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  int ldr;
+  __nv_bfloat16* out;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                const ConvFwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = a.m_tiles * a.n_tiles;
+  const int c_chunks = a.Cin / BK;
+  const int num_kb = a.R * a.S * c_chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_w);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA producer
+      uint32_t stage = 0, phase = 0;
+      const uint32_t tx_bytes = A_BYTES + a.block_n * BK * 2;
+      const int PQ = a.P * a.Q;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
+        const int m0 = m_tile * BM;
+        const int img = m0 / PQ, rem = m0 - img * PQ;
+        const int p0 = rem / a.Q, q0 = rem - p0 * a.Q;
+        const int w0 = q0 * a.stride - a.pad, h0 = p0 * a.stride - a.pad;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / c_chunks, c0 = (kb - tap * c_chunks) * BK;
+          const int r = tap / a.S, s = tap - r * a.S;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          tma_load_im2col_4d(sa, &tmap_x, &full_bar[stage], c0, w0, h0, img, (uint16_t)s,
+                             (uint16_t)r);
+          tma_load_2d(sa + A_BYTES, &tmap_w, &full_bar[stage], tap * a.Cin + c0,
+                      n_tile * a.block_n);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------ MMA issuer
+      const uint32_t idesc = umma_idesc_bf16(BM, a.block_n, 0, 0);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = umma_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bd = umma_smem_desc_sw128(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // -------------------------------------------------- epilogue (4 warps, TMEM lane quadrant = warp % 4)
+    const int quad = warp & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
+      const int m = m_tile * BM + quad * 32 + lane;
+      const int nbase = n_tile * a.block_n;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
+      for (int c = 0; c < a.block_n; c += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(taddr + c, v);
+        tmem_ld_wait();
+        const int n0 = nbase + c;
+        if (m < a.M && n0 < a.Cout) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (a.scale) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] *= __ldg(a.scale + n0 + i);
+          }
+          if (a.shift) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += __ldg(a.shift + n0 + i);
+          }
+          if (a.residual) {
+            const uint4* rp =
+                reinterpret_cast<const uint4*>(a.residual + (size_t)m * a.ldr + n0);
+            uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[i]);
+              f[2 * i] += __low2float(h);
+              f[2 * i + 1] += __high2float(h);
+            }
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          uint4 o0, o1;
+          o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+          o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+          o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+          o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+          uint4* op = reinterpret_cast<uint4*>(a.out + (size_t)m * a.ldo + n0);
+          op[0] = o0;
+          op[1] = o1;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------ wgrad
+constexpr int WG_PIX = 64;                      // pixels (GEMM-K) per stage
+constexpr int WG_BLK_BYTES = WG_PIX * 64 * 2;   // one [64 pix][64 ch] swizzled block = 8 KiB
+constexpr int WG_A_BYTES = 2 * WG_BLK_BYTES;    // 128 output channels
+constexpr int WG_B_BYTES = 4 * WG_BLK_BYTES;    // up to 256 input channels
+constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
+constexpr int WG_SMEM_BYTES = STAGES * WG_STAGE_BYTES + 1024 + 256;
+
+struct ConvWgradArgs {
+  int Mpix, Cout, Cin, R, S, P, Q, stride, pad;
+  int block_n;      // input-channel tile width (64 / 128 / 256)
+  int c_tiles, n_tiles, taps;
+  int kb_total, kb_per_split;
+  const float* scale;   // optional per-Cout factor (FrozenBN scale)
+  float* dw;            // [Cout, R*S*Cin] fp32, accumulated
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                  const ConvWgradArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * WG_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int tile = blockIdx.x;
+  const int c_tile = tile % a.c_tiles; tile /= a.c_tiles;
+  const int tap = tile % a.taps;       tile /= a.taps;
+  const int n_tile = tile;
+  const int kb_begin = blockIdx.y * a.kb_per_split;
+  const int kb_end = min(a.kb_total, kb_begin + a.kb_per_split);
+  if (kb_begin >= kb_end) return;   // uniform for the whole CTA
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_g);
+    prefetch_tmap(&tmap_x);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nblk = a.block_n / 64;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t tx_bytes = (2 + nblk) * WG_BLK_BYTES;
+      const int PQ = a.P * a.Q;
+      const int r = tap / a.S, s = tap - r * a.S;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int pix0 = kb * WG_PIX;
+        const int img = pix0 / PQ, rem = pix0 - img * PQ;
+        const int p0 = rem / a.Q, q0 = rem - p0 * a.Q;
+        const int w0 = q0 * a.stride - a.pad, h0 = p0 * a.stride - a.pad;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * WG_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+        for (int j = 0; j < 2; ++j)
+          tma_load_2d(sa + j * WG_BLK_BYTES, &tmap_g, &full_bar[stage], n_tile * 128 + j * 64,
+                      pix0);
+        for (int j = 0; j < nblk; ++j)
+          tma_load_im2col_4d(sa + WG_A_BYTES + j * WG_BLK_BYTES, &tmap_x, &full_bar[stage],
+                             c_tile * a.block_n + j * 64, w0, h0, img, (uint16_t)s, (uint16_t)r);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, a.block_n, 1, 1);
+      uint32_t stage = 0, phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * WG_STAGE_BYTES);
+        const uint32_t sb = sa + WG_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_PIX / 16; ++k) {
+          // MN-major SW128: 64-channel blocks LBO apart, 8-pixel groups SBO apart.
+          const uint64_t ad = umma_smem_desc_sw128(sa + k * 2048, WG_BLK_BYTES, 1024);
+          const uint64_t bd = umma_smem_desc_sw128(sb + k * 2048, WG_BLK_BYTES, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (kb != kb_begin) || (k != 0));
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int n = n_tile * 128 + quad * 32 + lane;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const size_t K = (size_t)a.R * a.S * a.Cin;
+    const float sc = (a.scale && n < a.Cout) ? __ldg(a.scale + n) : 1.f;
+    for (int c = 0; c < a.block_n; c += 16) {
+      uint32_t v[16];
+      tmem_ld_32x16(taddr + c, v);
+      tmem_ld_wait();
+      if (n < a.Cout) {
+        float* dst = a.dw + (size_t)n * K + (size_t)tap * a.Cin + c_tile * a.block_n + c;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(dst + i, __uint_as_float(v[i]) * sc);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------ probe
+// Debug: one im2col TMA load -> raw smem dump (used by tests to pin the descriptor semantics).
+__global__ void im2col_probe_kernel(const __grid_constant__ CUtensorMap tmap, int c, int w, int h,
+                                    int n, int off_w, int off_h, int bytes, uint8_t* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar, bytes);
+    tma_load_im2col_4d(smem, &tmap, &bar, c, w, h, n, (uint16_t)off_w, (uint16_t)off_h);
+    mbar_wait(&bar, 0);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = smem[i];
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+static int pick_block_n(int cout) {
+  if (cout % 16) return -1;
+  if (cout <= 256) return cout;
+  if (cout % 256 == 0) return 256;
+  if (cout % 128 == 0) return 128;
+  return -1;
+}
+
+}  // namespace ut2
+
+using namespace ut2;
+
+extern "C" int ut2_conv2d_nhwc_bf16_fwd(const void* x, int N, int H, int W, int Cin, const void* w,
+                                        int Cout, int R, int S, int stride, int pad,
+                                        const float* scale, const float* shift,
+                                        const void* residual, int relu, void* y, void* stream) {
+  if (!x || !w || !y) return ut2_fail(-1, "conv_fwd: null pointer");
+  if (Cin % 64 || Cin <= 0) return ut2_fail(-2, "conv_fwd: Cin must be a multiple of 64");
+  const int block_n = pick_block_n(Cout);
+  if (block_n < 0) return ut2_fail(-3, "conv_fwd: unsupported Cout (need %16==0; >256 needs %128==0)");
+  if (stride < 1 || stride > 8 || pad < 0 || R < 1 || S < 1) return ut2_fail(-4, "conv_fwd: bad geometry");
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  if (P <= 0 || Q <= 0) return ut2_fail(-4, "conv_fwd: empty output");
+  ConvFwdArgs a;
+  a.M = N * P * Q; a.Cout = Cout; a.ldo = Cout;
+  a.block_n = block_n; a.n_tiles = (Cout + block_n - 1) / block_n; a.m_tiles = (a.M + BM - 1) / BM;
+  a.P = P; a.Q = Q; a.stride = stride; a.pad = pad; a.R = R; a.S = S; a.Cin = Cin;
+  a.relu = relu; a.scale = scale; a.shift = shift;
+  a.residual = static_cast<const __nv_bfloat16*>(residual); a.ldr = Cout;
+  a.out = static_cast<__nv_bfloat16*>(y);
+  CUtensorMap tx, tw;
+  int rc = make_tmap_im2col_bf16(&tx, x, N, H, W, Cin, R, S, stride, pad, 64, BM);
+  if (rc) return ut2_fail(rc, "conv_fwd: activation tensor map encode failed");
+  rc = make_tmap_2d_bf16(&tw, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64, block_n);
+  if (rc) return ut2_fail(rc, "conv_fwd: weight tensor map encode failed");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return ut2_fail((int)e, "conv_fwd: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  const int tiles = a.m_tiles * a.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tx, tw, a);
+  return ut2_check_launch("conv_fwd");
+}
+
+extern "C" int ut2_conv2d_nhwc_bf16_wgrad(const void* x, int N, int H, int W, int Cin,
+                                          const void* dy, int Cout, int R, int S, int stride,
+                                          int pad, const float* scale, float* dw, void* stream) {
+  if (!x || !dy || !dw) return ut2_fail(-1, "conv_wgrad: null pointer");
+  if (Cin % 64 || Cin <= 0) return ut2_fail(-2, "conv_wgrad: Cin must be a multiple of 64");
+  if (Cout % 8) return ut2_fail(-3, "conv_wgrad: Cout must be a multiple of 8");
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  if (P <= 0 || Q <= 0) return ut2_fail(-4, "conv_wgrad: empty output");
+  ConvWgradArgs a;
+  a.Mpix = N * P * Q; a.Cout = Cout; a.Cin = Cin; a.R = R; a.S = S; a.P = P; a.Q = Q;
+  a.stride = stride; a.pad = pad;
+  a.block_n = Cin % 256 == 0 ? 256 : (Cin % 128 == 0 ? 128 : 64);
+  a.c_tiles = Cin / a.block_n; a.n_tiles = (Cout + 127) / 128; a.taps = R * S;
+  a.kb_total = (a.Mpix + WG_PIX - 1) / WG_PIX;
+  const int out_tiles = a.c_tiles * a.n_tiles * a.taps;
+  int splits = (2 * num_sms() + out_tiles - 1) / out_tiles;
+  if (splits > a.kb_total) splits = a.kb_total;
+  if (splits < 1) splits = 1;
+  a.kb_per_split = (a.kb_total + splits - 1) / splits;
+  splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
+  a.scale = scale; a.dw = dw;
+  CUtensorMap tg, tx;
+  int rc = make_tmap_2d_bf16(&tg, dy, a.Mpix, Cout, Cout, 64, WG_PIX);
+  if (rc) return ut2_fail(rc, "conv_wgrad: dY tensor map encode failed");
+  rc = make_tmap_im2col_bf16(&tx, x, N, H, W, Cin, R, S, stride, pad, 64, WG_PIX);
+  if (rc) return ut2_fail(rc, "conv_wgrad: activation tensor map encode failed");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+    if (e != cudaSuccess) return ut2_fail((int)e, "conv_wgrad: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  dim3 grid(out_tiles, splits);
+  conv_wgrad_kernel<<<grid, NUM_THREADS, WG_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tg, tx, a);
+  return ut2_check_launch("conv_wgrad");
+}
+
+extern "C" int ut2_debug_im2col_probe(const void* x, int N, int H, int W, int C, int R, int S,
+                                      int stride, int pad, int pixels, int c, int w, int h, int n,
+                                      int off_w, int off_h, void* out, void* stream) {
+  CUtensorMap tx;
+  int rc = make_tmap_im2col_bf16(&tx, x, N, H, W, C, R, S, stride, pad, 64, pixels);
+  if (rc) return ut2_fail(rc, "probe: tensor map encode failed");
+  const int bytes = pixels * 128;
+  cudaFuncSetAttribute(im2col_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + 1024);
+  im2col_probe_kernel<<<1, 128, bytes + 1024, static_cast<cudaStream_t>(stream)>>>(
+      tx, c, w, h, n, off_w, off_h, bytes, static_cast<uint8_t*>(out));
+  return ut2_check_launch("im2col_probe");
+}
