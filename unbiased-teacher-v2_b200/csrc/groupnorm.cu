@@ -1,0 +1,229 @@
+// GroupNorm(32, 256) + ReLU for the FCOS towers, NHWC bf16 (reference: nn.GroupNorm + nn.ReLU,
+// ubteacher/modeling/fcos/fcos.py:263-264,283). Eight channels per group == one 16-byte vector per
+// (pixel, group), so every kernel is a flat coalesced uint4 stream; statistics are accumulated in
+// fp64 atomics per (image, group).
+//
+// Algorithmic bytes per element (bf16): fwd = read x twice + write y = 6 B; bwd = read x, dy twice +
+// write dx = 10 B.
+#include "ut2_internal.h"
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace {
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8]) {
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = __uint_as_float(u[j] << 16);
+    f[2 * j + 1] = __uint_as_float(u[j] & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    o[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+constexpr int GN_G = 32;          // groups (== vectors per pixel)
+constexpr int GN_ROWS = 8;        // pixel rows per block iteration (256 threads)
+
+// stats[n][g] = {sum, sumsq} over HW x 8 channels
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats, int HW, int pix_per_block) {
+  const int n = blockIdx.y, g = threadIdx.x & 31, row = threadIdx.x >> 5;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + (size_t)n * HW * GN_G;
+  float s1 = 0.f, s2 = 0.f;
+  for (int p = p0 + row; p < p1; p += GN_ROWS) {
+    float f[8];
+    unpack8(__ldg(xv + (size_t)p * GN_G + g), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
+  }
+  __shared__ float red[GN_ROWS][GN_G][2];
+  red[row][g][0] = s1;
+  red[row][g][1] = s2;
+  __syncthreads();
+  if (row == 0) {
+    double d1 = 0.0, d2 = 0.0;
+    for (int k = 0; k < GN_ROWS; ++k) { d1 += red[k][g][0]; d2 += red[k][g][1]; }
+    atomicAdd(stats + ((size_t)n * GN_G + g) * 2, d1);
+    atomicAdd(stats + ((size_t)n * GN_G + g) * 2 + 1, d2);
+  }
+}
+
+__device__ __forceinline__ void mean_rstd(const double* stats, int n, int g, int HW, float eps, float& mean,
+                                          float& rstd) {
+  const double m = (double)HW * 8.0;
+  const double mu = stats[((size_t)n * GN_G + g) * 2] / m;
+  double var = stats[((size_t)n * GN_G + g) * 2 + 1] / m - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean = (float)mu;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, bf16* __restrict__ y, int HW, int pix_per_block,
+                int relu) {
+  const int n = blockIdx.y, g = threadIdx.x & 31, row = threadIdx.x >> 5;
+  float mean, rstd;
+  mean_rstd(stats, n, g, HW, eps, mean, rstd);
+  float ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ga[j] = gamma[g * 8 + j] * rstd; be[j] = beta[g * 8 + j] - mean * ga[j]; }
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + (size_t)n * HW * GN_G;
+  uint4* yv = reinterpret_cast<uint4*>(y) + (size_t)n * HW * GN_G;
+  for (int p = p0 + row; p < p1; p += GN_ROWS) {
+    float f[8];
+    unpack8(__ldg(xv + (size_t)p * GN_G + g), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], ga[j], be[j]);
+      if (relu) f[j] = fmaxf(f[j], 0.f);
+    }
+    yv[(size_t)p * GN_G + g] = pack8(f);
+  }
+}
+
+// pass 1 of backward: per-(n, group) sums s1 = sum g*gamma, s2 = sum g*gamma*xhat; per-channel dgamma/dbeta
+__global__ void __launch_bounds__(256)
+gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const double* __restrict__ stats,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                     double* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int HW,
+                     int pix_per_block, int relu) {
+  const int n = blockIdx.y, g = threadIdx.x & 31, row = threadIdx.x >> 5;
+  float mean, rstd;
+  mean_rstd(stats, n, g, HW, eps, mean, rstd);
+  float ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ga[j] = gamma[g * 8 + j]; be[j] = beta[g * 8 + j]; }
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + (size_t)n * HW * GN_G;
+  const uint4* dv = reinterpret_cast<const uint4*>(dy) + (size_t)n * HW * GN_G;
+  float dg[8], db[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { dg[j] = 0.f; db[j] = 0.f; }
+  for (int p = p0 + row; p < p1; p += GN_ROWS) {
+    float f[8], d[8];
+    unpack8(__ldg(xv + (size_t)p * GN_G + g), f);
+    unpack8(__ldg(dv + (size_t)p * GN_G + g), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (f[j] - mean) * rstd;
+      float gj = d[j];
+      if (relu && !(fmaf(xh, ga[j], be[j]) > 0.f)) gj = 0.f;
+      dg[j] = fmaf(gj, xh, dg[j]);
+      db[j] += gj;
+      const float gg = gj * ga[j];
+      s1 += gg;
+      s2 = fmaf(gg, xh, s2);
+    }
+  }
+  __shared__ float red[GN_ROWS][GN_G][18];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[row][g][j] = dg[j]; red[row][g][8 + j] = db[j]; }
+  red[row][g][16] = s1;
+  red[row][g][17] = s2;
+  __syncthreads();
+  if (row == 0) {
+    float acc[18];
+#pragma unroll
+    for (int j = 0; j < 18; ++j) acc[j] = 0.f;
+    for (int k = 0; k < GN_ROWS; ++k)
+#pragma unroll
+      for (int j = 0; j < 18; ++j) acc[j] += red[k][g][j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(dgamma + g * 8 + j, acc[j]);
+      atomicAdd(dbeta + g * 8 + j, acc[8 + j]);
+    }
+    atomicAdd(ws + ((size_t)n * GN_G + g) * 2, (double)acc[16]);
+    atomicAdd(ws + ((size_t)n * GN_G + g) * 2 + 1, (double)acc[17]);
+  }
+}
+
+// pass 2: dx = rstd * (g*gamma - s1/m - xhat*s2/m)
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const double* __restrict__ stats,
+                    const double* __restrict__ ws, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float eps, bf16* __restrict__ dx, int HW, int pix_per_block, int relu) {
+  const int n = blockIdx.y, g = threadIdx.x & 31, row = threadIdx.x >> 5;
+  float mean, rstd;
+  mean_rstd(stats, n, g, HW, eps, mean, rstd);
+  const double m = (double)HW * 8.0;
+  const float a1 = (float)(ws[((size_t)n * GN_G + g) * 2] / m);
+  const float a2 = (float)(ws[((size_t)n * GN_G + g) * 2 + 1] / m);
+  float ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ga[j] = gamma[g * 8 + j]; be[j] = beta[g * 8 + j]; }
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + (size_t)n * HW * GN_G;
+  const uint4* dv = reinterpret_cast<const uint4*>(dy) + (size_t)n * HW * GN_G;
+  uint4* ov = reinterpret_cast<uint4*>(dx) + (size_t)n * HW * GN_G;
+  for (int p = p0 + row; p < p1; p += GN_ROWS) {
+    float f[8], d[8];
+    unpack8(__ldg(xv + (size_t)p * GN_G + g), f);
+    unpack8(__ldg(dv + (size_t)p * GN_G + g), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (f[j] - mean) * rstd;
+      float gj = d[j];
+      if (relu && !(fmaf(xh, ga[j], be[j]) > 0.f)) gj = 0.f;
+      f[j] = rstd * (gj * ga[j] - a1 - xh * a2);
+    }
+    ov[(size_t)p * GN_G + g] = pack8(f);
+  }
+}
+
+inline int pix_per_block(int HW, int N) {
+  // aim for ~148*4 blocks in total, at least 64 pixels each
+  int blocks_per_img = (148 * 4 + N - 1) / N;
+  int ppb = (HW + blocks_per_img - 1) / blocks_per_img;
+  if (ppb < 64) ppb = 64;
+  return (ppb + GN_ROWS - 1) / GN_ROWS * GN_ROWS;
+}
+}  // namespace
+
+#define STREAM static_cast<cudaStream_t>(stream)
+
+// stats: double[N*32*2] workspace owned by the caller (kept for backward).
+extern "C" int ut2_groupnorm_relu_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y,
+                                      double* stats, int N, int HW, int C, int G, int relu, void* stream) {
+  if (C != 256 || G != 32) return ut2_fail(-2, "groupnorm: only GroupNorm(32, 256) is supported");
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * N * GN_G * 2, STREAM);
+  if (e != cudaSuccess) return ut2_fail((int)e, "groupnorm: memset failed");
+  const int ppb = pix_per_block(HW, N);
+  dim3 grid((HW + ppb - 1) / ppb, N);
+  gn_stats_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(x), stats, HW, ppb);
+  gn_apply_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(x), stats, gamma, beta, eps,
+                                            static_cast<bf16*>(y), HW, ppb, relu);
+  return ut2_check_launch("groupnorm_fwd");
+}
+
+// ws: double[N*32*2] scratch; dgamma/dbeta are accumulated (+=) in fp32.
+extern "C" int ut2_groupnorm_relu_bwd(const void* dy, const void* x, const double* stats, const float* gamma,
+                                      const float* beta, float eps, void* dx, float* dgamma, float* dbeta,
+                                      double* ws, int N, int HW, int C, int G, int relu, void* stream) {
+  if (C != 256 || G != 32) return ut2_fail(-2, "groupnorm: only GroupNorm(32, 256) is supported");
+  cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * N * GN_G * 2, STREAM);
+  if (e != cudaSuccess) return ut2_fail((int)e, "groupnorm: memset failed");
+  const int ppb = pix_per_block(HW, N);
+  dim3 grid((HW + ppb - 1) / ppb, N);
+  gn_bwd_reduce_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats, gamma,
+                                                 beta, eps, ws, dgamma, dbeta, HW, ppb, relu);
+  gn_bwd_apply_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats, ws, gamma,
+                                                beta, eps, static_cast<bf16*>(dx), HW, ppb, relu);
+  return ut2_check_launch("groupnorm_bwd");
+}

@@ -1,0 +1,115 @@
+// Flat-arena optimiser kernels: EMA teacher update, SGD-momentum step (+ grad zeroing) and the
+// table-driven bf16 weight packer that refreshes every conv's tensor-core operands in one launch.
+//
+// Reference: ubteacher/engine/trainer.py:468-486 (_update_teacher_model: new = s*(1-k) + t*k over the whole
+// state_dict), :422-429 (zero_grad / backward / optimizer.step with [D2]-built torch.optim.SGD).
+// Algorithmic bytes: EMA 12 B/element (read s, read t, write t); SGD 20 B/element (p, g, buf read; p, buf
+// write) + 4 B when the gradient is zeroed in the same pass.
+#include "ut2_internal.h"
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace {
+typedef __nv_bfloat16 bf16;
+
+// bit-exact with torch: both products rounded to fp32, then one rounded add (no FMA contraction)
+__global__ void __launch_bounds__(256)
+ema_kernel(const float4* __restrict__ s, float4* __restrict__ t, size_t n4, const float* __restrict__ s_tail,
+           float* __restrict__ t_tail, int tail, float a, float b) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 sv = __ldg(s + i);
+    float4 tv = t[i];
+    tv.x = __fadd_rn(__fmul_rn(sv.x, a), __fmul_rn(tv.x, b));
+    tv.y = __fadd_rn(__fmul_rn(sv.y, a), __fmul_rn(tv.y, b));
+    tv.z = __fadd_rn(__fmul_rn(sv.z, a), __fmul_rn(tv.z, b));
+    tv.w = __fadd_rn(__fmul_rn(sv.w, a), __fmul_rn(tv.w, b));
+    t[i] = tv;
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail)
+    t_tail[threadIdx.x] = __fadd_rn(__fmul_rn(s_tail[threadIdx.x], a), __fmul_rn(t_tail[threadIdx.x], b));
+}
+
+// torch.optim.SGD(momentum, weight_decay, dampening=0, nesterov=False):
+//   g' = g + wd*p ; buf = first ? g' : mom*buf + g' ; p -= lr*buf ; (optionally g = 0)
+__global__ void __launch_bounds__(256)
+sgd_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf, size_t n, float lr, float mom,
+           float wd, int first, int zero_grad, float gscale) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float pv = p[i];
+    const float gv = g[i] * gscale + wd * pv;
+    const float bv = first ? gv : mom * buf[i] + gv;
+    buf[i] = bv;
+    p[i] = pv - lr * bv;
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+
+struct PackDesc {          // one conv weight: master fp32 [Cout, R, S, Cin] (channels-last physical layout)
+  long long src;           // float offset in the parameter arena
+  long long wf;            // bf16 offset of the forward operand [rows, R, S, Cin] in the pack arena, or -1
+  long long wt;            // bf16 offset of the dgrad operand [Cin, R, S, CoutT] (flipped taps), or -1
+  long long begin;         // prefix sum of element counts (begin of this descriptor)
+  int Cout, Cin, R, S, CoutT, pad;
+};
+
+__global__ void __launch_bounds__(256)
+pack_batched_kernel(const PackDesc* __restrict__ descs, int num, long long total, const float* __restrict__ arena,
+                    bf16* __restrict__ packed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = num - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (descs[mid].begin <= i) lo = mid; else hi = mid - 1;
+    }
+    const PackDesc d = descs[lo];
+    const long long e = i - d.begin;
+    const int c = (int)(e % d.Cin);
+    long long t = e / d.Cin;
+    const int s = (int)(t % d.S); t /= d.S;
+    const int r = (int)(t % d.R);
+    const int n = (int)(t / d.R);
+    const bf16 v = __float2bfloat16_rn(arena[d.src + e]);
+    if (d.wf >= 0) packed[d.wf + e] = v;
+    if (d.wt >= 0)
+      packed[d.wt + (((long long)c * d.R + (d.R - 1 - r)) * d.S + (d.S - 1 - s)) * d.CoutT + n] = v;
+  }
+}
+
+inline int grid_for(size_t n) {
+  size_t g = (n + 255) / 256;
+  const size_t cap = 148 * 16;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+}  // namespace
+
+#define STREAM static_cast<cudaStream_t>(stream)
+
+extern "C" int ut2_ema_update(const float* student, float* teacher, long long n, double keep_rate, void* stream) {
+  if (n <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(student) | reinterpret_cast<uintptr_t>(teacher)) & 15)
+    return ut2_fail(-2, "ema: arenas must be 16-byte aligned");
+  const float a = (float)(1.0 - keep_rate), b = (float)keep_rate;
+  const size_t n4 = (size_t)n / 4;
+  const int tail = (int)(n - (long long)n4 * 4);
+  ema_kernel<<<grid_for(n4), 256, 0, STREAM>>>(reinterpret_cast<const float4*>(student), reinterpret_cast<float4*>(teacher),
+                                               n4, student + n4 * 4, teacher + n4 * 4, tail, a, b);
+  return ut2_check_launch("ema_update");
+}
+
+extern "C" int ut2_sgd_step(float* p, float* g, float* buf, long long n, float lr, float momentum, float weight_decay,
+                            int first_step, int zero_grad, float grad_scale, void* stream) {
+  if (n <= 0) return 0;
+  sgd_kernel<<<grid_for(n), 256, 0, STREAM>>>(p, g, buf, (size_t)n, lr, momentum, weight_decay, first_step, zero_grad,
+                                              grad_scale);
+  return ut2_check_launch("sgd_step");
+}
+
+// descs: device array of `num` 64-byte records {src, wf, wt, begin, Cout, Cin, R, S, CoutT, pad}.
+extern "C" int ut2_pack_conv_weights_batched(const void* descs, int num, long long total, const float* arena,
+                                             void* packed, void* stream) {
+  if (num <= 0 || total <= 0) return 0;
+  pack_batched_kernel<<<grid_for(total), 256, 0, STREAM>>>(static_cast<const PackDesc*>(descs), num, total, arena,
+                                                           static_cast<bf16*>(packed));
+  return ut2_check_launch("pack_conv_weights_batched");
+}

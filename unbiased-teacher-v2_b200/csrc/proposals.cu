@@ -1,0 +1,502 @@
+// Dense FCOS outputs -> proposals: threshold-compact, per-level top-k (radix select), box decode,
+// batched multi-class NMS (bit-exact coordinate trick), post-NMS top-k, and the pseudo-label
+// threshold-scatter. Everything stays on the device: variable-length results are fixed-capacity
+// buffers + device counters, there is no host synchronisation.
+//
+// Reference (paths under /root/reference/ubteacher):
+//   modeling/fcos/fcos_outputs.py:1046-1132 predict_proposals, :1134-1298 forward_for_single_feature_map,
+//   :1300-1320 select_over_all_levels; layers/ml_nms.py:8-31 -> [D2] batched_nms -> [tv] nms;
+//   modeling/pseudo_generator.py:39-131 (process_pseudo_label / threshold_bbox / threshold_cls_ctr_bbox)
+//
+// Tie rule (the reference leaves it to torch.topk(sorted=False) / sort): equal scores are ordered by the
+// canonical index (level, h, w, class) ascending, i.e. the order torch.nonzero() produces.
+#include "ut2_internal.h"
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace {
+typedef __nv_bfloat16 bf16;
+constexpr int MAXL = 8;
+
+struct Levels {
+  int num;
+  int H[MAXL], W[MAXL], stride[MAXL];
+  int off[MAXL + 1];
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ void locate(const Levels& lv, int N, long long p, int& l, int& img, int& hw) {
+  l = 0;
+#pragma unroll
+  for (int i = 1; i < MAXL; ++i)
+    if (i < lv.num && p >= (long long)lv.off[i] * N) l = i;
+  const long long r = p - (long long)lv.off[l] * N;
+  const int HW = lv.H[l] * lv.W[l];
+  img = (int)(r / HW);
+  hw = (int)(r - (long long)img * HW);
+}
+
+// ---------------------------------------------------------------- 1. threshold + collect
+// method: 0 = cls, 1 = cls_n_ctr, 2 = cls_n_loc. Candidate mask is always sigmoid(logit) > thr.
+__global__ void __launch_bounds__(256)
+collect_kernel(Levels lv, int N, int C, const bf16* __restrict__ cls_out, const bf16* __restrict__ box_out, int ld,
+               int method, float thr, float* __restrict__ cand_key, int* __restrict__ cand_idx,
+               int* __restrict__ cand_cnt) {
+  const long long P = (long long)lv.off[lv.num] * N;
+  const long long total = P * (C / 2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / (C / 2);
+    const int c = (int)(i - p * (C / 2)) * 2;
+    const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(cls_out + p * ld + c));
+    const float pr[2] = {sigmoidf_(__uint_as_float(u << 16)), sigmoidf_(__uint_as_float(u & 0xFFFF0000u))};
+    if (!(pr[0] > thr) && !(pr[1] > thr)) continue;
+    int l, img, hw;
+    locate(lv, N, p, l, img, hw);
+    float q = 1.f;
+    if (method == 1) {
+      q = sigmoidf_(__bfloat162float(box_out[p * ld + 72]));
+    } else if (method == 2) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s += 1.f - sigmoidf_(__bfloat162float(box_out[p * ld + 68 + k]));
+      q = s / 4.f;
+    }
+    const long long base = ((long long)lv.off[l] * N + (long long)img * lv.H[l] * lv.W[l]) * C;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (pr[k] > thr) {
+        const int slot = atomicAdd(cand_cnt + img * lv.num + l, 1);
+        cand_key[base + slot] = method == 0 ? pr[k] : __fmul_rn(pr[k], q);
+        cand_idx[base + slot] = hw * C + c + k;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- 2. per-(image, level) top-k
+__global__ void __launch_bounds__(1024)
+topk_kernel(Levels lv, int N, int C, int K, const float* __restrict__ cand_key, const int* __restrict__ cand_idx,
+            const int* __restrict__ cand_cnt, float* __restrict__ sel_key, int* __restrict__ sel_idx,
+            int* __restrict__ sel_cnt) {
+  const int l = blockIdx.x, img = blockIdx.y;
+  const int n = cand_cnt[img * lv.num + l];
+  const long long base = ((long long)lv.off[l] * N + (long long)img * lv.H[l] * lv.W[l]) * C;
+  const float* key = cand_key + base;
+  const int* idx = cand_idx + base;
+  float* okey = sel_key + ((size_t)img * lv.num + l) * K;
+  int* oidx = sel_idx + ((size_t)img * lv.num + l) * K;
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int s_prefix, s_need, s_cnt;
+  if (n <= K) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { okey[i] = key[i]; oidx[i] = idx[i]; }
+    if (threadIdx.x == 0) sel_cnt[img * lv.num + l] = n;
+    return;
+  }
+  // radix select on the (positive) float bits: find T with count(key > T) < K <= count(key >= T)
+  unsigned int prefix = 0, mask = 0, need = K;
+  for (int pass = 3; pass >= 0; --pass) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned int k = __float_as_uint(key[i]);
+      if ((k & mask) == prefix) atomicAdd(&hist[(k >> (8 * pass)) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int cum = 0;
+      int b = 255;
+      for (; b > 0; --b) {
+        if (cum + hist[b] >= need) break;
+        cum += hist[b];
+      }
+      s_prefix = prefix | ((unsigned int)b << (8 * pass));
+      s_need = need - cum;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    need = s_need;
+    mask |= 0xFFu << (8 * pass);
+    __syncthreads();
+  }
+  const unsigned int T = prefix;      // `need` of the elements with key == T are taken, smallest idx first
+  unsigned int prefix2 = 0, mask2 = 0, need2 = need;
+  for (int pass = 2; pass >= 0; --pass) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      if (__float_as_uint(key[i]) != T) continue;
+      const unsigned int k = (unsigned int)idx[i];
+      if ((k & mask2) == prefix2) atomicAdd(&hist[(k >> (8 * pass)) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int cum = 0;
+      int b = 0;
+      for (; b < 255; ++b) {
+        if (cum + hist[b] >= need2) break;
+        cum += hist[b];
+      }
+      s_prefix = prefix2 | ((unsigned int)b << (8 * pass));
+      s_need = need2 - cum;
+    }
+    __syncthreads();
+    prefix2 = s_prefix;
+    need2 = s_need;
+    mask2 |= 0xFFu << (8 * pass);
+    __syncthreads();
+  }
+  const unsigned int idxT = prefix2;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned int k = __float_as_uint(key[i]);
+    const unsigned int id = (unsigned int)idx[i];
+    if (k > T || (k == T && id <= idxT)) {
+      const unsigned int slot = atomicAdd(&s_cnt, 1u);
+      if (slot < (unsigned int)K) { okey[slot] = key[i]; oidx[slot] = (int)id; }
+    }
+  }
+  if (threadIdx.x == 0) sel_cnt[img * lv.num + l] = K;
+}
+
+// ---------------------------------------------------------------- 3. decode selected candidates
+// det layout per image: M = num_levels * K slots; det_box [N, M, 4], det_score [N, M], det_canon [N, M]
+// (canon = (level_off + hw) * C + class), det_cnt [N].
+__global__ void __launch_bounds__(256)
+decode_kernel(Levels lv, int N, int C, int K, const float* __restrict__ sel_key, const int* __restrict__ sel_idx,
+              const int* __restrict__ sel_cnt, const bf16* __restrict__ box_out, int ld, const float* __restrict__ scales,
+              int sqrt_score, float* __restrict__ det_box, float* __restrict__ det_score, int* __restrict__ det_canon,
+              int* __restrict__ det_cnt) {
+  const int img = blockIdx.y;
+  const int M = lv.num * K;
+  int pre[MAXL + 1];
+  pre[0] = 0;
+  for (int l = 0; l < lv.num; ++l) pre[l + 1] = pre[l] + sel_cnt[img * lv.num + l];
+  if (blockIdx.x == 0 && threadIdx.x == 0) det_cnt[img] = pre[lv.num];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= pre[lv.num]) return;
+  int l = 0;
+  for (int i = 1; i < lv.num; ++i)
+    if (j >= pre[i]) l = i;
+  const int s = j - pre[l];
+  const float key = sel_key[((size_t)img * lv.num + l) * K + s];
+  const int id = sel_idx[((size_t)img * lv.num + l) * K + s];
+  const int hw = id / C, c = id - hw * C;
+  const int h = hw / lv.W[l], w = hw - h * lv.W[l];
+  const float x = (float)(w * lv.stride[l]) + (float)(lv.stride[l] / 2);
+  const float y = (float)(h * lv.stride[l]) + (float)(lv.stride[l] / 2);
+  const long long p = (long long)lv.off[l] * N + (long long)img * lv.H[l] * lv.W[l] + hw;
+  const bf16* row = box_out + p * ld;
+  const float sc = scales[l];
+  float d[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float mx = -3.0e38f;
+    for (int i = 0; i < 17; ++i) mx = fmaxf(mx, sc * __bfloat162float(row[k * 17 + i]));
+    float den = 0.f, num = 0.f;
+    for (int i = 0; i < 17; ++i) {
+      const float e = expf(sc * __bfloat162float(row[k * 17 + i]) - mx);
+      den += e;
+      num += e * (float)i;
+    }
+    d[k] = __fmul_rn(num / den, (float)lv.stride[l]);
+  }
+  float* b = det_box + ((size_t)img * M + j) * 4;
+  b[0] = x - d[0]; b[1] = y - d[1]; b[2] = x + d[2]; b[3] = y + d[3];
+  det_score[(size_t)img * M + j] = sqrt_score ? __fsqrt_rn(key) : key;
+  det_canon[(size_t)img * M + j] = (lv.off[l] + hw) * C + c;
+}
+
+// ---------------------------------------------------------------- 4. NMS
+constexpr int SORT_CAP = 8192;
+
+// Sort one image's detections by (score desc, canon asc); emit order[] and the boxes used for the IoU test
+// (coordinate trick: box + class * (max_coord + 1), all in fp32 exactly like torchvision).
+__global__ void __launch_bounds__(1024)
+nms_sort_kernel(int M, int C, const float* __restrict__ det_box, const float* __restrict__ det_score,
+                const int* __restrict__ det_canon, const int* __restrict__ det_cnt, int class_aware,
+                int* __restrict__ order, float* __restrict__ nms_box) {
+  extern __shared__ unsigned long long skey[];                 // SORT_CAP keys
+  unsigned short* sval = reinterpret_cast<unsigned short*>(skey + SORT_CAP);
+  __shared__ float smax[32];
+  const int img = blockIdx.x;
+  const int n = min(det_cnt[img], SORT_CAP);
+  const float* box = det_box + (size_t)img * M * 4;
+  float mx = -3.0e38f;
+  for (int i = threadIdx.x; i < n * 4; i += blockDim.x) mx = fmaxf(mx, box[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
+  for (int i = threadIdx.x; i < SORT_CAP; i += blockDim.x) {
+    unsigned long long k = ~0ull;
+    if (i < n) {
+      const unsigned int sb = __float_as_uint(det_score[(size_t)img * M + i]);
+      k = ((unsigned long long)(0xFFFFFFFFu - sb) << 32) | (unsigned int)det_canon[(size_t)img * M + i];
+    }
+    skey[i] = k;
+    sval[i] = (unsigned short)i;
+  }
+  __syncthreads();
+  mx = smax[0];
+  for (int i = 1; i < 32; ++i) mx = fmaxf(mx, smax[i]);
+  for (int k = 2; k <= SORT_CAP; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < SORT_CAP; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = (i & k) == 0;
+          const unsigned long long a = skey[i], b = skey[ixj];
+          if ((a > b) == up) {
+            skey[i] = b; skey[ixj] = a;
+            const unsigned short t = sval[i]; sval[i] = sval[ixj]; sval[ixj] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const float offs1 = mx + 1.0f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int src = sval[i];
+    order[(size_t)img * M + i] = src;
+    const int cls = det_canon[(size_t)img * M + src] % C;
+    const float off = class_aware ? __fmul_rn((float)cls, offs1) : 0.f;
+    const float4 b = reinterpret_cast<const float4*>(box)[src];
+    reinterpret_cast<float4*>(nms_box)[(size_t)img * M + i] = make_float4(b.x + off, b.y + off, b.z + off, b.w + off);
+  }
+}
+
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float width = fmaxf(right - left, 0.f), height = fmaxf(bottom - top, 0.f);
+  const float inter = __fmul_rn(width, height);
+  const float sa = __fmul_rn(a.z - a.x, a.w - a.y);
+  const float sb = __fmul_rn(b.z - b.x, b.w - b.y);
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter)) > thr;
+}
+
+// mask[img][i][cb] bit j: sorted box i suppresses sorted box cb*64+j (only j > i matters)
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(int M, int MW, const float* __restrict__ nms_box, const int* __restrict__ det_cnt, float thr,
+                unsigned long long* __restrict__ mask) {
+  const int img = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
+  const int n = min(det_cnt[img], SORT_CAP);
+  if (rb * 64 >= n || cb * 64 >= n || cb < rb) return;
+  __shared__ float4 cbox[64];
+  const float4* bx = reinterpret_cast<const float4*>(nms_box) + (size_t)img * M;
+  const int cn = min(64, n - cb * 64);
+  if (threadIdx.x < cn) cbox[threadIdx.x] = bx[cb * 64 + threadIdx.x];
+  __syncthreads();
+  const int i = rb * 64 + threadIdx.x;
+  if (i < n) {
+    const float4 a = bx[i];
+    unsigned long long bits = 0;
+    const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+    for (int j = start; j < cn; ++j)
+      if (iou_gt(a, cbox[j], thr)) bits |= 1ull << j;
+    mask[((size_t)img * M + i) * MW + cb] = bits;
+  }
+}
+
+// serial scan + post-NMS top-k + gather of the per-detection fields the pseudo-labeler needs
+__global__ void __launch_bounds__(128)
+nms_scan_kernel(Levels lv, int N, int C, int M, int MW, int post_topk, int OUT_CAP,
+                const unsigned long long* __restrict__ mask, const int* __restrict__ order,
+                const float* __restrict__ det_box, const float* __restrict__ det_score,
+                const int* __restrict__ det_canon, const int* __restrict__ det_cnt, const bf16* __restrict__ cls_out,
+                const bf16* __restrict__ box_out, int ld, float* __restrict__ out_box, float* __restrict__ out_score,
+                long long* __restrict__ out_cls, float* __restrict__ out_ctr, float* __restrict__ out_conf,
+                float* __restrict__ out_std, float* __restrict__ out_loc, long long* __restrict__ out_lvl,
+                int* __restrict__ out_cnt) {
+  extern __shared__ unsigned long long remv[];       // MW words
+  __shared__ int kept[1024];
+  __shared__ int s_nkeep;
+  const int img = blockIdx.x;
+  const int n = min(det_cnt[img], SORT_CAP);
+  const int nw = (n + 63) / 64;
+  for (int i = threadIdx.x; i < MW; i += blockDim.x) remv[i] = 0;
+  if (threadIdx.x == 0) s_nkeep = 0;
+  __syncthreads();
+  // Only the first `limit` survivors can matter: post-NMS keeps scores >= the post_topk-th best survivor,
+  // ties included; stop once a survivor with a strictly smaller score than the post_topk-th appears.
+  const float* score = det_score + (size_t)img * M;
+  const int* ord = order + (size_t)img * M;
+  int nkeep = 0;
+  float kth = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const bool dead = (remv[i >> 6] >> (i & 63)) & 1ull;     // uniform across the block
+    if (!dead) {
+      const float sc = score[ord[i]];
+      if (post_topk > 0 && nkeep >= post_topk) {
+        if (nkeep == post_topk) kth = score[ord[kept[post_topk - 1]]];
+        if (sc < kth || nkeep >= 1024 || nkeep >= OUT_CAP) break;
+      }
+      if (threadIdx.x == 0) kept[nkeep] = i;
+      ++nkeep;
+      const unsigned long long* mrow = mask + ((size_t)img * M + i) * MW;
+      for (int w = (i >> 6) + threadIdx.x; w < nw; w += blockDim.x) remv[w] |= mrow[w];
+    }
+    __syncthreads();
+  }
+  if (nkeep > OUT_CAP) nkeep = OUT_CAP;
+  __syncthreads();
+  if (threadIdx.x == 0) out_cnt[img] = nkeep;
+  for (int k = threadIdx.x; k < nkeep; k += blockDim.x) {
+    const int src = ord[kept[k]];
+    const int canon = det_canon[(size_t)img * M + src];
+    const int cls = canon % C;
+    const int gl = canon / C;               // level_off + hw
+    int l = 0;
+    for (int i = 1; i < lv.num; ++i)
+      if (gl >= lv.off[i]) l = i;
+    const int hw = gl - lv.off[l];
+    const int h = hw / lv.W[l], w = hw - h * lv.W[l];
+    const long long p = (long long)lv.off[l] * N + (long long)img * lv.H[l] * lv.W[l] + hw;
+    const size_t o = (size_t)img * OUT_CAP + k;
+    reinterpret_cast<float4*>(out_box)[o] = reinterpret_cast<const float4*>(det_box)[(size_t)img * M + src];
+    out_score[o] = det_score[(size_t)img * M + src];
+    out_cls[o] = cls;
+    out_lvl[o] = l;
+    out_ctr[o] = sigmoidf_(__bfloat162float(box_out[p * ld + 72]));
+    out_conf[o] = sigmoidf_(__bfloat162float(cls_out[p * ld + cls]));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) out_std[o * 4 + q] = __bfloat162float(box_out[p * ld + 68 + q]);
+    out_loc[o * 2] = (float)(w * lv.stride[l]) + (float)(lv.stride[l] / 2);
+    out_loc[o * 2 + 1] = (float)(h * lv.stride[l]) + (float)(lv.stride[l] / 2);
+  }
+}
+
+// ---------------------------------------------------------------- 5. pseudo-label threshold-scatter
+// mode 0: valid = score > thr0 ; mode 1: valid = cls_confid > thr0 && centerness > thr1. Order preserving.
+__global__ void __launch_bounds__(32)
+threshold_scatter_kernel(int CAP, int mode, float thr0, float thr1, const int* __restrict__ in_cnt,
+                         const float* __restrict__ box, const float* __restrict__ score, const long long* __restrict__ cls,
+                         const float* __restrict__ ctr, const float* __restrict__ conf, const float* __restrict__ stdv,
+                         int* __restrict__ out_cnt, float* __restrict__ obox, float* __restrict__ oscore,
+                         long long* __restrict__ ocls, float* __restrict__ octr, float* __restrict__ oconf,
+                         float* __restrict__ ostd) {
+  const int img = blockIdx.x, lane = threadIdx.x;
+  const int n = min(in_cnt[img], CAP);
+  int base = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    bool v = false;
+    if (i < n) {
+      const size_t s = (size_t)img * CAP + i;
+      v = mode == 0 ? (score[s] > thr0) : (conf[s] > thr0 && ctr[s] > thr1);
+    }
+    const unsigned int b = __ballot_sync(0xffffffffu, v);
+    if (v) {
+      const size_t s = (size_t)img * CAP + i;
+      const size_t d = (size_t)img * CAP + base + __popc(b & ((1u << lane) - 1));
+      reinterpret_cast<float4*>(obox)[d] = reinterpret_cast<const float4*>(box)[s];
+      oscore[d] = score[s]; ocls[d] = cls[s]; octr[d] = ctr[s]; oconf[d] = conf[s];
+      reinterpret_cast<float4*>(ostd)[d] = reinterpret_cast<const float4*>(stdv)[s];
+    }
+    base += __popc(b);
+  }
+  if (lane == 0) out_cnt[img] = base;
+}
+
+int fill_levels(Levels& lv, int num_levels, const int* hw, const int* strides) {
+  if (num_levels < 1 || num_levels > MAXL) return -1;
+  lv.num = num_levels;
+  lv.off[0] = 0;
+  for (int i = 0; i < num_levels; ++i) {
+    lv.H[i] = hw[2 * i]; lv.W[i] = hw[2 * i + 1]; lv.stride[i] = strides[i];
+    lv.off[i + 1] = lv.off[i] + hw[2 * i] * hw[2 * i + 1];
+  }
+  return 0;
+}
+}  // namespace
+
+#define STREAM static_cast<cudaStream_t>(stream)
+
+// Workspace (bytes) for ut2_fcos_predict_proposals with N images, L locations/image, C classes, K pre-NMS top-k.
+extern "C" long long ut2_fcos_predict_workspace_bytes(int num_levels, int N, long long L, int C, int K) {
+  const long long M = (long long)num_levels * K, MW = (M + 63) / 64;
+  long long b = 0;
+  b += N * L * C * 4 * 2;              // cand_key, cand_idx
+  b += (long long)N * num_levels * 4 * 2;   // cand_cnt, sel_cnt
+  b += N * M * 4 * 2;                  // sel_key, sel_idx
+  b += N * M * (16 + 4 + 4);           // det_box, det_score, det_canon
+  b += N * 4;                          // det_cnt
+  b += N * M * 4 + N * M * 16;         // order, nms_box
+  b += N * M * MW * 8;                 // mask
+  return b + 4096;
+}
+
+// One call = predict_proposals for a batch: dense head outputs -> <= OUT_CAP detections per image.
+// method: 0 "cls", 1 "cls_n_ctr", 2 "cls_n_loc". All out_* are [N, OUT_CAP(, k)], out_cnt [N].
+extern "C" int ut2_fcos_predict_proposals(int num_levels, const int* hw, const int* strides, int N, int C,
+                                          const void* cls_out, const void* box_out, int ld, const float* scales,
+                                          int method, float pre_thr, int pre_topk, float nms_thr, int post_topk,
+                                          int out_cap, void* workspace, long long workspace_bytes, float* out_box,
+                                          float* out_score, long long* out_cls, float* out_ctr, float* out_conf,
+                                          float* out_std, float* out_loc, long long* out_lvl, int* out_cnt,
+                                          void* stream) {
+  Levels lv;
+  if (fill_levels(lv, num_levels, hw, strides)) return ut2_fail(-2, "predict: bad level count");
+  if (method < 0 || method > 2) return ut2_fail(-3, "predict: undefined nms criteria");
+  const long long L = lv.off[lv.num];
+  const int K = pre_topk;
+  const long long M = (long long)num_levels * K, MW = (M + 63) / 64;
+  if (M > SORT_CAP) return ut2_fail(-4, "predict: num_levels * pre_topk exceeds the in-CTA sort capacity (8192)");
+  if (out_cap > 1024) return ut2_fail(-4, "predict: out_cap > 1024");
+  if (ut2_fcos_predict_workspace_bytes(num_levels, N, L, C, K) > workspace_bytes)
+    return ut2_fail(-5, "predict: workspace too small");
+  char* w = static_cast<char*>(workspace);
+  auto take = [&](long long bytes) { char* p = w; w += (bytes + 255) / 256 * 256; return p; };
+  int* cand_cnt = reinterpret_cast<int*>(take((long long)N * num_levels * 4));
+  int* sel_cnt = reinterpret_cast<int*>(take((long long)N * num_levels * 4));
+  int* det_cnt = reinterpret_cast<int*>(take(N * 4));
+  float* cand_key = reinterpret_cast<float*>(take(N * L * C * 4));
+  int* cand_idx = reinterpret_cast<int*>(take(N * L * C * 4));
+  float* sel_key = reinterpret_cast<float*>(take(N * M * 4));
+  int* sel_idx = reinterpret_cast<int*>(take(N * M * 4));
+  float* det_box = reinterpret_cast<float*>(take(N * M * 16));
+  float* det_score = reinterpret_cast<float*>(take(N * M * 4));
+  int* det_canon = reinterpret_cast<int*>(take(N * M * 4));
+  int* order = reinterpret_cast<int*>(take(N * M * 4));
+  float* nms_box = reinterpret_cast<float*>(take(N * M * 16));
+  unsigned long long* mask = reinterpret_cast<unsigned long long*>(take(N * M * MW * 8));
+  if (w - static_cast<char*>(workspace) > workspace_bytes) return ut2_fail(-5, "predict: workspace too small");
+
+  cudaMemsetAsync(cand_cnt, 0, (size_t)N * num_levels * 4, STREAM);
+  const long long total = (long long)N * L * (C / 2);
+  long long g = (total + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  collect_kernel<<<(int)g, 256, 0, STREAM>>>(lv, N, C, static_cast<const bf16*>(cls_out), static_cast<const bf16*>(box_out),
+                                             ld, method, pre_thr, cand_key, cand_idx, cand_cnt);
+  topk_kernel<<<dim3(num_levels, N), 1024, 0, STREAM>>>(lv, N, C, K, cand_key, cand_idx, cand_cnt, sel_key, sel_idx, sel_cnt);
+  decode_kernel<<<dim3((unsigned)((M + 255) / 256), N), 256, 0, STREAM>>>(
+      lv, N, C, K, sel_key, sel_idx, sel_cnt, static_cast<const bf16*>(box_out), ld, scales, method != 0, det_box,
+      det_score, det_canon, det_cnt);
+  const int sort_smem = SORT_CAP * 8 + SORT_CAP * 2;
+  static bool set = false;
+  if (!set) {
+    cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sort_smem);
+    set = true;
+  }
+  nms_sort_kernel<<<N, 1024, sort_smem, STREAM>>>((int)M, C, det_box, det_score, det_canon, det_cnt, 1, order, nms_box);
+  const int nb = (int)((M + 63) / 64);
+  nms_mask_kernel<<<dim3(nb, nb, N), 64, 0, STREAM>>>((int)M, (int)MW, nms_box, det_cnt, nms_thr, mask);
+  nms_scan_kernel<<<N, 128, (size_t)MW * 8, STREAM>>>(lv, N, C, (int)M, (int)MW, post_topk, out_cap, mask, order, det_box,
+                                                      det_score, det_canon, det_cnt, static_cast<const bf16*>(cls_out),
+                                                      static_cast<const bf16*>(box_out), ld, out_box, out_score, out_cls,
+                                                      out_ctr, out_conf, out_std, out_loc, out_lvl, out_cnt);
+  return ut2_check_launch("fcos_predict_proposals");
+}
+
+extern "C" int ut2_threshold_scatter(int N, int cap, int mode, float thr0, float thr1, const int* in_cnt,
+                                     const float* box, const float* score, const long long* cls, const float* ctr,
+                                     const float* conf, const float* stdv, int* out_cnt, float* obox, float* oscore,
+                                     long long* ocls, float* octr, float* oconf, float* ostd, void* stream) {
+  if (N <= 0) return 0;
+  threshold_scatter_kernel<<<N, 32, 0, STREAM>>>(cap, mode, thr0, thr1, in_cnt, box, score, cls, ctr, conf, stdv, out_cnt,
+                                                 obox, oscore, ocls, octr, oconf, ostd);
+  return ut2_check_launch("threshold_scatter");
+}

@@ -44,6 +44,8 @@ def _conv(a):
         return ctypes.c_void_p(0)
     if isinstance(a, torch.Tensor):
         return ctypes.c_void_p(a.data_ptr())
+    if isinstance(a, ctypes.Array):
+        return a
     if isinstance(a, bool):
         return ctypes.c_int(int(a))
     if isinstance(a, f32):

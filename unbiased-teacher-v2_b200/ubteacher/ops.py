@@ -1,0 +1,227 @@
+"""Thin Python wrappers over the C-ABI kernels (include/ut2.h). Tensors are torch CUDA tensors used as
+device-memory handles only; every arithmetic op below is one of our sm_100a kernels."""
+import ctypes
+
+import torch
+
+from . import _C
+from ._C import f32, f64, i64
+
+BF16 = torch.bfloat16
+
+
+def conv_out_hw(H, W, R, S, stride, pad):
+    return (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+
+
+def conv2d(x, w, cout, R, S, stride, pad, scale=None, shift=None, residual=None, relu=False, out=None):
+    """x: [N,H,W,Cin] bf16 NHWC; w: bf16 [>=cout, R, S, Cin]; returns [N,P,Q,cout] bf16."""
+    N, H, W, Cin = x.shape
+    P, Q = conv_out_hw(H, W, R, S, stride, pad)
+    if out is None:
+        out = torch.empty((N, P, Q, cout), dtype=BF16, device=x.device)
+    _C.counted_call("ut2_conv2d_nhwc_bf16_fwd", x, N, H, W, Cin, w, cout, R, S, stride, pad, scale, shift, residual,
+                    int(relu), out)
+    return out
+
+
+def conv2d_wgrad(x, dy, cout, R, S, stride, pad, dw, scale=None):
+    """Accumulates dW (fp32, [cout, R, S, Cin]) += dY^T * im2col(X)."""
+    N, H, W, Cin = x.shape
+    _C.counted_call("ut2_conv2d_nhwc_bf16_wgrad", x, N, H, W, Cin, dy, cout, R, S, stride, pad, scale, dw)
+
+
+def groupnorm_relu_fwd(x, gamma, beta, eps=1e-5, relu=True):
+    N, H, W, C = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty((N, 32, 2), dtype=torch.float64, device=x.device)
+    _C.counted_call("ut2_groupnorm_relu_fwd", x, gamma, beta, f32(eps), y, stats, N, H * W, C, 32, int(relu))
+    _C.launch_count += 1  # two kernels
+    return y, stats
+
+
+def groupnorm_relu_bwd(dy, x, stats, gamma, beta, dgamma, dbeta, eps=1e-5, relu=True):
+    N, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    ws = torch.empty((N, 32, 2), dtype=torch.float64, device=x.device)
+    _C.counted_call("ut2_groupnorm_relu_bwd", dy, x, stats, gamma, beta, f32(eps), dx, dgamma, dbeta, ws, N, H * W, C,
+                    32, int(relu))
+    _C.launch_count += 1
+    return dx
+
+
+def stem_conv(img_u8_chw, w_rsck, scale, shift, mean, std, out_slice, P, Q):
+    _, h, w = img_u8_chw.shape
+    _C.counted_call("ut2_stem_conv_u8", img_u8_chw, h, w, w_rsck, scale, shift, f32(mean[0]), f32(mean[1]),
+                    f32(mean[2]), f32(std[0]), f32(std[1]), f32(std[2]), out_slice, P, Q)
+
+
+def maxpool3x3s2(x):
+    N, H, W, C = x.shape
+    P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((N, P, Q, C), dtype=BF16, device=x.device)
+    _C.counted_call("ut2_maxpool3x3s2_nhwc", x, y, N, H, W, C)
+    return y
+
+
+def upsample2x_add(lat, top):
+    N, H, W, C = lat.shape
+    out = torch.empty_like(lat)
+    _C.counted_call("ut2_upsample2x_add_nhwc", lat, top, out, N, H, W, C)
+    return out
+
+
+def downsample2x_sum(g, addend=None):
+    N, H, W, C = g.shape
+    out = torch.empty((N, H // 2, W // 2, C), dtype=BF16, device=g.device)
+    _C.counted_call("ut2_downsample2x_sum_nhwc", g, addend, out, N, H // 2, W // 2, C)
+    return out
+
+
+def relu_bwd(dy, y, dy2=None):
+    g = torch.empty_like(y)
+    _C.counted_call("ut2_relu_bwd_bf16", dy, dy2, y, g, i64(y.numel()))
+    return g
+
+
+def add_bf16(a, b):
+    out = torch.empty_like(a)
+    _C.counted_call("ut2_add_bf16", a, b, out, i64(a.numel()))
+    return out
+
+
+def zero_stuff_s2(g, H, W, oh=0, ow=0):
+    N, P, Q, C = g.shape
+    out = torch.empty((N, H, W, C), dtype=BF16, device=g.device)
+    _C.counted_call("ut2_zero_stuff_s2_nhwc", g, out, N, P, Q, H, W, C, oh, ow)
+    return out
+
+
+def colsum(g2d, db):
+    M, C = g2d.shape
+    _C.counted_call("ut2_colsum_bf16", g2d, db, M, C)
+
+
+def pack_conv_weight(w_master, wf, wt, cout, cin, R, S, coutT):
+    _C.counted_call("ut2_pack_conv_weight", w_master, wf, wt, cout, cin, R, S, coutT)
+
+
+def ema_update(student_flat, teacher_flat, keep_rate):
+    _C.counted_call("ut2_ema_update", student_flat, teacher_flat, i64(student_flat.numel()), f64(keep_rate))
+
+
+def sgd_step(p, g, buf, lr, momentum, wd, first_step, zero_grad=True, grad_scale=1.0):
+    _C.counted_call("ut2_sgd_step", p, g, buf, i64(p.numel()), f32(lr), f32(momentum), f32(wd), int(first_step),
+                    int(zero_grad), f32(grad_scale))
+
+
+class LevelGeom:
+    """Host-side description of the FPN levels a batch was run on (launch parameters for the loss,
+    target-assignment and proposal kernels)."""
+
+    def __init__(self, hw, strides, sizes_of_interest=None):
+        self.hw = [tuple(x) for x in hw]
+        self.strides = list(strides)
+        self.num = len(self.hw)
+        self.L = sum(h * w for h, w in self.hw)
+        self.c_hw = (ctypes.c_int * (2 * self.num))(*[v for x in self.hw for v in x])
+        self.c_strides = (ctypes.c_int * self.num)(*self.strides)
+        if sizes_of_interest is not None:
+            INF = 100000000.0
+            rng, prev = [], -1.0
+            for s in sizes_of_interest:
+                rng += [prev, float(s)]
+                prev = float(s)
+            rng += [prev, INF]
+            self.c_ranges = (ctypes.c_float * (2 * self.num))(*rng[: 2 * self.num])
+        else:
+            self.c_ranges = None
+        off = [0]
+        for h, w in self.hw:
+            off.append(off[-1] + h * w)
+        self.off = off
+
+
+def fcos_assign_targets(geom, N, boxes, classes, counts, bvar, num_classes=80):
+    """boxes [N,G,4] f32, classes [N,G] i64, counts [N] i32, bvar [N,G,4] f32 or None."""
+    dev = boxes.device
+    P = geom.L * N
+    G = boxes.shape[1]
+    out = {
+        "labels": torch.empty(P, dtype=torch.int64, device=dev),
+        "target_inds": torch.empty(P, dtype=torch.int64, device=dev),
+        "reg_targets": torch.empty((P, 4), dtype=torch.float32, device=dev),
+        "boundary_vars": torch.empty((P, 4), dtype=torch.float32, device=dev),
+        "keep_locations": torch.empty(P, dtype=torch.uint8, device=dev),
+        "norm": torch.empty(2, dtype=torch.float32, device=dev),
+    }
+    _C.counted_call("ut2_fcos_assign_targets", geom.num, geom.c_hw, geom.c_strides, geom.c_ranges, N, G, boxes,
+                    classes, counts, bvar, num_classes, out["labels"], out["target_inds"], out["reg_targets"],
+                    out["boundary_vars"], out["keep_locations"], out["norm"])
+    return out
+
+
+def fcos_loss_fwd(geom, N, cls_out, box_out, scales, tg, mode, alpha, gamma, kl_w, ts_better, ts_cert, world,
+                  num_classes=80):
+    dev = box_out.device
+    acc = torch.empty(8, dtype=torch.float64, device=dev)
+    losses = torch.empty(4, dtype=torch.float32, device=dev)
+    _C.counted_call("ut2_fcos_loss_fwd", geom.num, geom.c_hw, geom.c_strides, N, cls_out, box_out, box_out.shape[-1],
+                    scales, tg["labels"], tg["reg_targets"], tg["boundary_vars"], num_classes, mode, f32(alpha),
+                    f32(gamma), f32(kl_w), f32(ts_better), f32(ts_cert), tg["norm"], f32(world), acc, losses)
+    _C.launch_count += 2 if mode != 2 else 1
+    return losses, acc
+
+
+def fcos_loss_bwd(geom, N, cls_out, box_out, scales, tg, mode, alpha, gamma, kl_w, ts_better, ts_cert, world, acc,
+                  gout, dcls, dbox, dscales, num_classes=80):
+    _C.counted_call("ut2_fcos_loss_bwd", geom.num, geom.c_hw, geom.c_strides, N, cls_out, box_out, box_out.shape[-1],
+                    scales, tg["labels"], tg["reg_targets"], tg["boundary_vars"], num_classes, mode, f32(alpha),
+                    f32(gamma), f32(kl_w), f32(ts_better), f32(ts_cert), tg["norm"], f32(world), acc, gout, dcls, dbox,
+                    dscales)
+    if mode != 2:
+        _C.launch_count += 1
+
+
+_NMS_METHOD = {"cls": 0, "cls_n_ctr": 1, "cls_n_loc": 2}
+
+
+def fcos_predict_proposals(geom, N, cls_out, box_out, scales, method, pre_thr, pre_topk, nms_thr, post_topk,
+                           out_cap=128, num_classes=80):
+    if method not in _NMS_METHOD:
+        raise ValueError("Undefined nms criteria")
+    dev = box_out.device
+    lib = _C.lib()
+    lib.ut2_fcos_predict_workspace_bytes.restype = ctypes.c_longlong
+    wsb = lib.ut2_fcos_predict_workspace_bytes(geom.num, N, ctypes.c_longlong(geom.L), num_classes, pre_topk)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    out = {
+        "pred_boxes": torch.zeros((N, out_cap, 4), dtype=torch.float32, device=dev),
+        "scores": torch.zeros((N, out_cap), dtype=torch.float32, device=dev),
+        "pred_classes": torch.zeros((N, out_cap), dtype=torch.int64, device=dev),
+        "centerness": torch.zeros((N, out_cap), dtype=torch.float32, device=dev),
+        "cls_confid": torch.zeros((N, out_cap), dtype=torch.float32, device=dev),
+        "reg_pred_std": torch.zeros((N, out_cap, 4), dtype=torch.float32, device=dev),
+        "locations": torch.zeros((N, out_cap, 2), dtype=torch.float32, device=dev),
+        "fpn_levels": torch.zeros((N, out_cap), dtype=torch.int64, device=dev),
+        "count": torch.zeros(N, dtype=torch.int32, device=dev),
+    }
+    _C.counted_call("ut2_fcos_predict_proposals", geom.num, geom.c_hw, geom.c_strides, N, num_classes, cls_out, box_out,
+                    box_out.shape[-1], scales, _NMS_METHOD[method], f32(pre_thr), pre_topk, f32(nms_thr), post_topk,
+                    out_cap, ws, i64(wsb), out["pred_boxes"], out["scores"], out["pred_classes"], out["centerness"],
+                    out["cls_confid"], out["reg_pred_std"], out["locations"], out["fpn_levels"], out["count"])
+    _C.launch_count += 5
+    return out
+
+
+def threshold_scatter(dets, mode, thr0, thr1=0.0):
+    """dets: dict from fcos_predict_proposals. Returns the compacted pseudo-label set (same capacity)."""
+    N, cap = dets["scores"].shape
+    out = {k: torch.zeros_like(dets[k]) for k in ["pred_boxes", "scores", "pred_classes", "centerness", "cls_confid",
+                                                  "reg_pred_std"]}
+    out["count"] = torch.zeros_like(dets["count"])
+    _C.counted_call("ut2_threshold_scatter", N, cap, mode, f32(thr0), f32(thr1), dets["count"], dets["pred_boxes"],
+                    dets["scores"], dets["pred_classes"], dets["centerness"], dets["cls_confid"], dets["reg_pred_std"],
+                    out["count"], out["pred_boxes"], out["scores"], out["pred_classes"], out["centerness"],
+                    out["cls_confid"], out["reg_pred_std"])
+    return out
