@@ -36,6 +36,7 @@ CASES = [
     (2, 13, 21, 64, 64, 3, 1, 1),
     (1, 25, 42, 256, 256, 3, 1, 1),
     (3, 9, 11, 128, 512, 1, 1, 0),
+    (2, 13, 21, 80, 256, 3, 1, 1),
     (2, 26, 42, 256, 128, 1, 2, 0),
     (2, 25, 42, 256, 256, 3, 2, 1),
     (2, 13, 21, 256, 80, 3, 1, 1),
@@ -90,7 +91,7 @@ def test_conv_fwd(case):
     Q = (W + 2 * pad - R) // stride + 1
     y = torch.full((N, P, Q, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
     _C.call("ut2_conv2d_nhwc_bf16_fwd", x.cuda(), N, H, W, Cin, w.cuda(), Cout, R, R, stride, pad,
-            None, None, None, 0, y)
+            None, None, None, 0, None, 0, y)
     torch.cuda.synchronize()
     ref = _ref_fwd(x, w, stride, pad)
     torch.testing.assert_close(y.float().cpu(), ref, rtol=RTOL, atol=ATOL)
@@ -107,7 +108,7 @@ def test_conv_fwd_epilogue():
     res = torch.randn(N, H, W, Cout, generator=g).bfloat16()
     y = torch.empty((N, H, W, Cout), dtype=torch.bfloat16, device="cuda")
     _C.call("ut2_conv2d_nhwc_bf16_fwd", x.cuda(), N, H, W, Cin, w.cuda(), Cout, R, R, stride, pad,
-            scale.cuda(), shift.cuda(), res.cuda(), 1, y)
+            scale.cuda(), shift.cuda(), res.cuda(), 0, None, 1, y)
     torch.cuda.synchronize()
     ref = _ref_fwd(x, w, stride, pad, scale, shift, res, True)
     torch.testing.assert_close(y.float().cpu(), ref, rtol=RTOL, atol=ATOL)
@@ -125,7 +126,7 @@ def test_conv_wgrad(case):
     dy = torch.randn(N, P, Q, Cout, generator=g).bfloat16()
     dw = torch.zeros(Cout, R, R, Cin, dtype=torch.float32, device="cuda")
     _C.call("ut2_conv2d_nhwc_bf16_wgrad", x.cuda(), N, H, W, Cin, dy.cuda(), Cout, R, R, stride, pad,
-            None, dw)
+            None, dw, 0)
     torch.cuda.synchronize()
     xr = x.float().permute(0, 3, 1, 2).requires_grad_(False)
     wr = w.float().permute(0, 3, 1, 2).clone().requires_grad_(True)

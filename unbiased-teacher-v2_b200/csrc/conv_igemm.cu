@@ -40,6 +40,8 @@ struct ConvFwdArgs {
   const float* shift;
   const __nv_bfloat16* residual;
   int ldr;
+  int res_up2;                      // residual is [N, P/2, Q/2, Cout]: nearest-2x upsampled on the fly (FPN top-down)
+  const __nv_bfloat16* relu_mask;   // optional [M, Cout]: output zeroed where mask <= 0 (ReLU backward fused in dgrad)
   __nv_bfloat16* out;
 };
 
@@ -63,7 +65,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = a.m_tiles * a.n_tiles;
-  const int c_chunks = a.Cin / BK;
+  const int c_chunks = (a.Cin + BK - 1) / BK;   // a ragged last chunk is zero-filled by TMA (OOB channels)
   const int num_kb = a.R * a.S * c_chunks;
 
   if (warp == 0 && lane == 0) {
@@ -167,8 +169,15 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             for (int i = 0; i < 16; ++i) f[i] += __ldg(a.shift + n0 + i);
           }
           if (a.residual) {
+            size_t rrow = (size_t)m;
+            if (a.res_up2) {
+              const int PQ = a.P * a.Q;
+              const int img = m / PQ, rem = m - img * PQ;
+              const int p = rem / a.Q, q = rem - p * a.Q;
+              rrow = ((size_t)img * (a.P / 2) + (p >> 1)) * (a.Q / 2) + (q >> 1);
+            }
             const uint4* rp =
-                reinterpret_cast<const uint4*>(a.residual + (size_t)m * a.ldr + n0);
+                reinterpret_cast<const uint4*>(a.residual + rrow * a.ldr + n0);
             uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
             const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
@@ -181,6 +190,17 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           if (a.relu) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (a.relu_mask) {
+            const uint4* mp = reinterpret_cast<const uint4*>(a.relu_mask + (size_t)m * a.ldo + n0);
+            uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&mw[i]);
+              if (!(__low2float(h) > 0.f)) f[2 * i] = 0.f;
+              if (!(__high2float(h) > 0.f)) f[2 * i + 1] = 0.f;
+            }
           }
           uint4 o0, o1;
           o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
@@ -221,6 +241,7 @@ struct ConvWgradArgs {
   int kb_total, kb_per_split;
   const float* scale;   // optional per-Cout factor (FrozenBN scale)
   float* dw;            // [Cout, R*S*Cin] fp32, accumulated
+  int cout_store;       // rows >= cout_store are not written (zero-padded fused predictors)
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -313,12 +334,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const size_t K = (size_t)a.R * a.S * a.Cin;
-    const float sc = (a.scale && n < a.Cout) ? __ldg(a.scale + n) : 1.f;
+    const float sc = (a.scale && n < a.cout_store) ? __ldg(a.scale + n) : 1.f;
     for (int c = 0; c < a.block_n; c += 16) {
       uint32_t v[16];
       tmem_ld_32x16(taddr + c, v);
       tmem_ld_wait();
-      if (n < a.Cout) {
+      if (n < a.cout_store) {
         float* dst = a.dw + (size_t)n * K + (size_t)tap * a.Cin + c_tile * a.block_n + c;
 #pragma unroll
         for (int i = 0; i < 16; ++i) atomicAdd(dst + i, __uint_as_float(v[i]) * sc);
@@ -382,9 +403,10 @@ using namespace ut2;
 extern "C" int ut2_conv2d_nhwc_bf16_fwd(const void* x, int N, int H, int W, int Cin, const void* w,
                                         int Cout, int R, int S, int stride, int pad,
                                         const float* scale, const float* shift,
-                                        const void* residual, int relu, void* y, void* stream) {
+                                        const void* residual, int res_up2, const void* relu_mask, int relu,
+                                        void* y, void* stream) {
   if (!x || !w || !y) return ut2_fail(-1, "conv_fwd: null pointer");
-  if (Cin % 64 || Cin <= 0) return ut2_fail(-2, "conv_fwd: Cin must be a multiple of 64");
+  if (Cin % 8 || Cin <= 0) return ut2_fail(-2, "conv_fwd: Cin must be a multiple of 8");
   const int block_n = pick_block_n(Cout);
   if (block_n < 0) return ut2_fail(-3, "conv_fwd: unsupported Cout (need %16==0; >256 needs %128==0)");
   if (stride < 1 || stride > 8 || pad < 0 || R < 1 || S < 1) return ut2_fail(-4, "conv_fwd: bad geometry");
@@ -396,6 +418,8 @@ extern "C" int ut2_conv2d_nhwc_bf16_fwd(const void* x, int N, int H, int W, int 
   a.P = P; a.Q = Q; a.stride = stride; a.pad = pad; a.R = R; a.S = S; a.Cin = Cin;
   a.relu = relu; a.scale = scale; a.shift = shift;
   a.residual = static_cast<const __nv_bfloat16*>(residual); a.ldr = Cout;
+  a.res_up2 = res_up2; a.relu_mask = static_cast<const __nv_bfloat16*>(relu_mask);
+  if (res_up2 && ((P & 1) || (Q & 1))) return ut2_fail(-4, "conv_fwd: res_up2 needs even output H, W");
   a.out = static_cast<__nv_bfloat16*>(y);
   CUtensorMap tx, tw;
   int rc = make_tmap_im2col_bf16(&tx, x, N, H, W, Cin, R, S, stride, pad, 64, BM);
@@ -416,7 +440,8 @@ extern "C" int ut2_conv2d_nhwc_bf16_fwd(const void* x, int N, int H, int W, int 
 
 extern "C" int ut2_conv2d_nhwc_bf16_wgrad(const void* x, int N, int H, int W, int Cin,
                                           const void* dy, int Cout, int R, int S, int stride,
-                                          int pad, const float* scale, float* dw, void* stream) {
+                                          int pad, const float* scale, float* dw, int cout_store,
+                                          void* stream) {
   if (!x || !dy || !dw) return ut2_fail(-1, "conv_wgrad: null pointer");
   if (Cin % 64 || Cin <= 0) return ut2_fail(-2, "conv_wgrad: Cin must be a multiple of 64");
   if (Cout % 8) return ut2_fail(-3, "conv_wgrad: Cout must be a multiple of 8");
@@ -435,6 +460,7 @@ extern "C" int ut2_conv2d_nhwc_bf16_wgrad(const void* x, int N, int H, int W, in
   a.kb_per_split = (a.kb_total + splits - 1) / splits;
   splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
   a.scale = scale; a.dw = dw;
+  a.cout_store = (cout_store > 0 && cout_store < Cout) ? cout_store : Cout;
   CUtensorMap tg, tx;
   int rc = make_tmap_2d_bf16(&tg, dy, a.Mpix, Cout, Cout, 64, WG_PIX);
   if (rc) return ut2_fail(rc, "conv_wgrad: dY tensor map encode failed");

@@ -139,14 +139,15 @@ __device__ __forceinline__ float focal_term(float x, bool t, float alpha, float 
 
 // sum over all P x C logits; acc[0] += sum
 __global__ void __launch_bounds__(256)
-focal_fwd_kernel(const bf16* __restrict__ logits, int ld, int C, const long long* __restrict__ labels, long long P,
-                 float alpha, float gamma, double* __restrict__ acc) {
+focal_fwd_kernel(const bf16* __restrict__ logits, int ld, int C, const long long* __restrict__ labels,
+                 const uint8_t* __restrict__ keep, long long P, float alpha, float gamma, double* __restrict__ acc) {
   const long long total = P * (C / 2);
   float s = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long p = i / (C / 2);
     const int c = (int)(i - p * (C / 2)) * 2;
+    if (keep && !keep[p]) continue;   // fcos_outputs.py:310 — images without GT are dropped from the labeled loss
     const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(logits + p * ld + c));
     const int lab = (int)labels[p];
     s += focal_term(__uint_as_float(u << 16), lab == c, alpha, gamma, nullptr);
@@ -166,8 +167,9 @@ focal_fwd_kernel(const bf16* __restrict__ logits, int ld, int C, const long long
 
 // dlogits = coef * dfocal/dx, coef = gout / max(norm[0] / world, 1)  (0 when zero_if_nopos and no positives)
 __global__ void __launch_bounds__(256)
-focal_bwd_kernel(const bf16* __restrict__ logits, int ld, int C, const long long* __restrict__ labels, long long P,
-                 float alpha, float gamma, const float* __restrict__ norm, float world, const float* __restrict__ gout,
+focal_bwd_kernel(const bf16* __restrict__ logits, int ld, int C, const long long* __restrict__ labels,
+                 const uint8_t* __restrict__ keep, long long P, float alpha, float gamma,
+                 const float* __restrict__ norm, float world, const float* __restrict__ gout,
                  const double* __restrict__ acc, int zero_if_nopos, bf16* __restrict__ dlogits) {
   float coef = gout[0] / fmaxf(norm[0] / world, 1.0f);
   if (zero_if_nopos && acc[6] == 0.0) coef = 0.f;
@@ -181,6 +183,7 @@ focal_bwd_kernel(const bf16* __restrict__ logits, int ld, int C, const long long
     float d0, d1;
     focal_term(__uint_as_float(u << 16), lab == c, alpha, gamma, &d0);
     focal_term(__uint_as_float(u & 0xFFFF0000u), lab == c + 1, alpha, gamma, &d1);
+    if (keep && !keep[p]) d0 = d1 = 0.f;
     __nv_bfloat162 h = __floats2bfloat162_rn(d0 * coef, d1 * coef);
     *reinterpret_cast<__nv_bfloat162*>(dlogits + p * ld + c) = h;
   }
@@ -362,14 +365,16 @@ pos_bwd_kernel(Levels lv, int N, const bf16* __restrict__ box_out, int ld, const
                const long long* __restrict__ labels, const float* __restrict__ reg_t, const float* __restrict__ bvar,
                int num_classes, int mode, float ts_better, float ts_cert, float kl_w, const double* __restrict__ acc,
                const float* __restrict__ norm, float world, const float* __restrict__ gout /*[cls, loc, ctr]*/,
-               bf16* __restrict__ dbox, float* __restrict__ dscales) {
+               bf16* __restrict__ dbox, float* __restrict__ dscales, int accumulate) {
   const long long P = (long long)lv.off[lv.num] * N;
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (p >= P) return;
   uint4* drow = reinterpret_cast<uint4*>(dbox + p * ld);
   if (labels[p] == num_classes) {
+    if (!accumulate) {
 #pragma unroll
-    for (int j = 0; j < 10; ++j) drow[j] = make_uint4(0, 0, 0, 0);
+      for (int j = 0; j < 10; ++j) drow[j] = make_uint4(0, 0, 0, 0);
+    }
     return;
   }
   const float num_pos_avg = fmaxf(norm[0] / world, 1.0f);
@@ -389,6 +394,11 @@ pos_bwd_kernel(Levels lv, int N, const bf16* __restrict__ box_out, int ld, const
   for (int j = 0; j < 80; ++j) grow[j] = 0.f;
   float ds = 0.f;
   pos_terms<true>(box_out + p * ld, scales[l], t, bv, mode, ts_better, ts_cert, c_bce, c_giou, c_nll, c_l1, grow, &ds);
+  if (accumulate) {
+    const bf16* old = dbox + p * ld;
+#pragma unroll
+    for (int j = 0; j < 80; ++j) grow[j] += __bfloat162float(old[j]);
+  }
 #pragma unroll
   for (int j = 0; j < 10; ++j) {
     uint32_t w[4];
@@ -435,9 +445,9 @@ extern "C" int ut2_fcos_assign_targets(int num_levels, const int* hw, const int*
 // acc: double[8] zeroed here; mode 0/1 also run the focal sum over cls_out. losses: float[4].
 extern "C" int ut2_fcos_loss_fwd(int num_levels, const int* hw, const int* strides, int N, const void* cls_out,
                                  const void* box_out, int ld, const float* scales, const long long* labels,
-                                 const float* reg_t, const float* bvar, int num_classes, int mode, float alpha,
-                                 float gamma, float kl_w, float ts_better, float ts_cert, const float* norm,
-                                 float world, double* acc, float* losses, void* stream) {
+                                 const unsigned char* keep, const float* reg_t, const float* bvar, int num_classes,
+                                 int mode, float alpha, float gamma, float kl_w, float ts_better, float ts_cert,
+                                 const float* norm, float world, double* acc, float* losses, void* stream) {
   Levels lv;
   if (fill_levels(lv, num_levels, hw, strides, nullptr)) return ut2_fail(-2, "fcos_loss_fwd: bad level count");
   const long long P = (long long)lv.off[lv.num] * N;
@@ -446,8 +456,8 @@ extern "C" int ut2_fcos_loss_fwd(int num_levels, const int* hw, const int* strid
     const long long total = P * (num_classes / 2);
     long long g = (total + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    focal_fwd_kernel<<<(int)g, 256, 0, STREAM>>>(static_cast<const bf16*>(cls_out), ld, num_classes, labels, P, alpha,
-                                                 gamma, acc);
+    focal_fwd_kernel<<<(int)g, 256, 0, STREAM>>>(static_cast<const bf16*>(cls_out), ld, num_classes, labels,
+                                                 mode == 0 ? keep : nullptr, P, alpha, gamma, acc);
   }
   pos_fwd_kernel<<<ut2_ceil_div(P, 128), 128, 0, STREAM>>>(lv, N, static_cast<const bf16*>(box_out), ld, scales, labels,
                                                            reg_t, bvar, num_classes, mode, ts_better, ts_cert, acc);
@@ -457,12 +467,13 @@ extern "C" int ut2_fcos_loss_fwd(int num_levels, const int* hw, const int* strid
 
 // gout: device float[3] = d(total)/d(cls, loc, ctr). dcls / dbox are fully written (zeros off the positives);
 // dcls may be null for mode 2, dbox may be null never. dscales (float[num_levels]) is accumulated.
+// accumulate != 0: dbox rows of the positives are added to (used to merge the pseudo cls-set and reg-set grads).
 extern "C" int ut2_fcos_loss_bwd(int num_levels, const int* hw, const int* strides, int N, const void* cls_out,
                                  const void* box_out, int ld, const float* scales, const long long* labels,
-                                 const float* reg_t, const float* bvar, int num_classes, int mode, float alpha,
-                                 float gamma, float kl_w, float ts_better, float ts_cert, const float* norm,
-                                 float world, const double* acc, const float* gout, void* dcls, void* dbox,
-                                 float* dscales, void* stream) {
+                                 const unsigned char* keep, const float* reg_t, const float* bvar, int num_classes,
+                                 int mode, float alpha, float gamma, float kl_w, float ts_better, float ts_cert,
+                                 const float* norm, float world, const double* acc, const float* gout, void* dcls,
+                                 void* dbox, float* dscales, int accumulate, void* stream) {
   Levels lv;
   if (fill_levels(lv, num_levels, hw, strides, nullptr)) return ut2_fail(-2, "fcos_loss_bwd: bad level count");
   const long long P = (long long)lv.off[lv.num] * N;
@@ -470,12 +481,13 @@ extern "C" int ut2_fcos_loss_bwd(int num_levels, const int* hw, const int* strid
     const long long total = P * (num_classes / 2);
     long long g = (total + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    focal_bwd_kernel<<<(int)g, 256, 0, STREAM>>>(static_cast<const bf16*>(cls_out), ld, num_classes, labels, P, alpha,
-                                                 gamma, norm, world, gout, acc, mode == 0,
-                                                 static_cast<bf16*>(dcls));
+    focal_bwd_kernel<<<(int)g, 256, 0, STREAM>>>(static_cast<const bf16*>(cls_out), ld, num_classes, labels,
+                                                 mode == 0 ? keep : nullptr, P, alpha, gamma, norm, world, gout, acc,
+                                                 mode == 0, static_cast<bf16*>(dcls));
   }
   pos_bwd_kernel<<<ut2_ceil_div(P, 128), 128, 0, STREAM>>>(lv, N, static_cast<const bf16*>(box_out), ld, scales, labels,
                                                            reg_t, bvar, num_classes, mode, ts_better, ts_cert, kl_w, acc,
-                                                           norm, world, gout, static_cast<bf16*>(dbox), dscales);
+                                                           norm, world, gout, static_cast<bf16*>(dbox), dscales,
+                                                           accumulate);
   return ut2_check_launch("fcos_loss_bwd");
 }

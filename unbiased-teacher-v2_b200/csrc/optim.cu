@@ -49,7 +49,7 @@ struct PackDesc {          // one conv weight: master fp32 [Cout, R, S, Cin] (ch
   long long wf;            // bf16 offset of the forward operand [rows, R, S, Cin] in the pack arena, or -1
   long long wt;            // bf16 offset of the dgrad operand [Cin, R, S, CoutT] (flipped taps), or -1
   long long begin;         // prefix sum of element counts (begin of this descriptor)
-  int Cout, Cin, R, S, CoutT, pad;
+  int Cout, Cin, R, S, CoutT, n_off;   // n_off: column offset inside wt rows (fused predictors)
 };
 
 __global__ void __launch_bounds__(256)
@@ -72,7 +72,7 @@ pack_batched_kernel(const PackDesc* __restrict__ descs, int num, long long total
     const bf16 v = __float2bfloat16_rn(arena[d.src + e]);
     if (d.wf >= 0) packed[d.wf + e] = v;
     if (d.wt >= 0)
-      packed[d.wt + (((long long)c * d.R + (d.R - 1 - r)) * d.S + (d.S - 1 - s)) * d.CoutT + n] = v;
+      packed[d.wt + (((long long)c * d.R + (d.R - 1 - r)) * d.S + (d.S - 1 - s)) * d.CoutT + n + d.n_off] = v;
   }
 }
 
@@ -105,7 +105,7 @@ extern "C" int ut2_sgd_step(float* p, float* g, float* buf, long long n, float l
   return ut2_check_launch("sgd_step");
 }
 
-// descs: device array of `num` 64-byte records {src, wf, wt, begin, Cout, Cin, R, S, CoutT, pad}.
+// descs: device array of `num` 64-byte records {src, wf, wt, begin, Cout, Cin, R, S, CoutT, n_off}.
 extern "C" int ut2_pack_conv_weights_batched(const void* descs, int num, long long total, const float* arena,
                                              void* packed, void* stream) {
   if (num <= 0 || total <= 0) return 0;

@@ -1,0 +1,53 @@
+"""Synthetic two-crop batches with the shape of the reference loader's output
+(ubteacher/data/build.py:144-272 yields (label_strong, label_weak, unlabel_strong, unlabel_weak) lists of
+dicts): uint8 BGR images 3x800x1333 in pinned host memory, ~7 COCO-like boxes per labeled image
+(SURVEY.md §8d). Used by bench.py, smoke() and the tests — there is no dataset on the box."""
+import torch
+
+from ..d2compat.structures import Boxes, Instances
+
+
+def synth_instances(g, h, w, n=7):
+    wh = torch.exp(torch.rand(n, 2, generator=g) * (6.238 - 3.466) + 3.466)       # log-uniform [32, 512]
+    wh[:, 0].clamp_(max=w - 2.0)
+    wh[:, 1].clamp_(max=h - 2.0)
+    xy = torch.rand(n, 2, generator=g) * (torch.tensor([float(w), float(h)]) - wh)
+    inst = Instances((h, w))
+    inst.gt_boxes = Boxes(torch.cat([xy, xy + wh], 1))
+    inst.gt_classes = torch.randint(0, 80, (n,), generator=g)
+    return inst
+
+
+class SyntheticTwoCropLoader:
+    def __init__(self, n_label, n_unlabel, h=800, w=1333, rank=0, boxes_per_image=7, pool=4, pin=True):
+        self.nl, self.nu, self.h, self.w, self.rank, self.nbox = n_label, n_unlabel, h, w, rank, boxes_per_image
+        g = torch.Generator().manual_seed(20260 + 1000 * rank)
+        # a small pool of pinned random images, re-used round-robin (generating 4x8 fresh 3.2 MB images per
+        # step on the host would measure torch.randint, not the training step)
+        n_img = pool * 2 * (n_label + n_unlabel)
+        self.pool = []
+        for _ in range(n_img):
+            t = torch.randint(0, 256, (3, h, w), generator=g, dtype=torch.uint8)
+            self.pool.append(t.pin_memory() if pin and torch.cuda.is_available() else t)
+        self.g = g
+        self.step = 0
+
+    def __iter__(self):
+        return self
+
+    def _img(self):
+        t = self.pool[self.step % len(self.pool)]
+        self.step += 1
+        return t
+
+    def __next__(self):
+        def lab(n):
+            q, k = [], []
+            for _ in range(n):
+                inst = synth_instances(self.g, self.h, self.w, self.nbox)
+                q.append({"image": self._img(), "instances": inst, "height": self.h, "width": self.w})
+                k.append({"image": self._img(), "instances": inst, "height": self.h, "width": self.w})
+            return q, k
+        lq, lk = lab(self.nl)
+        uq, uk = lab(self.nu)
+        return lq, lk, uq, uk

@@ -1,0 +1,233 @@
+"""``UBTeacherTrainer`` — the FCOS Unbiased-Teacher-v2 training loop with the reference's surface
+(ubteacher/engine/trainer.py:38-610): ctor(cfg), train(), run_step_full_semisup(), _update_teacher_model(),
+_write_metrics(), attributes model / model_teacher / optimizer / pseudo_generator / iter / storage.
+
+What changed underneath (B200-first, same arithmetic):
+  * teacher and student are FcosEngine replicas (flat arenas, tensor-core implicit-GEMM convs);
+  * pseudo labels never leave the device (no .item()/nonzero syncs: fixed-capacity sets + counters);
+  * the labeled and the unlabeled student passes are back-propagated right after their forward with the
+    reference's loss weights as the incoming gradient (identical sum of gradients, half the live activations);
+  * data parallel = one NCCL all-reduce of the contiguous gradient arena, mean folded into the SGD kernel;
+  * EMA is one kernel over the whole state (trainer.py:468-486 is a ~320-tensor Python loop);
+  * metrics are stacked on the device and read back once every `metrics_period` iterations.
+"""
+import logging
+import time
+
+import numpy as np
+import torch
+
+from ..d2compat import comm
+from ..d2compat.events import EventStorage
+from ..d2compat.registry import META_ARCH_REGISTRY
+from ..modeling.meta_arch.ts_ensemble import EnsembleTSModel
+from ..modeling.pseudo_generator import PseudoGenerator
+from ..solver.lr_scheduler import WarmupMultiStepLR
+
+logger = logging.getLogger(__name__)
+
+
+class ArenaSGD:
+    """torch.optim-like facade over the fused SGD kernel ([D2] build_optimizer: SGD, momentum 0.9, wd 1e-4,
+    WEIGHT_DECAY_NORM 0 for the GroupNorm parameters, no gradient clipping)."""
+
+    def __init__(self, cfg, model):
+        s = cfg.SOLVER
+        self.model = model
+        self.momentum = s.MOMENTUM
+        self.param_groups = [
+            {"name": "decay", "lr": s.BASE_LR, "initial_lr": s.BASE_LR, "weight_decay": s.WEIGHT_DECAY},
+            {"name": "norm", "lr": s.BASE_LR, "initial_lr": s.BASE_LR, "weight_decay": s.WEIGHT_DECAY_NORM},
+        ]
+        self.steps = 0
+        self.grad_scale = 1.0
+
+    def zero_grad(self, set_to_none=False):
+        pass  # the SGD kernel clears the gradient arena in the same pass that consumes it
+
+    def step(self):
+        eng = self.model.engine
+        eng.sgd_step(self.param_groups[0]["lr"], self.momentum, self.param_groups[0]["weight_decay"],
+                     self.param_groups[1]["weight_decay"], self.steps == 0, self.grad_scale)
+        eng.refresh_operands()
+        self.steps += 1
+
+    def state_dict(self):
+        return {"steps": self.steps, "momentum_buffer": self.model.engine.arena.mom,
+                "param_groups": self.param_groups}
+
+    def load_state_dict(self, sd):
+        self.steps = sd["steps"]
+        self.model.engine.arena.mom.copy_(sd["momentum_buffer"])
+
+
+class UBTeacherTrainer:
+    def __init__(self, cfg, data_loader=None):
+        self.cfg = cfg
+        if comm.get_world_size() > 1:
+            torch.cuda.set_device(comm.get_local_rank())
+        model = self.build_model(cfg)
+        self.optimizer = self.build_optimizer(cfg, model)
+        model_teacher = self.build_model(cfg)
+        self.model_teacher = model_teacher
+        self.model_teacher.eval()                       # trainer.py:55
+        self.model = model
+        self.model.train()
+        self.data_loader = data_loader if data_loader is not None else self.build_train_loader(cfg)
+        self._data_loader_iter = iter(self.data_loader)
+        self.scheduler = self.build_lr_scheduler(cfg, self.optimizer)
+        self.ensem_ts_model = EnsembleTSModel(model_teacher, model)
+        self.pseudo_generator = PseudoGenerator(cfg)
+        self.start_iter = 0
+        self.iter = 0
+        self.max_iter = cfg.SOLVER.MAX_ITER
+        self.storage = None
+        self.metrics_period = 20                        # PeriodicWriter period (trainer.py:551)
+        self._metric_names, self._metric_buf = None, []
+        self.last_losses = None
+        if comm.get_world_size() > 1:                   # DDP's initial parameter broadcast
+            torch.distributed.broadcast(model.engine.arena.data, 0)
+            model.engine.refresh_operands()
+            self.optimizer.grad_scale = 1.0 / comm.get_world_size()
+
+    # ---------------------------------------------------------------- builders ([D2] DefaultTrainer API)
+    @classmethod
+    def build_model(cls, cfg):
+        return META_ARCH_REGISTRY.get(cfg.MODEL.META_ARCHITECTURE)(cfg)
+
+    @classmethod
+    def build_optimizer(cls, cfg, model):
+        return ArenaSGD(cfg, model)
+
+    @classmethod
+    def build_lr_scheduler(cls, cfg, optimizer):
+        return WarmupMultiStepLR(optimizer, cfg.SOLVER.STEPS, cfg.SOLVER.GAMMA, cfg.SOLVER.WARMUP_FACTOR,
+                                 cfg.SOLVER.WARMUP_ITERS, cfg.SOLVER.WARMUP_METHOD)
+
+    @classmethod
+    def build_train_loader(cls, cfg):
+        from ..data.synthetic import SyntheticTwoCropLoader
+        logger.warning("no dataset on this box: using the synthetic two-crop loader (SURVEY.md §8d)")
+        w = comm.get_world_size()
+        return SyntheticTwoCropLoader(cfg.SOLVER.IMG_PER_BATCH_LABEL // w, cfg.SOLVER.IMG_PER_BATCH_UNLABEL // w,
+                                      rank=comm.get_rank())
+
+    def resume_or_load(self, resume=True):
+        return None   # checkpoint I/O is outside the hot path
+
+    # ---------------------------------------------------------------- loop
+    def train(self):
+        self.train_loop(self.start_iter, self.max_iter)
+
+    def train_loop(self, start_iter, max_iter):
+        self.iter = self.start_iter = start_iter
+        self.max_iter = max_iter
+        with EventStorage(start_iter) as self.storage:
+            for self.iter in range(start_iter, max_iter):
+                self.run_step_full_semisup()
+                self.scheduler.step()
+                self.storage.step()
+
+    # ---------------------------------------------------------------- pseudo-labeling helpers (trainer.py:161-175)
+    def remove_label(self, label_data):
+        for d in label_data:
+            if "instances" in d:
+                del d["instances"]
+        return label_data
+
+    def add_label(self, unlabled_data, label, labeltype=""):
+        key = {"class": "instances_class", "reg": "instances_reg"}.get(labeltype, "instances")
+        for d in unlabled_data:
+            d[key] = label       # the whole batch's device-resident BoxSet (one object shared by the dicts)
+        return unlabled_data
+
+    # ---------------------------------------------------------------- the step (trainer.py:181-429)
+    def run_step_full_semisup(self):
+        assert self.model.training, "[UBTeacherTrainer] model was changed to eval mode!"
+        cfg, ss = self.cfg, self.cfg.SEMISUPNET
+        start = time.perf_counter()
+        label_data_q, label_data_k, unlabel_data_q, unlabel_data_k = next(self._data_loader_iter)
+        data_time = time.perf_counter() - start
+        record = {}
+        if self.iter < ss.BURN_UP_STEP:
+            losses, pending = self.model.forward_train(label_data_q + label_data_k, "labeled")
+            record.update(losses)
+            self.model.backward_pending(pending, [[1.0, 1.0, 1.0, 0.0]])
+        else:
+            if self.iter == ss.BURN_UP_STEP:
+                self._update_teacher_model(keep_rate=0.00)
+                ema_keep_rate = ss.EMA_KEEP_RATE
+            elif (self.iter - ss.BURN_UP_STEP) % ss.TEACHER_UPDATE_ITER == 0:
+                ema_keep_rate = ss.EMA_KEEP_RATE
+                self._update_teacher_model(keep_rate=ema_keep_rate)
+            else:
+                ema_keep_rate = ss.EMA_KEEP_RATE
+            record["ema_rate_1000x"] = ema_keep_rate * 1000
+            # teacher on the weak views (trainer.py:231-237) + second NMS criterion (:240-242)
+            pred_teacher, raw_pred_teacher = self.model_teacher(
+                unlabel_data_k, output_raw=True, nms_method=cfg.MODEL.FCOS.NMS_CRITERIA_TRAIN, branch="teacher_weak")
+            raw_pred_teacher["scales"] = self.model_teacher.engine.scales
+            pred_teacher_loc = self.pseudo_generator.nms_from_dense(raw_pred_teacher, cfg.MODEL.FCOS.NMS_CRITERIA_REG_TRAIN)
+            thr = self._threshold(ss.PSEUDO_BBOX_SAMPLE, ss.BBOX_THRESHOLD, ss.BBOX_CTR_THRESHOLD)
+            thr_reg = self._threshold(ss.PSEUDO_BBOX_SAMPLE_REG, ss.BBOX_THRESHOLD_REG, ss.BBOX_CTR_THRESHOLD_REG)
+            pseudo_cls, _ = self.pseudo_generator.process_pseudo_label(pred_teacher, thr, "roih", ss.PSEUDO_BBOX_SAMPLE)
+            pseudo_reg, _ = self.pseudo_generator.process_pseudo_label(pred_teacher_loc, thr_reg, "roih",
+                                                                       ss.PSEUDO_BBOX_SAMPLE_REG)
+            unlabel_data_q = self.remove_label(unlabel_data_q)
+            unlabel_data_q = self.add_label(unlabel_data_q, pseudo_cls, "class")
+            unlabel_data_q = self.add_label(unlabel_data_q, pseudo_reg, "reg")
+            lam, mu = ss.UNSUP_LOSS_WEIGHT, ss.UNSUP_REG_LOSS_WEIGHT
+            # student: labeled strong + weak (trainer.py:315-322), weights :378-416
+            losses, pending = self.model.forward_train(label_data_q + label_data_k, "labeled")
+            record.update(losses)
+            self.model.backward_pending(pending, [[1.0 / (lam + 1.0), 1.0 / (mu + 1.0), 1.0 / (lam + 1.0), 0.0]])
+            # student: unlabeled strong with the two pseudo-label sets (trainer.py:331-349)
+            losses_u, pending_u = self.model.forward_train(unlabel_data_q, "unlabeled")
+            record.update({k + "_pseudo": v for k, v in losses_u.items()})
+            self.model.backward_pending(pending_u, [[lam / (lam + 1.0), 0.0, lam / (lam + 1.0), 0.0],
+                                                    [0.0, mu / (mu + 1.0), 0.0, 0.0]])
+        record["data_time"] = data_time
+        self._write_metrics(record)
+        if comm.get_world_size() > 1:       # the DDP gradient all-reduce, one contiguous buffer (mean in the SGD kernel)
+            torch.distributed.all_reduce(self.model.engine.arena.grad)
+        self.optimizer.zero_grad()
+        self.optimizer.step()
+
+    @staticmethod
+    def _threshold(method, t0, t1):
+        if method == "thresholding":
+            return t0
+        if method == "thresholding_cls_ctr":
+            return (t0, t1)
+        raise ValueError
+
+    # ---------------------------------------------------------------- metrics (trainer.py:431-466)
+    def _write_metrics(self, metrics_dict):
+        names = [k for k, v in metrics_dict.items() if isinstance(v, torch.Tensor)]
+        vec = torch.stack([metrics_dict[k].detach().float().reshape(()) for k in names])
+        self.last_losses = (names, vec)
+        if self.storage is None or (self.iter + 1) % self.metrics_period:
+            return
+        host = vec.cpu().tolist()                                   # the only D2H of the step
+        md = {k: float(v) for k, v in metrics_dict.items() if not isinstance(v, torch.Tensor)}
+        md.update(dict(zip(names, host)))
+        all_md = comm.gather(md)
+        if comm.is_main_process():
+            if "data_time" in all_md[0]:
+                self.storage.put_scalar("data_time", np.max([x.pop("data_time") for x in all_md]))
+            md = {k: np.mean([x[k] for x in all_md]) for k in all_md[0].keys()}
+            self.storage.put_scalar("total_loss", sum(v for k, v in md.items() if k[:4] == "loss"))
+            if len(md) > 1:
+                self.storage.put_scalars(**md)
+
+    # ---------------------------------------------------------------- EMA (trainer.py:468-486)
+    @torch.no_grad()
+    def _update_teacher_model(self, keep_rate=0.996):
+        t = self.model_teacher.engine
+        t.ema_from(self.model.engine, keep_rate)
+        t.refresh_operands()
+
+    @torch.no_grad()
+    def _copy_main_model(self):
+        self.model_teacher.engine.arena.copy_from(self.model.engine.arena)
+        self.model_teacher.engine.refresh_operands()

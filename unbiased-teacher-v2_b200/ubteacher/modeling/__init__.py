@@ -1,0 +1,2 @@
+from .one_stage_detector import OneStageDetector, PseudoProposalNetwork  # noqa: F401
+from .pseudo_generator import PseudoGenerator  # noqa: F401

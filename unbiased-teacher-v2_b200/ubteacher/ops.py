@@ -14,21 +14,23 @@ def conv_out_hw(H, W, R, S, stride, pad):
     return (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
 
 
-def conv2d(x, w, cout, R, S, stride, pad, scale=None, shift=None, residual=None, relu=False, out=None):
+def conv2d(x, w, cout, R, S, stride, pad, scale=None, shift=None, residual=None, relu=False, out=None,
+           res_up2=False, relu_mask=None):
     """x: [N,H,W,Cin] bf16 NHWC; w: bf16 [>=cout, R, S, Cin]; returns [N,P,Q,cout] bf16."""
     N, H, W, Cin = x.shape
     P, Q = conv_out_hw(H, W, R, S, stride, pad)
     if out is None:
         out = torch.empty((N, P, Q, cout), dtype=BF16, device=x.device)
     _C.counted_call("ut2_conv2d_nhwc_bf16_fwd", x, N, H, W, Cin, w, cout, R, S, stride, pad, scale, shift, residual,
-                    int(relu), out)
+                    int(res_up2), relu_mask, int(relu), out)
     return out
 
 
-def conv2d_wgrad(x, dy, cout, R, S, stride, pad, dw, scale=None):
+def conv2d_wgrad(x, dy, cout, R, S, stride, pad, dw, scale=None, cout_store=0):
     """Accumulates dW (fp32, [cout, R, S, Cin]) += dY^T * im2col(X)."""
     N, H, W, Cin = x.shape
-    _C.counted_call("ut2_conv2d_nhwc_bf16_wgrad", x, N, H, W, Cin, dy, cout, R, S, stride, pad, scale, dw)
+    _C.counted_call("ut2_conv2d_nhwc_bf16_wgrad", x, N, H, W, Cin, dy, cout, R, S, stride, pad, scale, dw,
+                    cout_store)
 
 
 def groupnorm_relu_fwd(x, gamma, beta, eps=1e-5, relu=True):
@@ -167,18 +169,18 @@ def fcos_loss_fwd(geom, N, cls_out, box_out, scales, tg, mode, alpha, gamma, kl_
     acc = torch.empty(8, dtype=torch.float64, device=dev)
     losses = torch.empty(4, dtype=torch.float32, device=dev)
     _C.counted_call("ut2_fcos_loss_fwd", geom.num, geom.c_hw, geom.c_strides, N, cls_out, box_out, box_out.shape[-1],
-                    scales, tg["labels"], tg["reg_targets"], tg["boundary_vars"], num_classes, mode, f32(alpha),
+                    scales, tg["labels"], tg["keep_locations"], tg["reg_targets"], tg["boundary_vars"], num_classes, mode, f32(alpha),
                     f32(gamma), f32(kl_w), f32(ts_better), f32(ts_cert), tg["norm"], f32(world), acc, losses)
     _C.launch_count += 2 if mode != 2 else 1
     return losses, acc
 
 
 def fcos_loss_bwd(geom, N, cls_out, box_out, scales, tg, mode, alpha, gamma, kl_w, ts_better, ts_cert, world, acc,
-                  gout, dcls, dbox, dscales, num_classes=80):
+                  gout, dcls, dbox, dscales, num_classes=80, accumulate=False):
     _C.counted_call("ut2_fcos_loss_bwd", geom.num, geom.c_hw, geom.c_strides, N, cls_out, box_out, box_out.shape[-1],
-                    scales, tg["labels"], tg["reg_targets"], tg["boundary_vars"], num_classes, mode, f32(alpha),
+                    scales, tg["labels"], tg["keep_locations"], tg["reg_targets"], tg["boundary_vars"], num_classes, mode, f32(alpha),
                     f32(gamma), f32(kl_w), f32(ts_better), f32(ts_cert), tg["norm"], f32(world), acc, gout, dcls, dbox,
-                    dscales)
+                    dscales, int(accumulate))
     if mode != 2:
         _C.launch_count += 1
 
