@@ -19,18 +19,33 @@ def synth_instances(g, h, w, n=7):
 
 
 class SyntheticTwoCropLoader:
-    def __init__(self, n_label, n_unlabel, h=800, w=1333, rank=0, boxes_per_image=7, pool=4, pin=True):
+    """device=None: images live in pinned host memory and GT are host ``Instances`` (the end-to-end mode, the
+    model does the H2D copies); device="cuda": the image pool and pre-packed GT ``BoxSet``s are resident in HBM."""
+
+    def __init__(self, n_label, n_unlabel, h=800, w=1333, rank=0, boxes_per_image=7, pool=2, pin=True, device=None):
         self.nl, self.nu, self.h, self.w, self.rank, self.nbox = n_label, n_unlabel, h, w, rank, boxes_per_image
+        self.device = device
         g = torch.Generator().manual_seed(20260 + 1000 * rank)
-        # a small pool of pinned random images, re-used round-robin (generating 4x8 fresh 3.2 MB images per
-        # step on the host would measure torch.randint, not the training step)
+        # a small pool of random images, re-used round-robin (generating 32 fresh 3.2 MB images per step on the
+        # host would measure torch.randint, not the training step)
         n_img = pool * 2 * (n_label + n_unlabel)
         self.pool = []
         for _ in range(n_img):
             t = torch.randint(0, 256, (3, h, w), generator=g, dtype=torch.uint8)
-            self.pool.append(t.pin_memory() if pin and torch.cuda.is_available() else t)
+            if device is not None:
+                t = t.to(device)
+            elif pin and torch.cuda.is_available():
+                t = t.pin_memory()
+            self.pool.append(t)
         self.g = g
         self.step = 0
+        self.gt_pool = []
+        if device is not None:
+            from ..modeling.fcos.fcos_outputs import BoxSet
+            for _ in range(4):
+                insts = [synth_instances(g, h, w, boxes_per_image) for _ in range(n_label)]
+                self.gt_pool.append(BoxSet.from_instances(insts + insts, device))
+            torch.cuda.synchronize()
 
     def __iter__(self):
         return self
@@ -41,6 +56,14 @@ class SyntheticTwoCropLoader:
         return t
 
     def __next__(self):
+        if self.device is not None:
+            mk = lambda n: [{"image": self._img(), "height": self.h, "width": self.w} for _ in range(n)]
+            lq, lk, uq, uk = mk(self.nl), mk(self.nl), mk(self.nu), mk(self.nu)
+            gt = self.gt_pool[(self.step // max(len(self.pool), 1)) % len(self.gt_pool)]
+            for d in lq + lk:
+                d["instances"] = gt          # batch-level device-resident ground truth (strong + weak share boxes)
+            return lq, lk, uq, uk
+
         def lab(n):
             q, k = [], []
             for _ in range(n):

@@ -56,8 +56,9 @@ class Conv:
             xc = ops.conv2d(g, self.wt, self.cin, 1, 1, 1, 0, None, None, residual)   # residual is compact here
             return ops.zero_stuff_s2(xc, H, W)
         gz = ops.zero_stuff_s2(g, H, W)
+        alg = 2.0 * g.shape[0] * g.shape[1] * g.shape[2] * self.cout * self.cin * k * k   # zeros are not work
         return ops.conv2d(gz, self.wt, self.cin, k, k, 1, k - 1 - self.pad, None, None, residual, False, None, False,
-                          relu_mask)
+                          relu_mask, alg)
 
     def dgrad_compact(self, g, residual=None):
         """stride-2 1x1 only: the un-stuffed [N, P, Q, Cin] gradient (so two of them can be summed first)."""

@@ -152,7 +152,8 @@ class OneStageDetector(PseudoProposalNetwork):
         elif "instances" in b0 and branch != "teacher_weak":
             if branch != "labeled":
                 raise ValueError("Incorrect branch name")
-            gt = as_boxset([x["instances"] for x in batched_inputs], self.device)
+            gt = b0["instances"] if isinstance(b0["instances"], BoxSet) else \
+                as_boxset([x["instances"] for x in batched_inputs], self.device)
             losses, ctxs = self.fcos_outputs.losses(fwd, eng.scales, gt)
             names = [[(0, "loss_fcos_cls"), (1, "loss_fcos_loc"), (2, "loss_fcos_ctr")]]
         else:

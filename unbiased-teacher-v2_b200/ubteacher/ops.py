@@ -9,28 +9,45 @@ from ._C import f32, f64, i64
 
 BF16 = torch.bfloat16
 
+# bench.py sets PROFILE = {"conv_fwd": [], "conv_wgrad": []} to bracket every tensor-core launch with CUDA events
+# on the launching stream: entries are (start_event, end_event, algorithmic_flops).
+PROFILE = None
+
+
+def _timed(kind, flops, name, *args):
+    if PROFILE is None:
+        _C.counted_call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _C.counted_call(name, *args)
+    e1.record()
+    PROFILE[kind].append((e0, e1, flops))
+
 
 def conv_out_hw(H, W, R, S, stride, pad):
     return (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
 
 
 def conv2d(x, w, cout, R, S, stride, pad, scale=None, shift=None, residual=None, relu=False, out=None,
-           res_up2=False, relu_mask=None):
+           res_up2=False, relu_mask=None, alg_flops=None):
     """x: [N,H,W,Cin] bf16 NHWC; w: bf16 [>=cout, R, S, Cin]; returns [N,P,Q,cout] bf16."""
     N, H, W, Cin = x.shape
     P, Q = conv_out_hw(H, W, R, S, stride, pad)
     if out is None:
         out = torch.empty((N, P, Q, cout), dtype=BF16, device=x.device)
-    _C.counted_call("ut2_conv2d_nhwc_bf16_fwd", x, N, H, W, Cin, w, cout, R, S, stride, pad, scale, shift, residual,
-                    int(res_up2), relu_mask, int(relu), out)
+    flops = alg_flops if alg_flops is not None else 2.0 * N * P * Q * cout * Cin * R * S
+    _timed("conv_fwd", flops, "ut2_conv2d_nhwc_bf16_fwd", x, N, H, W, Cin, w, cout, R, S, stride, pad, scale, shift,
+           residual, int(res_up2), relu_mask, int(relu), out)
     return out
 
 
 def conv2d_wgrad(x, dy, cout, R, S, stride, pad, dw, scale=None, cout_store=0):
     """Accumulates dW (fp32, [cout, R, S, Cin]) += dY^T * im2col(X)."""
     N, H, W, Cin = x.shape
-    _C.counted_call("ut2_conv2d_nhwc_bf16_wgrad", x, N, H, W, Cin, dy, cout, R, S, stride, pad, scale, dw,
-                    cout_store)
+    flops = 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * (cout_store or cout) * Cin * R * S
+    _timed("conv_wgrad", flops, "ut2_conv2d_nhwc_bf16_wgrad", x, N, H, W, Cin, dy, cout, R, S, stride, pad, scale, dw,
+           cout_store)
 
 
 def groupnorm_relu_fwd(x, gamma, beta, eps=1e-5, relu=True):
