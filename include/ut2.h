@@ -1,0 +1,132 @@
+/* ut2.h — C ABI of libut2_sm100.so, the B200 (sm_100a) kernel library behind the Unbiased-Teacher-v2 hot path.
+ *
+ * The reference has no FFI of its own: every device op below is reached there through Python -> torch /
+ * Detectron2 / torchvision / fvcore. Each entry point cites the reference call site it replaces
+ * (paths under /root/reference/ubteacher unless marked [D2] = Detectron2 v0.6, [tv] = torchvision, [fvcore]).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; all pointers are DEVICE pointers unless a parameter says "host".
+ *   - the caller owns every buffer (outputs and workspaces); the library never allocates device memory.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and never synchronises the host.
+ *   - return value: 0 = ok, < 0 = argument / shape error, > 0 = cudaError_t. ut2_last_error_string() (thread-local)
+ *     describes the last failure. No exceptions cross the boundary.
+ *   - activations are NHWC bf16 (== row-major [N*H*W, C]); conv weights are [Cout, R, S, Cin] bf16; accumulation fp32.
+ *   - variable-length results are fixed-capacity buffers + a device-side count.
+ *   - "level-major" per-location tensors: position p = level_off[l]*N + img*H_l*W_l + h*W_l + w, i.e. the per-level
+ *     NHWC head outputs laid back to back (the order fcos_outputs.py:257-296 builds with permute+reshape+cat).
+ */
+#ifndef UT2_H
+#define UT2_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- library */
+int ut2_version(void);
+const char* ut2_last_error_string(void);
+int ut2_device_sm_count(void);
+
+/* ---------------------------------------------------------------- tensor-core convolutions (tcgen05 + TMA im2col)
+ * Replaces torch.nn.functional.conv2d -> cuDNN for: [D2] ResNet bottlenecks / FPN (modeling/backbone/fpn.py:59-78),
+ * LastLevelP6P7 (backbone/fpn.py:11-29), FCOS towers and prediction convs (modeling/fcos/fcos.py:248-304,338-376).
+ * y[n,p,q,co] = act( scale[co] * sum_{r,s,ci} x[n, p*stride-pad+r, q*stride-pad+s, ci] * w[co,r,s,ci] + shift[co]
+ *                    (+ residual[n,p,q,co] | residual[n,p/2,q/2,co] when res_up2) ) , then zeroed where relu_mask <= 0.
+ * Cin % 8 == 0; Cout % 16 == 0 (<= 256, or a multiple of 128). scale/shift/residual/relu_mask may be NULL.
+ * The data-gradient is the same entry point applied to dY with the flipped/transposed filter (see ut2_pack_*). */
+int ut2_conv2d_nhwc_bf16_fwd(const void* x, int N, int H, int W, int Cin, const void* w, int Cout, int R, int S,
+                             int stride, int pad, const float* scale, const float* shift, const void* residual,
+                             int res_up2, const void* relu_mask, int relu, void* y, void* stream);
+/* dW[co,r,s,ci] (fp32, accumulated with atomics) += scale[co] * sum_{n,p,q} dy[n,p,q,co] * x[n,p*stride-pad+r,...,ci].
+ * Replaces the cuDNN wgrad autograd runs for the same layers (engine/trainer.py:422-429 -> losses.backward()).
+ * Rows >= cout_store (if > 0) are not written (zero-padded fused predictors). Cin % 64 == 0, Cout % 8 == 0. */
+int ut2_conv2d_nhwc_bf16_wgrad(const void* x, int N, int H, int W, int Cin, const void* dy, int Cout, int R, int S,
+                               int stride, int pad, const float* scale, float* dw, int cout_store, void* stream);
+/* test hook: one im2col-mode TMA load dumped from shared memory (pins the descriptor semantics) */
+int ut2_debug_im2col_probe(const void* x, int N, int H, int W, int C, int R, int S, int stride, int pad, int pixels,
+                           int c, int w, int h, int n, int off_w, int off_h, void* out, void* stream);
+
+/* ---------------------------------------------------------------- backbone helpers
+ * stem: pixel normalisation (one_stage_detector.py:88-89,165-166) + ImageList zero padding (:90,:167) + [D2] BasicStem
+ * conv7x7 s2 + FrozenBN + ReLU, from one uint8 CHW (BGR) image; wgt is fp32 [7][7][3][64]. */
+int ut2_stem_conv_u8(const void* img_chw, int h, int w, const float* wgt_rsck, const float* scale, const float* shift,
+                     float mean0, float mean1, float mean2, float std0, float std1, float std2, void* out, int P, int Q,
+                     void* stream);
+int ut2_maxpool3x3s2_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream);          /* [D2] BasicStem max_pool2d */
+int ut2_upsample2x_add_nhwc(const void* lat, const void* top, void* out, int N, int H, int W, int C, void* stream); /* [D2] FPN top-down */
+int ut2_downsample2x_sum_nhwc(const void* g, const void* addend, void* gtop, int N, int Ht, int Wt, int C, void* stream);
+int ut2_relu_bwd_bf16(const void* dy, const void* dy2, const void* y, void* g, long long n, void* stream);
+int ut2_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+int ut2_zero_stuff_s2_nhwc(const void* in, void* out, int N, int P, int Q, int H, int W, int C, int oh, int ow, void* stream);
+int ut2_colsum_bf16(const void* g, float* db, int M, int C, void* stream);                             /* conv bias gradients */
+int ut2_frozen_bn_fold(const float* w, const float* b, const float* mean, const float* var, float eps, float* scale,
+                       float* shift, int C, void* stream);                                             /* [D2] FrozenBatchNorm2d */
+int ut2_cast_f32_bf16(const float* x, void* y, long long n, void* stream);
+
+/* GroupNorm(32, 256) + ReLU of the FCOS towers (fcos/fcos.py:263-264,283). stats/ws: double[N*32*2]. */
+int ut2_groupnorm_relu_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, double* stats,
+                           int N, int HW, int C, int G, int relu, void* stream);
+int ut2_groupnorm_relu_bwd(const void* dy, const void* x, const double* stats, const float* gamma, const float* beta,
+                           float eps, void* dx, float* dgamma, float* dbeta, double* ws, int N, int HW, int C, int G,
+                           int relu, void* stream);
+
+/* ---------------------------------------------------------------- FCOS targets and losses
+ * ut2_fcos_assign_targets: FCOSOutputs._get_ground_truth + compute_targets_for_locations
+ * (fcos/fcos_outputs.py:649-698, :772-906; CENTER_SAMPLE False). hw/strides/ranges are HOST arrays
+ * ([H,W] x levels, stride x levels, [lo,hi] x levels). boxes [N,G,4], classes [N,G] (int64), counts [N] (int32),
+ * bvar [N,G,4] or NULL (teacher reg_pred_std). norm[2] receives {num_pos, sum of centerness targets}. */
+int ut2_fcos_assign_targets(int num_levels, const int* hw, const int* strides, const float* ranges, int N, int G,
+                            const float* boxes, const long long* classes, const int* counts, const float* bvar,
+                            int num_classes, long long* labels, long long* tinds, float* reg_t, float* bv_out,
+                            unsigned char* keep, float* norm, void* stream);
+/* mode 0: FCOSOutputs.fcos_losses (fcos_outputs.py:307-444); mode 1 / 2: fcos_pseudo_losses on the classification /
+ * regression pseudo-label set (:492-631). Includes Integral (:44-77), centerness / IoU targets (:80-129), IOULoss giou
+ * (layers/iou_loss.py:23-76), NLLoss (layers/kl_loss.py:75-105), [fvcore] sigmoid_focal_loss_jit.
+ * cls_out / box_out are [P, ld] bf16 (box_out: 68 distribution logits | 4 std | 1 centerness | pad); scales[levels] is
+ * the learnable Scale (fcos/fcos.py:22-29,367). norm is the (all-reduced) output of ut2_fcos_assign_targets, world the
+ * number of ranks. acc: double[8] scratch kept for backward; losses: float[4] = {cls, loc, ctr, teacher_better_student}. */
+int ut2_fcos_loss_fwd(int num_levels, const int* hw, const int* strides, int N, const void* cls_out, const void* box_out,
+                      int ld, const float* scales, const long long* labels, const unsigned char* keep, const float* reg_t,
+                      const float* bvar, int num_classes, int mode, float alpha, float gamma, float kl_w, float ts_better,
+                      float ts_cert, const float* norm, float world, double* acc, float* losses, void* stream);
+int ut2_fcos_loss_bwd(int num_levels, const int* hw, const int* strides, int N, const void* cls_out, const void* box_out,
+                      int ld, const float* scales, const long long* labels, const unsigned char* keep, const float* reg_t,
+                      const float* bvar, int num_classes, int mode, float alpha, float gamma, float kl_w, float ts_better,
+                      float ts_cert, const float* norm, float world, const double* acc, const float* gout, void* dcls,
+                      void* dbox, float* dscales, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------- proposals, NMS, pseudo labels
+ * FCOSOutputs.predict_proposals + forward_for_single_feature_map + select_over_all_levels
+ * (fcos_outputs.py:1046-1320) with ml_nms -> [D2] batched_nms -> [tv] nms (layers/ml_nms.py:8-31), bit-exact
+ * coordinate-trick IoU. method 0 "cls", 1 "cls_n_ctr", 2 "cls_n_loc". Outputs are [N, out_cap(, k)] + out_cnt[N]. */
+long long ut2_fcos_predict_workspace_bytes(int num_levels, int N, long long L, int C, int K);
+int ut2_fcos_predict_proposals(int num_levels, const int* hw, const int* strides, int N, int C, const void* cls_out,
+                               const void* box_out, int ld, const float* scales, int method, float pre_thr, int pre_topk,
+                               float nms_thr, int post_topk, int out_cap, void* workspace, long long workspace_bytes,
+                               float* out_box, float* out_score, long long* out_cls, float* out_ctr, float* out_conf,
+                               float* out_std, float* out_loc, long long* out_lvl, int* out_cnt, void* stream);
+/* PseudoGenerator.threshold_bbox (mode 0: score > thr0) / threshold_cls_ctr_bbox (mode 1: cls_confid > thr0 and
+ * centerness > thr1) — modeling/pseudo_generator.py:62-131; order-preserving compaction. */
+int ut2_threshold_scatter(int N, int cap, int mode, float thr0, float thr1, const int* in_cnt, const float* box,
+                          const float* score, const long long* cls, const float* ctr, const float* conf,
+                          const float* stdv, int* out_cnt, float* obox, float* oscore, long long* ocls, float* octr,
+                          float* oconf, float* ostd, void* stream);
+
+/* ---------------------------------------------------------------- optimiser / EMA over flat arenas
+ * _update_teacher_model (engine/trainer.py:468-486): teacher = student*(1-keep) + teacher*keep, bit-exact with torch
+ * (both products rounded to fp32, one rounded add). */
+int ut2_ema_update(const float* student, float* teacher, long long n, double keep_rate, void* stream);
+/* torch.optim.SGD as built by [D2] build_optimizer (engine/trainer.py:422-429): g' = grad_scale*g + wd*p;
+ * buf = first ? g' : mom*buf + g'; p -= lr*buf; optionally clears g. */
+int ut2_sgd_step(float* p, float* g, float* buf, long long n, float lr, float momentum, float weight_decay,
+                 int first_step, int zero_grad, float grad_scale, void* stream);
+/* fp32 master weights (channels-last) -> bf16 forward operand [Cout,R,S,Cin] and dgrad operand [Cin,R,S,CoutT]
+ * (taps flipped). The batched form takes a device table of 56-byte records
+ * {int64 src, wf, wt, begin; int32 Cout, Cin, R, S, CoutT, n_off}. */
+int ut2_pack_conv_weight(const float* w, void* wf, void* wt, int Cout, int Cin, int R, int S, int CoutT, void* stream);
+int ut2_pack_conv_weights_batched(const void* descs, int num, long long total, const float* arena, void* packed,
+                                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UT2_H */

@@ -1,0 +1,98 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU and exports every symbol that
+include/ut2.h declares; host logic (config, schedulers, arena layout rules) behaves like the reference's."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "unbiased-teacher-v2_b200", "lib", "libut2_sm100.so")
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "ut2.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ut2_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(LIB):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(LIB)
+    names = declared_symbols()
+    assert len(names) >= 28
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ut2.h but not exported"
+    assert lib.ut2_version() >= 100
+
+
+def test_product_path_fails_loudly_without_library(tmp_path, monkeypatch):
+    from ubteacher import _C
+    monkeypatch.setattr(_C, "_lib", None)
+    monkeypatch.setattr(_C, "LIB_PATH", str(tmp_path / "missing.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _C.lib()
+
+
+def test_model_refuses_cpu_device():
+    from util_cfg import fcos_cfg
+    from ubteacher.modeling import OneStageDetector
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        OneStageDetector(fcos_cfg(**{"MODEL.DEVICE": "cpu"}))
+
+
+def test_config_recipes_resolve_like_the_reference():
+    """Effective values of SURVEY.md A.2 for both shipped sup1 recipes."""
+    from util_cfg import PKG
+    from ubteacher.config import add_ubteacher_config
+    from ubteacher.d2compat.config import get_cfg
+    cfg = get_cfg()
+    add_ubteacher_config(cfg)
+    cfg.merge_from_file(os.path.join(PKG, "configs/FCOS/coco-standard/fcos_R_50_ut2_sup1_run0.yaml"))
+    f, s = cfg.MODEL.FCOS, cfg.SEMISUPNET
+    assert cfg.MODEL.META_ARCHITECTURE == "OneStageDetector" and cfg.MODEL.BACKBONE.NAME == "build_fcos_resnet_fpn_backbone"
+    assert (f.NMS_CRITERIA_TRAIN, f.NMS_CRITERIA_REG_TRAIN, f.NMS_CRITERIA_TEST) == ("cls", "cls_n_loc", "cls_n_ctr")
+    assert f.REG_DISCRETE and f.KL_LOSS and f.KL_LOSS_TYPE == "nlloss" and f.KLLOSS_WEIGHT == 0.05 and not f.CENTER_SAMPLE
+    assert (s.Trainer, s.BURN_UP_STEP, s.EMA_KEEP_RATE, s.UNSUP_LOSS_WEIGHT, s.UNSUP_REG_LOSS_WEIGHT) == \
+        ("ubteacher", 10000, 0.9999, 3.0, 0.2)
+    assert s.TS_BETTER == 0.1 and s.TS_BETTER_CERT == 0.8 and s.CONSIST_REG_LOSS == "ts_locvar_better_nms_nll_l1"
+    assert cfg.SOLVER.AMP.ENABLED and cfg.SOLVER.IMG_PER_BATCH_LABEL == 8 and cfg.INPUT.MIN_SIZE_TRAIN == (400, 1200)
+    r = get_cfg()
+    add_ubteacher_config(r)
+    r.merge_from_file(os.path.join(PKG, "configs/Faster-RCNN/coco-standard/faster_rcnn_R_50_FPN_ut2_sup1_run0.yaml"))
+    assert r.MODEL.META_ARCHITECTURE == "TwoStagePseudoLabGeneralizedRCNN" and r.MODEL.ROI_HEADS.LOSS == "FocalLoss_BoundaryVar"
+    assert r.MODEL.RPN.POSITIVE_FRACTION == 0.25 and r.MODEL.ROI_BOX_HEAD.CLS_AGNOSTIC_BBOX_REG
+    assert (r.SEMISUPNET.BBOX_THRESHOLD, r.SEMISUPNET.EMA_KEEP_RATE, r.SEMISUPNET.BURN_UP_STEP) == (0.7, 0.9996, 2000)
+    r.freeze()
+    with pytest.raises(AttributeError):
+        r.SEED = 3
+
+
+def test_warmup_multistep_lr():
+    from ubteacher.solver.lr_scheduler import WarmupMultiStepLR
+
+    class Opt:
+        param_groups = [{"lr": 0.01, "initial_lr": 0.01}]
+
+    sch = WarmupMultiStepLR(Opt(), (5,), 0.1, 0.001, 4, "linear")
+    lrs = []
+    for _ in range(7):
+        lrs.append(Opt.param_groups[0]["lr"])
+        sch.step()
+    assert abs(lrs[0] - 0.01 * 0.001) < 1e-12 and abs(lrs[2] - 0.01 * (0.001 * 0.5 + 0.5)) < 1e-12
+    assert abs(lrs[4] - 0.01) < 1e-12 and abs(lrs[5] - 0.001) < 1e-12
+
+
+def test_instances_and_imagelist_shims():
+    import torch
+    from ubteacher.d2compat.structures import Boxes, ImageList, Instances
+    a = Instances((10, 20), gt_boxes=Boxes(torch.tensor([[0., 0., 4., 5.], [1., 1., 3., 3.]])), gt_classes=torch.tensor([3, 7]))
+    assert len(a) == 2 and a[torch.tensor([False, True])].gt_classes.tolist() == [7]
+    assert float(a.gt_boxes.area()[0]) == 20.0
+    c = Instances.cat([a, a[0]])
+    assert len(c) == 3 and c.gt_boxes.tensor.shape == (3, 4)
+    il = ImageList.from_tensors([torch.ones(3, 30, 50), torch.ones(3, 33, 40)], 32)
+    assert il.tensor.shape == (2, 3, 64, 64) and il.image_sizes == [(30, 50), (33, 40)]
+    assert float(il.tensor[0, :, 30:, :].abs().sum()) == 0.0
