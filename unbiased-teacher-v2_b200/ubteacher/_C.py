@@ -75,9 +75,18 @@ def call(name, *args):
 
 
 launch_count = 0
+# set to {} by tools/bench to bracket EVERY C-ABI call with CUDA events: {tag: [(start, end), ...]}
+EVENT_PROFILE = None
 
 
-def counted_call(name, *args):
+def counted_call(name, *args, tag=None):
     global launch_count
     launch_count += 1
+    if EVENT_PROFILE is None:
+        call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     call(name, *args)
+    e1.record()
+    EVENT_PROFILE.setdefault(tag or name, []).append((e0, e1))

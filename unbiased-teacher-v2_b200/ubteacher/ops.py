@@ -16,7 +16,11 @@ PROFILE = None
 
 def _timed(kind, flops, name, *args):
     if PROFILE is None:
-        _C.counted_call(name, *args)
+        tag = None
+        if _C.EVENT_PROFILE is not None:   # per-shape breakdown: N,H,W,Cin -> Cout RxS /stride
+            a = args
+            tag = f"{kind} {a[1]}x{a[2]}x{a[3]}x{a[4]}->{a[6]} {a[7]}x{a[8]}/{a[9]}"
+        _C.counted_call(name, *args, tag=tag)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
