@@ -117,8 +117,8 @@ int ut2_threshold_scatter(int N, int cap, int mode, float thr0, float thr1, cons
 int ut2_ema_update(const float* student, float* teacher, long long n, double keep_rate, void* stream);
 /* torch.optim.SGD as built by [D2] build_optimizer (engine/trainer.py:422-429): g' = grad_scale*g + wd*p;
  * buf = first ? g' : mom*buf + g'; p -= lr*buf; optionally clears g. */
-int ut2_sgd_step(float* p, float* g, float* buf, long long n, float lr, float momentum, float weight_decay,
-                 int first_step, int zero_grad, float grad_scale, void* stream);
+int ut2_sgd_step(float* p, float* g, float* buf, long long n, float lr, const float* lr_dev /* overrides lr if set */,
+                 float momentum, float weight_decay, int first_step, int zero_grad, float grad_scale, void* stream);
 /* fp32 master weights (channels-last) -> bf16 forward operand [Cout,R,S,Cin] and dgrad operand [Cin,R,S,CoutT]
  * (taps flipped). The batched form takes a device table of 56-byte records
  * {int64 src, wf, wt, begin; int32 Cout, Cin, R, S, CoutT, n_off}. */

@@ -26,7 +26,9 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KiB
 constexpr int B_BYTES = 256 * BK * 2;       // 32 KiB (block_n <= 256)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_ROW_BYTES = 144;                        // 64 bf16 + 16 B pad: conflict-free row-per-lane access
+constexpr int EPI_STAGE_BYTES = 32 * EPI_ROW_BYTES;       // per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * EPI_STAGE_BYTES;
 constexpr int NUM_THREADS = 192;            // warp0 TMA, warp1 MMA, warps2-5 epilogue
 constexpr int TMEM_COLS = 512;              // 2 accumulator buffers x 256 fp32 columns
 
@@ -142,75 +144,125 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
   } else {
     // -------------------------------------------------- epilogue (4 warps, TMEM lane quadrant = warp % 4)
+    // TMEM gives each lane one output ROW; global memory wants 128-byte row segments per instruction. Each warp
+    // therefore transposes through a private 32 x 64 bf16 staging tile (144-byte row stride, conflict-free):
+    //   (a) residual rows -> staging, coalesced (8 lanes x 16 B per row)
+    //   (c) accumulators (row per lane) + scale/shift + residual + ReLU -> bf16 -> staging
+    //   (e) staging -> global, coalesced, ReLU-backward mask applied on the way out
     const int quad = warp & 3;
+    uint8_t* stage = smem + STAGES * STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
+    const int g = lane & 7, rr = lane >> 3;
     uint32_t acc = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
-      const int m = m_tile * BM + quad * 32 + lane;
+      const int row0 = m_tile * BM + quad * 32;
       const int nbase = n_tile * a.block_n;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
-      for (int c = 0; c < a.block_n; c += 16) {
-        uint32_t v[16];
-        tmem_ld_32x16(taddr + c, v);
-        tmem_ld_wait();
-        const int n0 = nbase + c;
-        if (m < a.M && n0 < a.Cout) {
-          float f[16];
+      for (int c0 = 0; c0 < a.block_n; c0 += 64) {
+        const int cw = min(64, a.block_n - c0);
+        const int n0 = nbase + c0;
+        const bool gcol = (g * 8 < cw) && (n0 + g * 8 < a.Cout);
+        if (a.residual) {
+          uint4 rv[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          if (a.scale) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] *= __ldg(a.scale + n0 + i);
-          }
-          if (a.shift) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] += __ldg(a.shift + n0 + i);
-          }
-          if (a.residual) {
-            size_t rrow = (size_t)m;
-            if (a.res_up2) {
-              const int PQ = a.P * a.Q;
-              const int img = m / PQ, rem = m - img * PQ;
-              const int p = rem / a.Q, q = rem - p * a.Q;
-              rrow = ((size_t)img * (a.P / 2) + (p >> 1)) * (a.Q / 2) + (q >> 1);
-            }
-            const uint4* rp =
-                reinterpret_cast<const uint4*>(a.residual + rrow * a.ldr + n0);
-            uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[i]);
-              f[2 * i] += __low2float(h);
-              f[2 * i + 1] += __high2float(h);
+          for (int ps = 0; ps < 8; ++ps) {
+            const int m = row0 + ps * 4 + rr;
+            rv[ps] = make_uint4(0, 0, 0, 0);
+            if (gcol && m < a.M) {
+              size_t rrow = (size_t)m;
+              if (a.res_up2) {
+                const int PQ = a.P * a.Q;
+                const int img = m / PQ, rem = m - img * PQ;
+                const int p = rem / a.Q, q = rem - p * a.Q;
+                rrow = ((size_t)img * (a.P / 2) + (p >> 1)) * (a.Q / 2) + (q >> 1);
+              }
+              rv[ps] = __ldg(reinterpret_cast<const uint4*>(a.residual + rrow * a.ldr + n0 + g * 8));
             }
           }
-          if (a.relu) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-          }
-          if (a.relu_mask) {
-            const uint4* mp = reinterpret_cast<const uint4*>(a.relu_mask + (size_t)m * a.ldo + n0);
-            uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&mw[i]);
-              if (!(__low2float(h) > 0.f)) f[2 * i] = 0.f;
-              if (!(__high2float(h) > 0.f)) f[2 * i + 1] = 0.f;
-            }
-          }
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-          o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-          o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-          o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-          uint4* op = reinterpret_cast<uint4*>(a.out + (size_t)m * a.ldo + n0);
-          op[0] = o0;
-          op[1] = o1;
+          for (int ps = 0; ps < 8; ++ps)
+            *reinterpret_cast<uint4*>(stage + (ps * 4 + rr) * EPI_ROW_BYTES + g * 16) = rv[ps];
+          __syncwarp();
         }
+        uint32_t v[4][16];
+        tmem_ld_32x16(taddr + c0, v[0]);
+        if (cw > 16) tmem_ld_32x16(taddr + c0 + 16, v[1]);
+        if (cw > 32) tmem_ld_32x16(taddr + c0 + 32, v[2]);
+        if (cw > 48) tmem_ld_32x16(taddr + c0 + 48, v[3]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j * 16 < cw) {
+            const int nj = n0 + j * 16;
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[j][i]);
+            if (nj < a.Cout) {
+              if (a.scale) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] *= __ldg(a.scale + nj + i);
+              }
+              if (a.shift) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] += __ldg(a.shift + nj + i);
+              }
+            }
+            uint4* sp = reinterpret_cast<uint4*>(stage + lane * EPI_ROW_BYTES + j * 32);
+            if (a.residual) {
+              const uint4 r0 = sp[0], r1 = sp[1];
+              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                f[2 * i] += __uint_as_float(rw[i] << 16);
+                f[2 * i + 1] += __uint_as_float(rw[i] & 0xFFFF0000u);
+              }
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            uint4 o0, o1;
+            o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+            o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+            o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+            o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+            sp[0] = o0;
+            sp[1] = o1;
+          }
+        }
+        __syncwarp();
+        uint4 mv[8];
+        if (a.relu_mask) {
+#pragma unroll
+          for (int ps = 0; ps < 8; ++ps) {
+            const int m = row0 + ps * 4 + rr;
+            mv[ps] = make_uint4(0, 0, 0, 0);
+            if (gcol && m < a.M)
+              mv[ps] = __ldg(reinterpret_cast<const uint4*>(a.relu_mask + (size_t)m * a.ldo + n0 + g * 8));
+          }
+        }
+#pragma unroll
+        for (int ps = 0; ps < 8; ++ps) {
+          const int m = row0 + ps * 4 + rr;
+          if (gcol && m < a.M) {
+            uint4 o = *reinterpret_cast<const uint4*>(stage + (ps * 4 + rr) * EPI_ROW_BYTES + g * 16);
+            if (a.relu_mask) {
+              uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+              const uint32_t mw[4] = {mv[ps].x, mv[ps].y, mv[ps].z, mv[ps].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                if ((mw[i] & 0x8000u) || !(mw[i] & 0x7FFFu)) ow[i] &= 0xFFFF0000u;
+                if ((mw[i] & 0x80000000u) || !(mw[i] & 0x7FFF0000u)) ow[i] &= 0x0000FFFFu;
+              }
+              o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+            *reinterpret_cast<uint4*>(a.out + (size_t)m * a.ldo + n0 + g * 8) = o;
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);

@@ -32,8 +32,9 @@ ema_kernel(const float4* __restrict__ s, float4* __restrict__ t, size_t n4, cons
 // torch.optim.SGD(momentum, weight_decay, dampening=0, nesterov=False):
 //   g' = g + wd*p ; buf = first ? g' : mom*buf + g' ; p -= lr*buf ; (optionally g = 0)
 __global__ void __launch_bounds__(256)
-sgd_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf, size_t n, float lr, float mom,
-           float wd, int first, int zero_grad, float gscale) {
+sgd_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf, size_t n, float lr,
+           const float* __restrict__ lr_dev, float mom, float wd, int first, int zero_grad, float gscale) {
+  if (lr_dev) lr = *lr_dev;      // device-resident learning rate: the step can live in a replayed CUDA graph
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float pv = p[i];
     const float gv = g[i] * gscale + wd * pv;
@@ -97,11 +98,11 @@ extern "C" int ut2_ema_update(const float* student, float* teacher, long long n,
   return ut2_check_launch("ema_update");
 }
 
-extern "C" int ut2_sgd_step(float* p, float* g, float* buf, long long n, float lr, float momentum, float weight_decay,
-                            int first_step, int zero_grad, float grad_scale, void* stream) {
+extern "C" int ut2_sgd_step(float* p, float* g, float* buf, long long n, float lr, const float* lr_dev, float momentum,
+                            float weight_decay, int first_step, int zero_grad, float grad_scale, void* stream) {
   if (n <= 0) return 0;
-  sgd_kernel<<<grid_for(n), 256, 0, STREAM>>>(p, g, buf, (size_t)n, lr, momentum, weight_decay, first_step, zero_grad,
-                                              grad_scale);
+  sgd_kernel<<<grid_for(n), 256, 0, STREAM>>>(p, g, buf, (size_t)n, lr, lr_dev, momentum, weight_decay, first_step,
+                                              zero_grad, grad_scale);
   return ut2_check_launch("sgd_step");
 }
 

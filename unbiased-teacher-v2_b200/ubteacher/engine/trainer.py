@@ -41,14 +41,22 @@ class ArenaSGD:
         ]
         self.steps = 0
         self.grad_scale = 1.0
+        dev = model.engine.device
+        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)      # read by the SGD kernel (graph replay)
+        self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     def zero_grad(self, set_to_none=False):
         pass  # the SGD kernel clears the gradient arena in the same pass that consumes it
 
-    def step(self):
+    def push_lr(self):
+        self._lr_host[0] = self.param_groups[0]["lr"]
+        self.lr_dev.copy_(self._lr_host, non_blocking=True)
+
+    def step(self, use_device_lr=False):
         eng = self.model.engine
         eng.sgd_step(self.param_groups[0]["lr"], self.momentum, self.param_groups[0]["weight_decay"],
-                     self.param_groups[1]["weight_decay"], self.steps == 0, self.grad_scale)
+                     self.param_groups[1]["weight_decay"], self.steps == 0, self.grad_scale,
+                     self.lr_dev if use_device_lr else None)
         eng.refresh_operands()
         self.steps += 1
 
@@ -85,6 +93,9 @@ class UBTeacherTrainer:
         self.metrics_period = 20                        # PeriodicWriter period (trainer.py:551)
         self._metric_names, self._metric_buf = None, []
         self.last_losses = None
+        self.use_cuda_graph = False                     # enable_cuda_graph(): replay the whole semi-sup step
+        self._graph = None
+        self._static = None
         if comm.get_world_size() > 1:                   # DDP's initial parameter broadcast
             torch.distributed.broadcast(model.engine.arena.data, 0)
             model.engine.refresh_operands()
@@ -144,10 +155,78 @@ class UBTeacherTrainer:
     # ---------------------------------------------------------------- the step (trainer.py:181-429)
     def run_step_full_semisup(self):
         assert self.model.training, "[UBTeacherTrainer] model was changed to eval mode!"
-        cfg, ss = self.cfg, self.cfg.SEMISUPNET
+        ss = self.cfg.SEMISUPNET
         start = time.perf_counter()
-        label_data_q, label_data_k, unlabel_data_q, unlabel_data_k = next(self._data_loader_iter)
+        data = next(self._data_loader_iter)
         data_time = time.perf_counter() - start
+        if self.use_cuda_graph and self.iter > ss.BURN_UP_STEP and self.optimizer.steps > 0 and \
+                (self.iter - ss.BURN_UP_STEP) % ss.TEACHER_UPDATE_ITER == 0:
+            return self._graph_step(data, data_time)
+        self._step_body(data, data_time)
+
+    # ---------------------------------------------------------------- CUDA-graph replay of the step
+    def enable_cuda_graph(self, flag=True):
+        """The semi-supervised step has no host synchronisation and static shapes (fixed-capacity pseudo-label sets),
+        so after the first eager steps it is captured once and replayed: ~4000 launches per step cost one
+        cudaGraphLaunch. Inputs are copied into static buffers; the learning rate lives in device memory."""
+        self.use_cuda_graph = flag
+        if not flag:
+            self._graph = self._static = None
+
+    def _stage_inputs(self, data):
+        from ..modeling.fcos.fcos_outputs import BoxSet, as_boxset
+        dev = self.model.device
+        lq, lk, uq, uk = data
+        lab = lq + lk
+        gt = lab[0]["instances"] if isinstance(lab[0]["instances"], BoxSet) else as_boxset([d["instances"] for d in lab], dev)
+        imgs = [d["image"] for d in lq + lk + uq + uk]
+        shapes = [tuple(i.shape) for i in imgs] + [tuple(gt.boxes.shape)]
+        if self._static is None:
+            st = {"shapes": shapes, "imgs": [torch.empty(i.shape, dtype=torch.uint8, device=dev) for i in imgs],
+                  "gt": BoxSet(torch.empty_like(gt.boxes), torch.empty_like(gt.classes), torch.empty_like(gt.counts))}
+            n = [len(lq), len(lk), len(uq), len(uk)]
+            o = [0, n[0], n[0] + n[1], n[0] + n[1] + n[2], sum(n)]
+            mk = lambda a, b, with_gt: [dict({"image": t}, **({"instances": st["gt"]} if with_gt else {})) for t in st["imgs"][a:b]]
+            st["data"] = (mk(o[0], o[1], True), mk(o[1], o[2], True), mk(o[2], o[3], False), mk(o[3], o[4], False))
+            self._static = st
+        st = self._static
+        if shapes != st["shapes"]:
+            return None
+        for dst, src in zip(st["imgs"], imgs):
+            dst.copy_(src, non_blocking=True)
+        st["gt"].boxes.copy_(gt.boxes, non_blocking=True)
+        st["gt"].classes.copy_(gt.classes, non_blocking=True)
+        st["gt"].counts.copy_(gt.counts, non_blocking=True)
+        return st["data"]
+
+    def _graph_step(self, data, data_time):
+        static = self._stage_inputs(data)
+        if static is None:                      # a differently shaped batch: run it eagerly
+            return self._step_body(data, data_time)
+        self.optimizer.push_lr()
+        if self._graph is None:
+            from .. import _C
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = _C.launch_count
+            with torch.cuda.graph(g):
+                # fresh dict views for every capture: remove_label/add_label mutate the dicts
+                self._step_body(tuple([dict(d) for d in part] for part in static), 0.0, device_lr=True, bookkeeping=False)
+            self._graph = g
+            self._graph_launches = _C.launch_count - l0
+            _C.launch_count = l0
+            self._graph_names = self.last_losses[0]
+            self._graph_vec = self.last_losses[1]
+        self._graph.replay()
+        from .. import _C
+        _C.launch_count += self._graph_launches      # kernels inside the replayed graph
+        self.optimizer.steps += 1
+        self.last_losses = (self._graph_names, self._graph_vec)
+        self._host_metrics({"data_time": data_time}, self._graph_names, self._graph_vec)
+
+    def _step_body(self, data, data_time, device_lr=False, bookkeeping=True):
+        cfg, ss = self.cfg, self.cfg.SEMISUPNET
+        label_data_q, label_data_k, unlabel_data_q, unlabel_data_k = data
         record = {}
         if self.iter < ss.BURN_UP_STEP:
             losses, pending = self.model.forward_train(label_data_q + label_data_k, "labeled")
@@ -187,11 +266,13 @@ class UBTeacherTrainer:
             self.model.backward_pending(pending_u, [[lam / (lam + 1.0), 0.0, lam / (lam + 1.0), 0.0],
                                                     [0.0, mu / (mu + 1.0), 0.0, 0.0]])
         record["data_time"] = data_time
-        self._write_metrics(record)
+        self._write_metrics(record, bookkeeping)
         if comm.get_world_size() > 1:       # the DDP gradient all-reduce, one contiguous buffer (mean in the SGD kernel)
             torch.distributed.all_reduce(self.model.engine.arena.grad)
         self.optimizer.zero_grad()
-        self.optimizer.step()
+        self.optimizer.step(use_device_lr=device_lr)
+        if not bookkeeping:
+            self.optimizer.steps -= 1       # capture does not execute; _graph_step counts the replays
 
     @staticmethod
     def _threshold(method, t0, t1):
@@ -202,14 +283,18 @@ class UBTeacherTrainer:
         raise ValueError
 
     # ---------------------------------------------------------------- metrics (trainer.py:431-466)
-    def _write_metrics(self, metrics_dict):
+    def _write_metrics(self, metrics_dict, bookkeeping=True):
         names = [k for k, v in metrics_dict.items() if isinstance(v, torch.Tensor)]
         vec = torch.stack([metrics_dict[k].detach().float().reshape(()) for k in names])
         self.last_losses = (names, vec)
+        if bookkeeping:
+            self._host_metrics({k: v for k, v in metrics_dict.items() if not isinstance(v, torch.Tensor)}, names, vec)
+
+    def _host_metrics(self, scalars, names, vec):
         if self.storage is None or (self.iter + 1) % self.metrics_period:
             return
         host = vec.cpu().tolist()                                   # the only D2H of the step
-        md = {k: float(v) for k, v in metrics_dict.items() if not isinstance(v, torch.Tensor)}
+        md = {k: float(v) for k, v in scalars.items()}
         md.update(dict(zip(names, host)))
         all_md = comm.gather(md)
         if comm.is_main_process():

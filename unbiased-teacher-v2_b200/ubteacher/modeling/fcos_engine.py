@@ -444,12 +444,13 @@ class FcosEngine:
         return b["conv1"].dgrad(g1, (H, W), residual=g3)
 
     # ------------------------------------------------------------------------------------ optimiser hooks
-    def sgd_step(self, lr, momentum, wd, wd_norm, first_step, grad_scale=1.0):
+    def sgd_step(self, lr, momentum, wd, wd_norm, first_step, grad_scale=1.0, lr_dev=None):
         A = self.arena
         d0, d1 = A.group_range["decay"]
         n0, n1 = A.group_range["nodecay"]
-        ops.sgd_step(A.data[d0:d1], A.grad[d0:d1], A.mom[d0:d1], lr, momentum, wd, first_step, True, grad_scale)
-        ops.sgd_step(A.data[n0:n1], A.grad[n0:n1], A.mom[n0:n1], lr, momentum, wd_norm, first_step, True, grad_scale)
+        ops.sgd_step(A.data[d0:d1], A.grad[d0:d1], A.mom[d0:d1], lr, momentum, wd, first_step, True, grad_scale, lr_dev)
+        ops.sgd_step(A.data[n0:n1], A.grad[n0:n1], A.mom[n0:n1], lr, momentum, wd_norm, first_step, True, grad_scale,
+                     lr_dev)
 
     def ema_from(self, student, keep_rate):
         ops.ema_update(student.arena.data, self.arena.data, keep_rate)

@@ -49,6 +49,7 @@ class PseudoProposalNetwork(nn.Module):
         self.yield_proposal = cfg.MODEL.FCOS.YIELD_PROPOSAL
         self._trigger = torch.zeros(1, device=dev, requires_grad=True)
         self._params = None
+        self._gout_cache = {}
         self.last_proposals = None
 
     # ---- nn.Module surface backed by the arena -------------------------------------------------
@@ -164,5 +165,10 @@ class OneStageDetector(PseudoProposalNetwork):
 
     def backward_pending(self, pending, weights):
         """weights: one [w_cls, w_loc, w_ctr, 0] float list per loss ctx (the trainer's loss weighting)."""
-        gouts = [torch.tensor(w, dtype=torch.float32).pin_memory().to(self.device, non_blocking=True) for w in weights]
+        gouts = []
+        for w in weights:       # loss weights are config constants: keep them resident (also graph-capture safe)
+            key = tuple(float(v) for v in w)
+            if key not in self._gout_cache:
+                self._gout_cache[key] = torch.tensor(key, dtype=torch.float32, device=self.device)
+            gouts.append(self._gout_cache[key])
         self._run_backward(pending, gouts)

@@ -133,8 +133,8 @@ def ema_update(student_flat, teacher_flat, keep_rate):
     _C.counted_call("ut2_ema_update", student_flat, teacher_flat, i64(student_flat.numel()), f64(keep_rate))
 
 
-def sgd_step(p, g, buf, lr, momentum, wd, first_step, zero_grad=True, grad_scale=1.0):
-    _C.counted_call("ut2_sgd_step", p, g, buf, i64(p.numel()), f32(lr), f32(momentum), f32(wd), int(first_step),
+def sgd_step(p, g, buf, lr, momentum, wd, first_step, zero_grad=True, grad_scale=1.0, lr_dev=None):
+    _C.counted_call("ut2_sgd_step", p, g, buf, i64(p.numel()), f32(lr), lr_dev, f32(momentum), f32(wd), int(first_step),
                     int(zero_grad), f32(grad_scale))
 
 
