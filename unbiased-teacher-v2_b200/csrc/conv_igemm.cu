@@ -22,15 +22,19 @@ namespace ut2 {
 
 constexpr int BM = 128;          // output pixels per tile (UMMA M)
 constexpr int BK = 64;           // K elements per pipeline stage (128 B rows, SWIZZLE_128B)
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KiB
 constexpr int B_BYTES = 256 * BK * 2;       // 32 KiB (block_n <= 256)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_ROW_BYTES = 144;                        // 64 bf16 + 16 B pad: conflict-free row-per-lane access
-constexpr int EPI_STAGE_BYTES = 32 * EPI_ROW_BYTES;       // per epilogue warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * EPI_STAGE_BYTES;
+constexpr int BAR_BYTES = 1024;             // mbarriers + TMEM slot (keeps what follows 1024-aligned)
+constexpr int EPI_TILE_BYTES = 32 * 128;    // one 32-row x 64-col bf16 staging tile, 128B-swizzled
 constexpr int NUM_THREADS = 192;            // warp0 TMA, warp1 MMA, warps2-5 epilogue
 constexpr int TMEM_COLS = 512;              // 2 accumulator buffers x 256 fp32 columns
+
+// shared memory: [stages x 48 KiB operands][barriers][4 x out staging tile][4 x 4 aux tiles (only with aux)]
+constexpr int smem_bytes(int stages, bool aux) {
+  return 1024 + stages * STAGE_BYTES + BAR_BYTES + 4 * EPI_TILE_BYTES + (aux ? 16 * EPI_TILE_BYTES : 0);
+}
 
 struct ConvFwdArgs {
   int M, Cout, ldo;
@@ -38,6 +42,9 @@ struct ConvFwdArgs {
   int P, Q, stride, pad;
   int R, S, Cin;
   int relu;
+  int stages;                       // operand ring depth: 4, or 3 when the aux tiles take their shared memory
+  int aux_kind;                     // 0 none, 1 residual tile via TMA, 2 relu-mask tile via TMA
+  int manual;                       // 1: epilogue with plain loads/stores (res_up2, residual+mask, Cout < 64)
   const float* scale;
   const float* shift;
   const __nv_bfloat16* residual;
@@ -51,18 +58,32 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// 16-byte chunk `c` of row `r` inside a 128B-swizzled [rows][128 B] tile (same pattern TMA SWIZZLE_128B uses)
+__device__ __forceinline__ uint32_t swz(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
+// zero the bf16 halves of `o` whose mask element is not > 0 (sign set or magnitude zero)
+__device__ __forceinline__ uint32_t mask_bf16x2(uint32_t o, uint32_t m) {
+  if ((m & 0x8000u) || !(m & 0x7FFFu)) o &= 0xFFFF0000u;
+  if ((m & 0x80000000u) || !(m & 0x7FFF0000u)) o &= 0x0000FFFFu;
+  return o;
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
                 const ConvFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int STAGES = a.stages;
+  uint8_t* bar_base = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2]
+  uint64_t* aux_bar = tempty_bar + 2;             // [4] one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 4);
+  uint8_t* out_stage = bar_base + BAR_BYTES;                 // 4 x 4 KiB
+  uint8_t* aux_stage = out_stage + 4 * EPI_TILE_BYTES;       // 4 x 16 KiB (aux_kind != 0 only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -73,6 +94,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
     prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_out);
+    if (a.aux_kind) prefetch_tmap(&tmap_aux);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -81,6 +104,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 128);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -111,7 +135,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                              (uint16_t)r);
           tma_load_2d(sa + A_BYTES, &tmap_w, &full_bar[stage], tap * a.Cin + c0,
                       n_tile * a.block_n);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -136,7 +160,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -144,54 +168,75 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
   } else {
     // -------------------------------------------------- epilogue (4 warps, TMEM lane quadrant = warp % 4)
-    // TMEM gives each lane one output ROW; global memory wants 128-byte row segments per instruction. Each warp
-    // therefore transposes through a private 32 x 64 bf16 staging tile (144-byte row stride, conflict-free):
-    //   (a) residual rows -> staging, coalesced (8 lanes x 16 B per row)
-    //   (c) accumulators (row per lane) + scale/shift + residual + ReLU -> bf16 -> staging
-    //   (e) staging -> global, coalesced, ReLU-backward mask applied on the way out
+    // TMEM hands each lane one output ROW; global memory wants whole 128-byte row segments. Every warp owns a
+    // 32-row x 64-column bf16 staging tile (128B-swizzled, conflict-free for row-per-lane access):
+    //   fast path   : accumulators (+ residual / ReLU-mask tile that TMA prefetched one tile ahead) -> staging ->
+    //                 one TMA store per 64 columns (asynchronous, hardware-coalesced, clipped at the tensor edge)
+    //   manual path : residual gathered with plain loads (nearest-2x upsampled FPN residual), plain coalesced stores
     const int quad = warp & 3;
-    uint8_t* stage = smem + STAGES * STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
+    const int ew = warp - 2;                                   // staging slot
+    uint8_t* ostage = out_stage + ew * EPI_TILE_BYTES;
+    uint8_t* astage = aux_stage + ew * 4 * EPI_TILE_BYTES;
+    const int nchunks = (a.block_n + 63) / 64;
+    const uint32_t aux_bytes = nchunks * EPI_TILE_BYTES;
     const int g = lane & 7, rr = lane >> 3;
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, aux_phase = 0;
+    if (a.aux_kind && !a.manual && lane == 0 && (int)blockIdx.x < num_tiles) {   // aux tiles of the first tile
+      const int t = blockIdx.x;
+      const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
+      mbar_arrive_expect_tx(&aux_bar[ew], aux_bytes);
+      for (int c = 0; c < nchunks; ++c)
+        tma_load_2d(astage + c * EPI_TILE_BYTES, &tmap_aux, &aux_bar[ew], n_tile * a.block_n + c * 64,
+                    m_tile * BM + quad * 32);
+    }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
       const int row0 = m_tile * BM + quad * 32;
       const int nbase = n_tile * a.block_n;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (a.aux_kind && !a.manual) mbar_wait(&aux_bar[ew], aux_phase);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
       for (int c0 = 0; c0 < a.block_n; c0 += 64) {
         const int cw = min(64, a.block_n - c0);
         const int n0 = nbase + c0;
         const bool gcol = (g * 8 < cw) && (n0 + g * 8 < a.Cout);
-        if (a.residual) {
-          uint4 rv[8];
-#pragma unroll
-          for (int ps = 0; ps < 8; ++ps) {
-            const int m = row0 + ps * 4 + rr;
-            rv[ps] = make_uint4(0, 0, 0, 0);
-            if (gcol && m < a.M) {
-              size_t rrow = (size_t)m;
-              if (a.res_up2) {
-                const int PQ = a.P * a.Q;
-                const int img = m / PQ, rem = m - img * PQ;
-                const int p = rem / a.Q, q = rem - p * a.Q;
-                rrow = ((size_t)img * (a.P / 2) + (p >> 1)) * (a.Q / 2) + (q >> 1);
-              }
-              rv[ps] = __ldg(reinterpret_cast<const uint4*>(a.residual + rrow * a.ldr + n0 + g * 8));
-            }
-          }
-#pragma unroll
-          for (int ps = 0; ps < 8; ++ps)
-            *reinterpret_cast<uint4*>(stage + (ps * 4 + rr) * EPI_ROW_BYTES + g * 16) = rv[ps];
-          __syncwarp();
-        }
         uint32_t v[4][16];
         tmem_ld_32x16(taddr + c0, v[0]);
         if (cw > 16) tmem_ld_32x16(taddr + c0 + 16, v[1]);
         if (cw > 32) tmem_ld_32x16(taddr + c0 + 32, v[2]);
         if (cw > 48) tmem_ld_32x16(taddr + c0 + 48, v[3]);
+        if (a.manual) {
+          if (a.residual) {          // (a) residual rows -> staging, coalesced
+            uint4 rv[8];
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+              const int m = row0 + ps * 4 + rr;
+              rv[ps] = make_uint4(0, 0, 0, 0);
+              if (gcol && m < a.M) {
+                size_t rrow = (size_t)m;
+                if (a.res_up2) {
+                  const int PQ = a.P * a.Q;
+                  const int img = m / PQ, rem = m - img * PQ;
+                  const int p = rem / a.Q, q = rem - p * a.Q;
+                  rrow = ((size_t)img * (a.P / 2) + (p >> 1)) * (a.Q / 2) + (q >> 1);
+                }
+                rv[ps] = __ldg(reinterpret_cast<const uint4*>(a.residual + rrow * a.ldr + n0 + g * 8));
+              }
+            }
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps)
+              *reinterpret_cast<uint4*>(ostage + swz(ps * 4 + rr, g)) = rv[ps];
+            __syncwarp();
+          }
+        } else {
+          // the previous chunk's TMA store must have drained the staging tile before it is overwritten
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
         tmem_ld_wait();
+        const uint8_t* rsrc = a.manual ? ostage : astage + (c0 >> 6) * EPI_TILE_BYTES;
+        const int kind = a.manual ? (a.residual ? 1 : 0) : a.aux_kind;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (j * 16 < cw) {
@@ -209,65 +254,88 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                 for (int i = 0; i < 16; ++i) f[i] += __ldg(a.shift + nj + i);
               }
             }
-            uint4* sp = reinterpret_cast<uint4*>(stage + lane * EPI_ROW_BYTES + j * 32);
-            if (a.residual) {
-              const uint4 r0 = sp[0], r1 = sp[1];
-              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
+            if (kind) {
+              x0 = *reinterpret_cast<const uint4*>(rsrc + swz(lane, 2 * j));
+              x1 = *reinterpret_cast<const uint4*>(rsrc + swz(lane, 2 * j + 1));
+            }
+            const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            if (kind == 1) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                f[2 * i] += __uint_as_float(rw[i] << 16);
-                f[2 * i + 1] += __uint_as_float(rw[i] & 0xFFFF0000u);
+                f[2 * i] += __uint_as_float(xw[i] << 16);
+                f[2 * i + 1] += __uint_as_float(xw[i] & 0xFFFF0000u);
               }
             }
             if (a.relu) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
             }
-            uint4 o0, o1;
-            o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-            o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-            o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-            o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-            sp[0] = o0;
-            sp[1] = o1;
+            uint32_t ow[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ow[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+            if (kind == 2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ow[i] = mask_bf16x2(ow[i], xw[i]);
+            }
+            *reinterpret_cast<uint4*>(ostage + swz(lane, 2 * j)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            *reinterpret_cast<uint4*>(ostage + swz(lane, 2 * j + 1)) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
           }
         }
-        __syncwarp();
-        uint4 mv[8];
-        if (a.relu_mask) {
+        if (!a.manual) {
+          fence_proxy_async();          // generic-proxy writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmap_out)),
+                         "r"(n0), "r"(row0), "r"(smem_u32(ostage))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else {
+          __syncwarp();
+          uint4 mv[8];
+          if (a.relu_mask) {
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+              const int m = row0 + ps * 4 + rr;
+              mv[ps] = make_uint4(0, 0, 0, 0);
+              if (gcol && m < a.M)
+                mv[ps] = __ldg(reinterpret_cast<const uint4*>(a.relu_mask + (size_t)m * a.ldo + n0 + g * 8));
+            }
+          }
 #pragma unroll
           for (int ps = 0; ps < 8; ++ps) {
             const int m = row0 + ps * 4 + rr;
-            mv[ps] = make_uint4(0, 0, 0, 0);
-            if (gcol && m < a.M)
-              mv[ps] = __ldg(reinterpret_cast<const uint4*>(a.relu_mask + (size_t)m * a.ldo + n0 + g * 8));
-          }
-        }
-#pragma unroll
-        for (int ps = 0; ps < 8; ++ps) {
-          const int m = row0 + ps * 4 + rr;
-          if (gcol && m < a.M) {
-            uint4 o = *reinterpret_cast<const uint4*>(stage + (ps * 4 + rr) * EPI_ROW_BYTES + g * 16);
-            if (a.relu_mask) {
-              uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-              const uint32_t mw[4] = {mv[ps].x, mv[ps].y, mv[ps].z, mv[ps].w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                if ((mw[i] & 0x8000u) || !(mw[i] & 0x7FFFu)) ow[i] &= 0xFFFF0000u;
-                if ((mw[i] & 0x80000000u) || !(mw[i] & 0x7FFF0000u)) ow[i] &= 0x0000FFFFu;
-              }
-              o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            if (gcol && m < a.M) {
+              uint4 o = *reinterpret_cast<const uint4*>(ostage + swz(ps * 4 + rr, g));
+              if (a.relu_mask)
+                o = make_uint4(mask_bf16x2(o.x, mv[ps].x), mask_bf16x2(o.y, mv[ps].y), mask_bf16x2(o.z, mv[ps].z),
+                               mask_bf16x2(o.w, mv[ps].w));
+              *reinterpret_cast<uint4*>(a.out + (size_t)m * a.ldo + n0 + g * 8) = o;
             }
-            *reinterpret_cast<uint4*>(a.out + (size_t)m * a.ldo + n0 + g * 8) = o;
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
+      // accumulators consumed: release the TMEM buffer, then prefetch the aux tiles of this CTA's next tile
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (a.aux_kind && !a.manual) {
+        aux_phase ^= 1;
+        __syncwarp();                   // every lane finished reading the aux tiles
+        const int tn = t + gridDim.x;
+        if (lane == 0 && tn < num_tiles) {
+          const int n_tile2 = tn % a.n_tiles, m_tile2 = tn / a.n_tiles;
+          mbar_arrive_expect_tx(&aux_bar[ew], aux_bytes);
+          for (int c = 0; c < nchunks; ++c)
+            tma_load_2d(astage + c * EPI_TILE_BYTES, &tmap_aux, &aux_bar[ew], n_tile2 * a.block_n + c * 64,
+                        m_tile2 * BM + quad * 32);
+        }
+      }
     }
+    if (!a.manual && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -279,6 +347,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------ wgrad
+constexpr int STAGES = 4;                       // wgrad operand ring depth
 constexpr int WG_PIX = 64;                      // pixels (GEMM-K) per stage
 constexpr int WG_BLK_BYTES = WG_PIX * 64 * 2;   // one [64 pix][64 ch] swizzled block = 8 KiB
 constexpr int WG_A_BYTES = 2 * WG_BLK_BYTES;    // 128 output channels
@@ -473,20 +542,33 @@ extern "C" int ut2_conv2d_nhwc_bf16_fwd(const void* x, int N, int H, int W, int 
   a.res_up2 = res_up2; a.relu_mask = static_cast<const __nv_bfloat16*>(relu_mask);
   if (res_up2 && ((P & 1) || (Q & 1))) return ut2_fail(-4, "conv_fwd: res_up2 needs even output H, W");
   a.out = static_cast<__nv_bfloat16*>(y);
-  CUtensorMap tx, tw;
+  a.manual = (Cout < 64) || (residual && res_up2) || (residual && relu_mask);
+  a.aux_kind = a.manual ? 0 : (residual ? 1 : (relu_mask ? 2 : 0));
+  a.stages = a.aux_kind ? 3 : 4;
+  CUtensorMap tx, tw, to, ta;
   int rc = make_tmap_im2col_bf16(&tx, x, N, H, W, Cin, R, S, stride, pad, 64, BM);
   if (rc) return ut2_fail(rc, "conv_fwd: activation tensor map encode failed");
   rc = make_tmap_2d_bf16(&tw, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64, block_n);
   if (rc) return ut2_fail(rc, "conv_fwd: weight tensor map encode failed");
+  const uint32_t bc = Cout < 64 ? Cout : 64;
+  rc = make_tmap_2d_bf16(&to, y, a.M, Cout, Cout, bc, 32);
+  if (rc) return ut2_fail(rc, "conv_fwd: output tensor map encode failed");
+  ta = to;
+  if (a.aux_kind) {
+    rc = make_tmap_2d_bf16(&ta, a.aux_kind == 1 ? residual : relu_mask, a.M, Cout, Cout, bc, 32);
+    if (rc) return ut2_fail(rc, "conv_fwd: aux tensor map encode failed");
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes(3, true) > smem_bytes(4, false) ? smem_bytes(3, true) : smem_bytes(4, false));
     if (e != cudaSuccess) return ut2_fail((int)e, "conv_fwd: cudaFuncSetAttribute");
     attr_set = true;
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tx, tw, a);
+  conv_fwd_kernel<<<grid, NUM_THREADS, smem_bytes(a.stages, a.aux_kind != 0), static_cast<cudaStream_t>(stream)>>>(
+      tx, tw, to, ta, a);
   return ut2_check_launch("conv_fwd");
 }
 
