@@ -51,6 +51,10 @@ int ut2_debug_im2col_probe(const void* x, int N, int H, int W, int C, int R, int
 int ut2_stem_conv_u8(const void* img_chw, int h, int w, const float* wgt_rsck, const float* scale, const float* shift,
                      float mean0, float mean1, float mean2, float std0, float std1, float std2, void* out, int P, int Q,
                      void* stream);
+/* same contract on the tensor cores (implicit GEMM, K = 147 padded to 192, bf16 inputs, fp32 accumulate) */
+int ut2_stem_conv_u8_tc(const void* img_chw, int h, int w, const float* wgt_rsck, const float* scale, const float* shift,
+                        float mean0, float mean1, float mean2, float std0, float std1, float std2, void* out, int P, int Q,
+                        void* stream);
 int ut2_maxpool3x3s2_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream);          /* [D2] BasicStem max_pool2d */
 int ut2_upsample2x_add_nhwc(const void* lat, const void* top, void* out, int N, int H, int W, int C, void* stream); /* [D2] FPN top-down */
 int ut2_downsample2x_sum_nhwc(const void* g, const void* addend, void* gtop, int N, int Ht, int Wt, int C, void* stream);

@@ -33,7 +33,7 @@ constexpr int TMEM_COLS = 512;              // 2 accumulator buffers x 256 fp32 
 
 // shared memory: [stages x 48 KiB operands][barriers][4 x out staging tile][4 x 4 aux tiles (only with aux)]
 constexpr int smem_bytes(int stages, bool aux) {
-  return 1024 + stages * STAGE_BYTES + BAR_BYTES + 4 * EPI_TILE_BYTES + (aux ? 16 * EPI_TILE_BYTES : 0);
+  return 1024 + stages * STAGE_BYTES + BAR_BYTES + (aux ? 4 + 16 : 8) * EPI_TILE_BYTES;
 }
 
 struct ConvFwdArgs {
@@ -82,7 +82,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
   uint64_t* aux_bar = tempty_bar + 2;             // [4] one per epilogue warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 4);
-  uint8_t* out_stage = bar_base + BAR_BYTES;                 // 4 x 4 KiB
+  uint8_t* out_stage = bar_base + BAR_BYTES;                 // 4 x 4 KiB (x2, double-buffered, when there is no aux)
   uint8_t* aux_stage = out_stage + 4 * EPI_TILE_BYTES;       // 4 x 16 KiB (aux_kind != 0 only)
 
   const int warp = threadIdx.x >> 5;
@@ -175,7 +175,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     //   manual path : residual gathered with plain loads (nearest-2x upsampled FPN residual), plain coalesced stores
     const int quad = warp & 3;
     const int ew = warp - 2;                                   // staging slot
-    uint8_t* ostage = out_stage + ew * EPI_TILE_BYTES;
+    const int oslots = (a.aux_kind || a.manual) ? 1 : 2;
+    uint8_t* ostage0 = out_stage + ew * oslots * EPI_TILE_BYTES;
+    uint8_t* ostage = ostage0;
+    uint32_t oslot = 0;
     uint8_t* astage = aux_stage + ew * 4 * EPI_TILE_BYTES;
     const int nchunks = (a.block_n + 63) / 64;
     const uint32_t aux_bytes = nchunks * EPI_TILE_BYTES;
@@ -230,8 +233,11 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             __syncwarp();
           }
         } else {
-          // the previous chunk's TMA store must have drained the staging tile before it is overwritten
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          // the TMA store that last used this staging slot must have drained it before it is overwritten
+          if (lane == 0) {
+            if (oslots == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
           __syncwarp();
         }
         tmem_ld_wait();
@@ -247,11 +253,17 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             if (nj < a.Cout) {
               if (a.scale) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] *= __ldg(a.scale + nj + i);
+                for (int i = 0; i < 4; ++i) {
+                  const float4 sv = __ldg(reinterpret_cast<const float4*>(a.scale + nj) + i);
+                  f[4 * i] *= sv.x; f[4 * i + 1] *= sv.y; f[4 * i + 2] *= sv.z; f[4 * i + 3] *= sv.w;
+                }
               }
               if (a.shift) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] += __ldg(a.shift + nj + i);
+                for (int i = 0; i < 4; ++i) {
+                  const float4 sv = __ldg(reinterpret_cast<const float4*>(a.shift + nj) + i);
+                  f[4 * i] += sv.x; f[4 * i + 1] += sv.y; f[4 * i + 2] += sv.z; f[4 * i + 3] += sv.w;
+                }
               }
             }
             uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
@@ -292,6 +304,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          if (oslots == 2) { oslot ^= 1; ostage = ostage0 + oslot * EPI_TILE_BYTES; }
         } else {
           __syncwarp();
           uint4 mv[8];
@@ -588,8 +601,10 @@ extern "C" int ut2_conv2d_nhwc_bf16_wgrad(const void* x, int N, int H, int W, in
   a.c_tiles = Cin / a.block_n; a.n_tiles = (Cout + 127) / 128; a.taps = R * S;
   a.kb_total = (a.Mpix + WG_PIX - 1) / WG_PIX;
   const int out_tiles = a.c_tiles * a.n_tiles * a.taps;
-  int splits = (2 * num_sms() + out_tiles - 1) / out_tiles;
-  if (splits > a.kb_total) splits = a.kb_total;
+  // split-K so that the grid is (at most) one full wave of CTAs, but keep >= 32 pixel blocks per CTA: the fp32
+  // atomic epilogue (128 x block_n values per CTA) must stay small next to the main loop
+  int splits = num_sms() / out_tiles;
+  if (splits > a.kb_total / 32) splits = a.kb_total / 32;
   if (splits < 1) splits = 1;
   a.kb_per_split = (a.kb_total + splits - 1) / splits;
   splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;

@@ -73,9 +73,10 @@ def groupnorm_relu_bwd(dy, x, stats, gamma, beta, dgamma, dbeta, eps=1e-5, relu=
     return dx
 
 
-def stem_conv(img_u8_chw, w_rsck, scale, shift, mean, std, out_slice, P, Q):
+def stem_conv(img_u8_chw, w_rsck, scale, shift, mean, std, out_slice, P, Q, tensor_core=True):
+    """tensor_core=True: tcgen05 implicit GEMM (bf16 inputs); False: the fp32 CUDA-core kernel."""
     _, h, w = img_u8_chw.shape
-    _C.counted_call("ut2_stem_conv_u8", img_u8_chw, h, w, w_rsck, scale, shift, f32(mean[0]), f32(mean[1]),
+    _C.counted_call("ut2_stem_conv_u8_tc" if tensor_core else "ut2_stem_conv_u8", img_u8_chw, h, w, w_rsck, scale, shift, f32(mean[0]), f32(mean[1]),
                     f32(mean[2]), f32(std[0]), f32(std[1]), f32(std[2]), out_slice, P, Q)
 
 
