@@ -33,7 +33,7 @@ constexpr int TMEM_COLS = 512;              // 2 accumulator buffers x 256 fp32 
 
 // shared memory: [stages x 48 KiB operands][barriers][4 x out staging tile][4 x 4 aux tiles (only with aux)]
 constexpr int smem_bytes(int stages, bool aux) {
-  return 1024 + stages * STAGE_BYTES + BAR_BYTES + (aux ? 4 + 16 : 8) * EPI_TILE_BYTES;
+  return 1024 + stages * STAGE_BYTES + BAR_BYTES + (aux ? 4 + 16 : 4) * EPI_TILE_BYTES;
 }
 
 struct ConvFwdArgs {
@@ -171,14 +171,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     // TMEM hands each lane one output ROW; global memory wants whole 128-byte row segments. Every warp owns a
     // 32-row x 64-column bf16 staging tile (128B-swizzled, conflict-free for row-per-lane access):
     //   fast path   : accumulators (+ residual / ReLU-mask tile that TMA prefetched one tile ahead) -> staging ->
-    //                 one TMA store per 64 columns (asynchronous, hardware-coalesced, clipped at the tensor edge)
-    //   manual path : residual gathered with plain loads (nearest-2x upsampled FPN residual), plain coalesced stores
+    //                 coalesced 16-byte stores (fire-and-forget; measured faster than TMA stores, whose completion
+    //                 latency caps the bytes in flight per SM)
+    //   manual path : residual gathered with plain loads (nearest-2x upsampled FPN residual), mask applied on the way out
     const int quad = warp & 3;
     const int ew = warp - 2;                                   // staging slot
-    const int oslots = (a.aux_kind || a.manual) ? 1 : 2;
-    uint8_t* ostage0 = out_stage + ew * oslots * EPI_TILE_BYTES;
-    uint8_t* ostage = ostage0;
-    uint32_t oslot = 0;
+    uint8_t* ostage = out_stage + ew * EPI_TILE_BYTES;
     uint8_t* astage = aux_stage + ew * 4 * EPI_TILE_BYTES;
     const int nchunks = (a.block_n + 63) / 64;
     const uint32_t aux_bytes = nchunks * EPI_TILE_BYTES;
@@ -232,13 +230,6 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
               *reinterpret_cast<uint4*>(ostage + swz(ps * 4 + rr, g)) = rv[ps];
             __syncwarp();
           }
-        } else {
-          // the TMA store that last used this staging slot must have drained it before it is overwritten
-          if (lane == 0) {
-            if (oslots == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          }
-          __syncwarp();
         }
         tmem_ld_wait();
         const uint8_t* rsrc = a.manual ? ostage : astage + (c0 >> 6) * EPI_TILE_BYTES;
@@ -294,21 +285,11 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             *reinterpret_cast<uint4*>(ostage + swz(lane, 2 * j + 1)) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
           }
         }
-        if (!a.manual) {
-          fence_proxy_async();          // generic-proxy writes -> visible to the TMA (async proxy)
-          __syncwarp();
-          if (lane == 0) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                             reinterpret_cast<uint64_t>(&tmap_out)),
-                         "r"(n0), "r"(row0), "r"(smem_u32(ostage))
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          if (oslots == 2) { oslot ^= 1; ostage = ostage0 + oslot * EPI_TILE_BYTES; }
-        } else {
+        {
+          // (e) staging -> global: 8 lanes x 16 B cover one 128-byte row segment, 4 rows per pass, fire-and-forget
           __syncwarp();
           uint4 mv[8];
-          if (a.relu_mask) {
+          if (a.manual && a.relu_mask) {
 #pragma unroll
             for (int ps = 0; ps < 8; ++ps) {
               const int m = row0 + ps * 4 + rr;
@@ -322,7 +303,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             const int m = row0 + ps * 4 + rr;
             if (gcol && m < a.M) {
               uint4 o = *reinterpret_cast<const uint4*>(ostage + swz(ps * 4 + rr, g));
-              if (a.relu_mask)
+              if (a.manual && a.relu_mask)
                 o = make_uint4(mask_bf16x2(o.x, mv[ps].x), mask_bf16x2(o.y, mv[ps].y), mask_bf16x2(o.z, mv[ps].z),
                                mask_bf16x2(o.w, mv[ps].w));
               *reinterpret_cast<uint4*>(a.out + (size_t)m * a.ldo + n0 + g * 8) = o;
@@ -348,7 +329,6 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         }
       }
     }
-    if (!a.manual && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();

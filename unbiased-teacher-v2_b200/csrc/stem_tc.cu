@@ -62,23 +62,35 @@ stem_tc_kernel(const uint8_t* __restrict__ img, int h, int w, const float* __res
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const float mean[3] = {m0, m1, m2}, istd[3] = {is0, is1, is2};
   const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
-  float sc[64 / 4], sh[64 / 4];   // per-thread slice is loaded in the epilogue instead (kept tiny here)
-  (void)sc; (void)sh;
   uint32_t parity = 0;
   const int num_tiles = P * tiles_per_row;
   for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
     const int p = t / tiles_per_row, q0 = (t - p * tiles_per_row) * ST_PIX;
     const int ih0 = 2 * p - 3, iw0 = 2 * q0 - 3;
     // 1. normalised input patch [3][7][ST_PW] (zero outside the image: conv padding and ImageList padding)
-    for (int i = tid; i < 3 * 7 * ST_PW; i += 128) {
-      const int c = i / (7 * ST_PW), r = (i / ST_PW) % 7, col = i % ST_PW;
-      const int ih = ih0 + r, iw = iw0 + col;
-      float v = 0.f;
-      if (ih >= 0 && ih < h && iw >= 0 && iw < w)
-        v = (static_cast<float>(__ldg(img + (size_t)c * h * w + (size_t)ih * w + iw)) - mean[c]) * istd[c];
-      patch[i] = __float2bfloat16_rn(v);
+    {
+      // 21 patch rows of ST_PW bytes: all loads of a thread are issued before any is consumed (latency overlap)
+      constexpr int PER = (3 * 7 * ST_PW + 127) / 128;     // 44
+      int raw[PER];
+#pragma unroll
+      for (int it = 0; it < PER; ++it) {
+        const int i = it * 128 + tid;
+        const int c = i / (7 * ST_PW), r = (i / ST_PW) % 7, col = i % ST_PW;
+        const int ih = ih0 + r, iw = iw0 + col;
+        raw[it] = -1;
+        if (i < 3 * 7 * ST_PW && ih >= 0 && ih < h && iw >= 0 && iw < w)
+          raw[it] = __ldg(img + (size_t)c * h * w + (size_t)ih * w + iw);
+      }
+#pragma unroll
+      for (int it = 0; it < PER; ++it) {
+        const int i = it * 128 + tid;
+        if (i < 3 * 7 * ST_PW) {
+          const int c = i / (7 * ST_PW);
+          const float mc = c == 0 ? m0 : (c == 1 ? m1 : m2), sc_ = c == 0 ? is0 : (c == 1 ? is1 : is2);
+          patch[i] = __float2bfloat16_rn(raw[it] < 0 ? 0.f : (static_cast<float>(raw[it]) - mc) * sc_);
+        }
+      }
     }
     __syncthreads();
     // 2. this thread's pixel row of A: 19 chunks of 8 k-values, k = (r*7 + s)*3 + c  ->  patch[c][r][2*tid + s]
