@@ -31,9 +31,9 @@ constexpr int EPI_TILE_BYTES = 32 * 128;    // one 32-row x 64-col bf16 staging 
 constexpr int NUM_THREADS = 192;            // warp0 TMA, warp1 MMA, warps2-5 epilogue
 constexpr int TMEM_COLS = 512;              // 2 accumulator buffers x 256 fp32 columns
 
-// shared memory: [stages x 48 KiB operands][barriers][4 x out staging tile][4 x 4 aux tiles (only with aux)]
+// shared memory: [stages x 48 KiB operands][barriers][4 warps x 4 aux tiles of 4 KiB (only with aux)]
 constexpr int smem_bytes(int stages, bool aux) {
-  return 1024 + stages * STAGE_BYTES + BAR_BYTES + (aux ? 4 + 16 : 4) * EPI_TILE_BYTES;
+  return 1024 + stages * STAGE_BYTES + BAR_BYTES + (aux ? 16 : 0) * EPI_TILE_BYTES;
 }
 
 struct ConvFwdArgs {
@@ -82,8 +82,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
   uint64_t* aux_bar = tempty_bar + 2;             // [4] one per epilogue warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 4);
-  uint8_t* out_stage = bar_base + BAR_BYTES;                 // 4 x 4 KiB (x2, double-buffered, when there is no aux)
-  uint8_t* aux_stage = out_stage + 4 * EPI_TILE_BYTES;       // 4 x 16 KiB (aux_kind != 0 only)
+  uint8_t* aux_stage = bar_base + BAR_BYTES;                 // 4 warps x 4 tiles x 4 KiB (aux_kind != 0 only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,7 +93,6 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
     prefetch_tmap(&tmap_w);
-    prefetch_tmap(&tmap_out);
     if (a.aux_kind) prefetch_tmap(&tmap_aux);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -168,21 +166,19 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
   } else {
     // -------------------------------------------------- epilogue (4 warps, TMEM lane quadrant = warp % 4)
-    // TMEM hands each lane one output ROW; global memory wants whole 128-byte row segments. Every warp owns a
-    // 32-row x 64-column bf16 staging tile (128B-swizzled, conflict-free for row-per-lane access):
-    //   fast path   : accumulators (+ residual / ReLU-mask tile that TMA prefetched one tile ahead) -> staging ->
-    //                 coalesced 16-byte stores (fire-and-forget; measured faster than TMA stores, whose completion
-    //                 latency caps the bytes in flight per SM)
-    //   manual path : residual gathered with plain loads (nearest-2x upsampled FPN residual), mask applied on the way out
+    // TMEM hands each lane one output ROW. Stores go straight from registers (32-byte sectors per lane: measured
+    // faster than staging + coalesced or TMA stores — L2 merges the sectors and nothing waits on a store). What must
+    // NOT sit in the dependency chain is the residual / ReLU-mask read: those tiles are TMA-prefetched into a
+    // 128B-swizzled shared-memory tile one output tile ahead and read row-per-lane without bank conflicts. The
+    // "manual" path (nearest-2x upsampled FPN residual, residual + mask together, Cout < 64) uses plain loads.
     const int quad = warp & 3;
-    const int ew = warp - 2;                                   // staging slot
-    uint8_t* ostage = out_stage + ew * EPI_TILE_BYTES;
+    const int ew = warp - 2;
     uint8_t* astage = aux_stage + ew * 4 * EPI_TILE_BYTES;
     const int nchunks = (a.block_n + 63) / 64;
     const uint32_t aux_bytes = nchunks * EPI_TILE_BYTES;
-    const int g = lane & 7, rr = lane >> 3;
+    const bool use_aux = a.aux_kind != 0;
     uint32_t acc = 0, acc_phase = 0, aux_phase = 0;
-    if (a.aux_kind && !a.manual && lane == 0 && (int)blockIdx.x < num_tiles) {   // aux tiles of the first tile
+    if (use_aux && lane == 0 && (int)blockIdx.x < num_tiles) {   // aux tiles of this CTA's first tile
       const int t = blockIdx.x;
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
       mbar_arrive_expect_tx(&aux_bar[ew], aux_bytes);
@@ -192,78 +188,67 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
-      const int row0 = m_tile * BM + quad * 32;
+      const int m = m_tile * BM + quad * 32 + lane;
       const int nbase = n_tile * a.block_n;
+      size_t rrow = (size_t)m;                 // residual row for the manual path
+      if (a.manual && a.residual && a.res_up2 && m < a.M) {
+        const int PQ = a.P * a.Q;
+        const int img = m / PQ, rem = m - img * PQ;
+        const int p = rem / a.Q, q = rem - p * a.Q;
+        rrow = ((size_t)img * (a.P / 2) + (p >> 1)) * (a.Q / 2) + (q >> 1);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      if (a.aux_kind && !a.manual) mbar_wait(&aux_bar[ew], aux_phase);
+      if (use_aux) mbar_wait(&aux_bar[ew], aux_phase);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
       for (int c0 = 0; c0 < a.block_n; c0 += 64) {
         const int cw = min(64, a.block_n - c0);
-        const int n0 = nbase + c0;
-        const bool gcol = (g * 8 < cw) && (n0 + g * 8 < a.Cout);
         uint32_t v[4][16];
         tmem_ld_32x16(taddr + c0, v[0]);
         if (cw > 16) tmem_ld_32x16(taddr + c0 + 16, v[1]);
         if (cw > 32) tmem_ld_32x16(taddr + c0 + 32, v[2]);
         if (cw > 48) tmem_ld_32x16(taddr + c0 + 48, v[3]);
-        if (a.manual) {
-          if (a.residual) {          // (a) residual rows -> staging, coalesced
-            uint4 rv[8];
-#pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-              const int m = row0 + ps * 4 + rr;
-              rv[ps] = make_uint4(0, 0, 0, 0);
-              if (gcol && m < a.M) {
-                size_t rrow = (size_t)m;
-                if (a.res_up2) {
-                  const int PQ = a.P * a.Q;
-                  const int img = m / PQ, rem = m - img * PQ;
-                  const int p = rem / a.Q, q = rem - p * a.Q;
-                  rrow = ((size_t)img * (a.P / 2) + (p >> 1)) * (a.Q / 2) + (q >> 1);
-                }
-                rv[ps] = __ldg(reinterpret_cast<const uint4*>(a.residual + rrow * a.ldr + n0 + g * 8));
-              }
-            }
-#pragma unroll
-            for (int ps = 0; ps < 8; ++ps)
-              *reinterpret_cast<uint4*>(ostage + swz(ps * 4 + rr, g)) = rv[ps];
-            __syncwarp();
-          }
-        }
         tmem_ld_wait();
-        const uint8_t* rsrc = a.manual ? ostage : astage + (c0 >> 6) * EPI_TILE_BYTES;
-        const int kind = a.manual ? (a.residual ? 1 : 0) : a.aux_kind;
+        const uint8_t* atile = astage + (c0 >> 6) * EPI_TILE_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (j * 16 < cw) {
-            const int nj = n0 + j * 16;
+          const int nj = nbase + c0 + j * 16;
+          if (j * 16 < cw && nj < a.Cout && m < a.M) {
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[j][i]);
-            if (nj < a.Cout) {
-              if (a.scale) {
+            if (a.scale) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float4 sv = __ldg(reinterpret_cast<const float4*>(a.scale + nj) + i);
-                  f[4 * i] *= sv.x; f[4 * i + 1] *= sv.y; f[4 * i + 2] *= sv.z; f[4 * i + 3] *= sv.w;
-                }
-              }
-              if (a.shift) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float4 sv = __ldg(reinterpret_cast<const float4*>(a.shift + nj) + i);
-                  f[4 * i] += sv.x; f[4 * i + 1] += sv.y; f[4 * i + 2] += sv.z; f[4 * i + 3] += sv.w;
-                }
+              for (int i = 0; i < 4; ++i) {
+                const float4 sv = __ldg(reinterpret_cast<const float4*>(a.scale + nj) + i);
+                f[4 * i] *= sv.x; f[4 * i + 1] *= sv.y; f[4 * i + 2] *= sv.z; f[4 * i + 3] *= sv.w;
               }
             }
-            uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
-            if (kind) {
-              x0 = *reinterpret_cast<const uint4*>(rsrc + swz(lane, 2 * j));
-              x1 = *reinterpret_cast<const uint4*>(rsrc + swz(lane, 2 * j + 1));
+            if (a.shift) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 sv = __ldg(reinterpret_cast<const float4*>(a.shift + nj) + i);
+                f[4 * i] += sv.x; f[4 * i + 1] += sv.y; f[4 * i + 2] += sv.z; f[4 * i + 3] += sv.w;
+              }
             }
-            const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-            if (kind == 1) {
+            uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0, y0 = x0, y1 = x0;   // x: residual, y: mask
+            int has_res = 0, has_mask = 0;
+            if (use_aux) {
+              const uint4 t0 = *reinterpret_cast<const uint4*>(atile + swz(lane, 2 * j));
+              const uint4 t1 = *reinterpret_cast<const uint4*>(atile + swz(lane, 2 * j + 1));
+              if (a.aux_kind == 1) { x0 = t0; x1 = t1; has_res = 1; } else { y0 = t0; y1 = t1; has_mask = 1; }
+            } else if (a.manual) {
+              if (a.residual) {
+                const uint4* rp = reinterpret_cast<const uint4*>(a.residual + rrow * a.ldr + nj);
+                x0 = __ldg(rp); x1 = __ldg(rp + 1); has_res = 1;
+              }
+              if (a.relu_mask) {
+                const uint4* mp = reinterpret_cast<const uint4*>(a.relu_mask + (size_t)m * a.ldo + nj);
+                y0 = __ldg(mp); y1 = __ldg(mp + 1); has_mask = 1;
+              }
+            }
+            if (has_res) {
+              const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 f[2 * i] += __uint_as_float(xw[i] << 16);
@@ -277,46 +262,22 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             uint32_t ow[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) ow[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-            if (kind == 2) {
+            if (has_mask) {
+              const uint32_t yw[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
 #pragma unroll
-              for (int i = 0; i < 8; ++i) ow[i] = mask_bf16x2(ow[i], xw[i]);
+              for (int i = 0; i < 8; ++i) ow[i] = mask_bf16x2(ow[i], yw[i]);
             }
-            *reinterpret_cast<uint4*>(ostage + swz(lane, 2 * j)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-            *reinterpret_cast<uint4*>(ostage + swz(lane, 2 * j + 1)) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+            uint4* op = reinterpret_cast<uint4*>(a.out + (size_t)m * a.ldo + nj);
+            op[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            op[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
           }
-        }
-        {
-          // (e) staging -> global: 8 lanes x 16 B cover one 128-byte row segment, 4 rows per pass, fire-and-forget
-          __syncwarp();
-          uint4 mv[8];
-          if (a.manual && a.relu_mask) {
-#pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-              const int m = row0 + ps * 4 + rr;
-              mv[ps] = make_uint4(0, 0, 0, 0);
-              if (gcol && m < a.M)
-                mv[ps] = __ldg(reinterpret_cast<const uint4*>(a.relu_mask + (size_t)m * a.ldo + n0 + g * 8));
-            }
-          }
-#pragma unroll
-          for (int ps = 0; ps < 8; ++ps) {
-            const int m = row0 + ps * 4 + rr;
-            if (gcol && m < a.M) {
-              uint4 o = *reinterpret_cast<const uint4*>(ostage + swz(ps * 4 + rr, g));
-              if (a.manual && a.relu_mask)
-                o = make_uint4(mask_bf16x2(o.x, mv[ps].x), mask_bf16x2(o.y, mv[ps].y), mask_bf16x2(o.z, mv[ps].z),
-                               mask_bf16x2(o.w, mv[ps].w));
-              *reinterpret_cast<uint4*>(a.out + (size_t)m * a.ldo + n0 + g * 8) = o;
-            }
-          }
-          __syncwarp();
         }
       }
       // accumulators consumed: release the TMEM buffer, then prefetch the aux tiles of this CTA's next tile
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (a.aux_kind && !a.manual) {
+      if (use_aux) {
         aux_phase ^= 1;
         __syncwarp();                   // every lane finished reading the aux tiles
         const int tn = t + gridDim.x;
@@ -535,7 +496,7 @@ extern "C" int ut2_conv2d_nhwc_bf16_fwd(const void* x, int N, int H, int W, int 
   a.res_up2 = res_up2; a.relu_mask = static_cast<const __nv_bfloat16*>(relu_mask);
   if (res_up2 && ((P & 1) || (Q & 1))) return ut2_fail(-4, "conv_fwd: res_up2 needs even output H, W");
   a.out = static_cast<__nv_bfloat16*>(y);
-  a.manual = (Cout < 64) || (residual && res_up2) || (residual && relu_mask);
+  a.manual = (Cout < 64 && (residual || relu_mask)) || (residual && res_up2) || (residual && relu_mask);
   a.aux_kind = a.manual ? 0 : (residual ? 1 : (relu_mask ? 2 : 0));
   a.stages = a.aux_kind ? 3 : 4;
   CUtensorMap tx, tw, to, ta;

@@ -239,27 +239,34 @@ __global__ void zero_stuff_kernel(const bf16* __restrict__ in, bf16* __restrict_
 }
 
 // ------------------------------------------------------------------------------ column sums (bias grad)
-// db[c] += scale * sum_m g[m, c]; g is [M, C] bf16. Block = 32 x 8 threads: 32 channel pairs x 8 rows.
-__global__ void colsum_kernel(const bf16* __restrict__ g, float* __restrict__ db, int M, int C, int rows_per_block) {
-  const int c2 = blockIdx.x * 32 + threadIdx.x;     // channel pair index
-  const int m0 = blockIdx.y * rows_per_block;
+// db[c] += sum_m g[m, c]; g is [M, C] bf16, C % 8 == 0. One thread = one 16-byte vector (8 channels) of a row, so a
+// warp reads whole 512-byte rows; per-thread fp32 partials over a strided set of rows, shared-memory reduce across
+// the threads that own the same channel group, one atomicAdd per channel per block.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const bf16* __restrict__ g, float* __restrict__ db, int M, int C8, int rows_per_block) {
+  const int rpp = 256 / C8;                       // rows per pass
+  const int cg = threadIdx.x % C8, ro = threadIdx.x / C8;
+  const int m0 = blockIdx.x * rows_per_block;
   const int m1 = min(M, m0 + rows_per_block);
-  float s0 = 0.f, s1 = 0.f;
-  if (c2 * 2 < C) {
-    for (int m = m0 + threadIdx.y; m < m1; m += 8) {
-      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(g + (size_t)m * C) + c2);
-      s0 += bflo(u);
-      s1 += bfhi(u);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (ro < rpp) {
+    for (int m = m0 + ro; m < m1; m += rpp) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(g) + (size_t)m * C8 + cg);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[2 * j] += bflo(u[j]); s[2 * j + 1] += bfhi(u[j]); }
     }
   }
-  __shared__ float red[8][32][2];
-  red[threadIdx.y][threadIdx.x][0] = s0;
-  red[threadIdx.y][threadIdx.x][1] = s1;
+  __shared__ float red[256][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = s[j];
   __syncthreads();
-  if (threadIdx.y == 0 && c2 * 2 < C) {
-    for (int k = 1; k < 8; ++k) { s0 += red[k][threadIdx.x][0]; s1 += red[k][threadIdx.x][1]; }
-    atomicAdd(db + 2 * c2, s0);
-    atomicAdd(db + 2 * c2 + 1, s1);
+  if (ro == 0) {
+    for (int k = 1; k < rpp; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += red[k * C8 + cg][j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(db + cg * 8 + j, s[j]);
   }
 }
 
@@ -376,10 +383,14 @@ extern "C" int ut2_zero_stuff_s2_nhwc(const void* in, void* out, int N, int P, i
 }
 
 extern "C" int ut2_colsum_bf16(const void* g, float* db, int M, int C, void* stream) {
-  if (C % 2) return ut2_fail(-2, "colsum: C % 2 != 0");
-  const int rows = 2048;
-  dim3 grid((C / 2 + 31) / 32, (M + rows - 1) / rows), block(32, 8);
-  colsum_kernel<<<grid, block, 0, STREAM>>>(static_cast<const bf16*>(g), db, M, C, rows);
+  if (C % 8 || C > 2048 || C <= 0) return ut2_fail(-2, "colsum: need C % 8 == 0 and C <= 2048");
+  const int C8 = C / 8;
+  int blocks = 148 * 4;
+  int rows = (M + blocks - 1) / blocks;
+  const int rpp = 256 / C8;
+  if (rows < 8 * rpp) rows = 8 * rpp;
+  blocks = (M + rows - 1) / rows;
+  colsum_kernel<<<blocks, 256, 0, STREAM>>>(static_cast<const bf16*>(g), db, M, C8, rows);
   return ut2_check_launch("colsum");
 }
 
