@@ -124,11 +124,12 @@ int ut2_ema_update(const float* student, float* teacher, long long n, double kee
 int ut2_sgd_step(float* p, float* g, float* buf, long long n, float lr, const float* lr_dev /* overrides lr if set */,
                  float momentum, float weight_decay, int first_step, int zero_grad, float grad_scale, void* stream);
 /* fp32 master weights (channels-last) -> bf16 forward operand [Cout,R,S,Cin] and dgrad operand [Cin,R,S,CoutT]
- * (taps flipped). The batched form takes a device table of 56-byte records
- * {int64 src, wf, wt, begin; int32 Cout, Cin, R, S, CoutT, n_off}. */
+ * (taps flipped). The batched form takes a device table of 64-byte records
+ * {int64 src, wf, wt, begin, scale; int32 Cout, Cin, R, S, CoutT, n_off}; scale >= 0 folds scales[scale + co]
+ * (the FrozenBN scale) into the packed weights. */
 int ut2_pack_conv_weight(const float* w, void* wf, void* wt, int Cout, int Cin, int R, int S, int CoutT, void* stream);
-int ut2_pack_conv_weights_batched(const void* descs, int num, long long total, const float* arena, void* packed,
-                                  void* stream);
+int ut2_pack_conv_weights_batched(const void* descs, int num, long long total, const float* arena, const float* scales,
+                                  void* packed, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,12 +26,12 @@ constexpr int MAX_STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KiB
 constexpr int B_BYTES = 256 * BK * 2;       // 32 KiB (block_n <= 256)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int BAR_BYTES = 1024;             // mbarriers + TMEM slot (keeps what follows 1024-aligned)
+constexpr int BAR_BYTES = 3072;             // 1 KiB mbarriers + TMEM slot | 1 KiB scale[256] | 1 KiB shift[256]
 constexpr int EPI_TILE_BYTES = 32 * 128;    // one 32-row x 64-col bf16 staging tile, 128B-swizzled
-constexpr int NUM_THREADS = 192;            // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int NUM_THREADS = 320;            // warp0 TMA, warp1 MMA, warps2-9 epilogue (two per TMEM lane quadrant)
 constexpr int TMEM_COLS = 512;              // 2 accumulator buffers x 256 fp32 columns
 
-// shared memory: [stages x 48 KiB operands][barriers][4 warps x 4 aux tiles of 4 KiB (only with aux)]
+// shared memory: [stages x 48 KiB operands][barriers, scale, shift][8 warps x 2 aux tiles of 4 KiB (only with aux)]
 constexpr int smem_bytes(int stages, bool aux) {
   return 1024 + stages * STAGE_BYTES + BAR_BYTES + (aux ? 16 : 0) * EPI_TILE_BYTES;
 }
@@ -80,9 +80,11 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
-  uint64_t* aux_bar = tempty_bar + 2;             // [4] one per epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 4);
-  uint8_t* aux_stage = bar_base + BAR_BYTES;                 // 4 warps x 4 tiles x 4 KiB (aux_kind != 0 only)
+  uint64_t* aux_bar = tempty_bar + 2;             // [8] one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 8);
+  float* s_scale = reinterpret_cast<float*>(bar_base + 1024);
+  float* s_shift = reinterpret_cast<float*>(bar_base + 2048);
+  uint8_t* aux_stage = bar_base + BAR_BYTES;                 // 8 warps x 2 tiles x 4 KiB (aux_kind != 0 only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,9 +102,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], 256);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -165,31 +167,44 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
     }
   } else {
-    // -------------------------------------------------- epilogue (4 warps, TMEM lane quadrant = warp % 4)
-    // TMEM hands each lane one output ROW. Stores go straight from registers (32-byte sectors per lane: measured
-    // faster than staging + coalesced or TMA stores — L2 merges the sectors and nothing waits on a store). What must
-    // NOT sit in the dependency chain is the residual / ReLU-mask read: those tiles are TMA-prefetched into a
-    // 128B-swizzled shared-memory tile one output tile ahead and read row-per-lane without bank conflicts. The
-    // "manual" path (nearest-2x upsampled FPN residual, residual + mask together, Cout < 64) uses plain loads.
+    // -------------------------------------------------- epilogue (8 warps: TMEM lane quadrant = warp % 4, two warps
+    // per quadrant take alternate 64-column chunks). TMEM hands each lane one output ROW. Stores go straight from
+    // registers (32-byte sectors per lane — measured faster than staging + coalesced or TMA stores: L2 merges the
+    // sectors and nothing waits on a store). What must NOT sit in the dependency chain is the residual / ReLU-mask
+    // read: those tiles are TMA-prefetched into 128B-swizzled shared-memory tiles one output tile ahead and read
+    // row-per-lane without bank conflicts; scale / shift vectors are staged in shared memory per n-tile. The "manual"
+    // path (nearest-2x upsampled FPN residual, residual + mask together, Cout < 64) uses plain loads.
     const int quad = warp & 3;
-    const int ew = warp - 2;
-    uint8_t* astage = aux_stage + ew * 4 * EPI_TILE_BYTES;
+    const int ew = warp - 2;                     // 0..7
+    const int half = ew >> 2;                    // which alternate chunks this warp owns
+    const int et = threadIdx.x - 64;             // 0..255 among the epilogue threads
+    uint8_t* astage = aux_stage + ew * 2 * EPI_TILE_BYTES;
     const int nchunks = (a.block_n + 63) / 64;
-    const uint32_t aux_bytes = nchunks * EPI_TILE_BYTES;
-    const bool use_aux = a.aux_kind != 0;
+    const int my_chunks = (nchunks - half + 1) / 2;           // chunks half, half+2, ...
+    const uint32_t aux_bytes = my_chunks * EPI_TILE_BYTES;
+    const bool use_aux = a.aux_kind != 0 && my_chunks > 0;
     uint32_t acc = 0, acc_phase = 0, aux_phase = 0;
+    int staged_n_tile = -1;
     if (use_aux && lane == 0 && (int)blockIdx.x < num_tiles) {   // aux tiles of this CTA's first tile
       const int t = blockIdx.x;
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
       mbar_arrive_expect_tx(&aux_bar[ew], aux_bytes);
-      for (int c = 0; c < nchunks; ++c)
-        tma_load_2d(astage + c * EPI_TILE_BYTES, &tmap_aux, &aux_bar[ew], n_tile * a.block_n + c * 64,
+      for (int c = 0; c < my_chunks; ++c)
+        tma_load_2d(astage + c * EPI_TILE_BYTES, &tmap_aux, &aux_bar[ew], n_tile * a.block_n + (half + 2 * c) * 64,
                     m_tile * BM + quad * 32);
     }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
       const int m = m_tile * BM + quad * 32 + lane;
       const int nbase = n_tile * a.block_n;
+      if (n_tile != staged_n_tile) {            // (re)stage scale / shift of this n-tile: uniform across the 8 warps
+        if (staged_n_tile >= 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int n = nbase + et;
+        s_scale[et] = (a.scale && et < a.block_n && n < a.Cout) ? __ldg(a.scale + n) : 1.f;
+        s_shift[et] = (a.shift && et < a.block_n && n < a.Cout) ? __ldg(a.shift + n) : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        staged_n_tile = n_tile;
+      }
       size_t rrow = (size_t)m;                 // residual row for the manual path
       if (a.manual && a.residual && a.res_up2 && m < a.M) {
         const int PQ = a.P * a.Q;
@@ -201,7 +216,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       tc_fence_after();
       if (use_aux) mbar_wait(&aux_bar[ew], aux_phase);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
-      for (int c0 = 0; c0 < a.block_n; c0 += 64) {
+      for (int c0 = half * 64, ci = 0; c0 < a.block_n; c0 += 128, ++ci) {
         const int cw = min(64, a.block_n - c0);
         uint32_t v[4][16];
         tmem_ld_32x16(taddr + c0, v[0]);
@@ -209,27 +224,21 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         if (cw > 32) tmem_ld_32x16(taddr + c0 + 32, v[2]);
         if (cw > 48) tmem_ld_32x16(taddr + c0 + 48, v[3]);
         tmem_ld_wait();
-        const uint8_t* atile = astage + (c0 >> 6) * EPI_TILE_BYTES;
+        const uint8_t* atile = astage + ci * EPI_TILE_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int nj = nbase + c0 + j * 16;
+          const int cj = c0 + j * 16;
+          const int nj = nbase + cj;
           if (j * 16 < cw && nj < a.Cout && m < a.M) {
             float f[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[j][i]);
-            if (a.scale) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 sv = __ldg(reinterpret_cast<const float4*>(a.scale + nj) + i);
-                f[4 * i] *= sv.x; f[4 * i + 1] *= sv.y; f[4 * i + 2] *= sv.z; f[4 * i + 3] *= sv.w;
-              }
-            }
-            if (a.shift) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 sv = __ldg(reinterpret_cast<const float4*>(a.shift + nj) + i);
-                f[4 * i] += sv.x; f[4 * i + 1] += sv.y; f[4 * i + 2] += sv.z; f[4 * i + 3] += sv.w;
-              }
+            for (int i = 0; i < 4; ++i) {
+              const float4 sv = *reinterpret_cast<const float4*>(s_scale + cj + 4 * i);
+              const float4 hv = *reinterpret_cast<const float4*>(s_shift + cj + 4 * i);
+              f[4 * i] = fmaf(__uint_as_float(v[j][4 * i]), sv.x, hv.x);
+              f[4 * i + 1] = fmaf(__uint_as_float(v[j][4 * i + 1]), sv.y, hv.y);
+              f[4 * i + 2] = fmaf(__uint_as_float(v[j][4 * i + 2]), sv.z, hv.z);
+              f[4 * i + 3] = fmaf(__uint_as_float(v[j][4 * i + 3]), sv.w, hv.w);
             }
             uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0, y0 = x0, y1 = x0;   // x: residual, y: mask
             int has_res = 0, has_mask = 0;
@@ -284,9 +293,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         if (lane == 0 && tn < num_tiles) {
           const int n_tile2 = tn % a.n_tiles, m_tile2 = tn / a.n_tiles;
           mbar_arrive_expect_tx(&aux_bar[ew], aux_bytes);
-          for (int c = 0; c < nchunks; ++c)
-            tma_load_2d(astage + c * EPI_TILE_BYTES, &tmap_aux, &aux_bar[ew], n_tile2 * a.block_n + c * 64,
-                        m_tile2 * BM + quad * 32);
+          for (int c = 0; c < my_chunks; ++c)
+            tma_load_2d(astage + c * EPI_TILE_BYTES, &tmap_aux, &aux_bar[ew],
+                        n_tile2 * a.block_n + (half + 2 * c) * 64, m_tile2 * BM + quad * 32);
         }
       }
     }

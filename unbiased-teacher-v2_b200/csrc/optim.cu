@@ -50,12 +50,13 @@ struct PackDesc {          // one conv weight: master fp32 [Cout, R, S, Cin] (ch
   long long wf;            // bf16 offset of the forward operand [rows, R, S, Cin] in the pack arena, or -1
   long long wt;            // bf16 offset of the dgrad operand [Cin, R, S, CoutT] (flipped taps), or -1
   long long begin;         // prefix sum of element counts (begin of this descriptor)
+  long long scale;         // float offset of a per-Cout scale folded into the packed weights (FrozenBN), or -1
   int Cout, Cin, R, S, CoutT, n_off;   // n_off: column offset inside wt rows (fused predictors)
 };
 
 __global__ void __launch_bounds__(256)
 pack_batched_kernel(const PackDesc* __restrict__ descs, int num, long long total, const float* __restrict__ arena,
-                    bf16* __restrict__ packed) {
+                    const float* __restrict__ scales, bf16* __restrict__ packed) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     int lo = 0, hi = num - 1;
@@ -70,7 +71,9 @@ pack_batched_kernel(const PackDesc* __restrict__ descs, int num, long long total
     const int s = (int)(t % d.S); t /= d.S;
     const int r = (int)(t % d.R);
     const int n = (int)(t / d.R);
-    const bf16 v = __float2bfloat16_rn(arena[d.src + e]);
+    float wv = arena[d.src + e];
+    if (d.scale >= 0) wv *= scales[d.scale + n];
+    const bf16 v = __float2bfloat16_rn(wv);
     if (d.wf >= 0) packed[d.wf + e] = v;
     if (d.wt >= 0)
       packed[d.wt + (((long long)c * d.R + (d.R - 1 - r)) * d.S + (d.S - 1 - s)) * d.CoutT + n + d.n_off] = v;
@@ -106,11 +109,11 @@ extern "C" int ut2_sgd_step(float* p, float* g, float* buf, long long n, float l
   return ut2_check_launch("sgd_step");
 }
 
-// descs: device array of `num` 64-byte records {src, wf, wt, begin, Cout, Cin, R, S, CoutT, n_off}.
+// descs: device array of `num` 64-byte records {int64 src, wf, wt, begin, scale; int32 Cout, Cin, R, S, CoutT, n_off}.
 extern "C" int ut2_pack_conv_weights_batched(const void* descs, int num, long long total, const float* arena,
-                                             void* packed, void* stream) {
+                                             const float* scales, void* packed, void* stream) {
   if (num <= 0 || total <= 0) return 0;
-  pack_batched_kernel<<<grid_for(total), 256, 0, STREAM>>>(static_cast<const PackDesc*>(descs), num, total, arena,
+  pack_batched_kernel<<<grid_for(total), 256, 0, STREAM>>>(static_cast<const PackDesc*>(descs), num, total, arena, scales,
                                                            static_cast<bf16*>(packed));
   return ut2_check_launch("pack_conv_weights_batched");
 }

@@ -107,7 +107,8 @@ class PackPlan:
 
     def __init__(self, arena):
         self.arena = arena
-        self.entries = []      # (src_off, wf_off, wt_off, Cout, Cin, R, S, CoutT, n_off)
+        self.entries = []      # (src_off, wf_off, wt_off, scale_off, Cout, Cin, R, S, CoutT, n_off)
+        self.scales = None     # fp32 tensor the scale offsets index (the folded FrozenBN scales)
         self.size = 0
         self.packed = None
         self.table = None
@@ -118,16 +119,16 @@ class PackPlan:
         self.size += (numel + 63) // 64 * 64     # 128-byte aligned operands for TMA
         return off
 
-    def add(self, name, wf_off, wt_off, cout, cin, R, S, coutT, n_off=0):
-        self.entries.append((self.arena.offset[name], wf_off, wt_off, cout, cin, R, S, coutT, n_off))
+    def add(self, name, wf_off, wt_off, cout, cin, R, S, coutT, n_off=0, scale_off=-1):
+        self.entries.append((self.arena.offset[name], wf_off, wt_off, scale_off, cout, cin, R, S, coutT, n_off))
 
     def finalize(self):
         dev = self.arena.device
         self.packed = torch.zeros(max(self.size, 64), dtype=torch.bfloat16, device=dev)
         raw = bytearray()
         begin = 0
-        for (src, wf, wt, cout, cin, R, S, coutT, n_off) in self.entries:
-            raw += struct.pack("<qqqqiiiiii", src, wf, wt, begin, cout, cin, R, S, coutT, n_off)
+        for (src, wf, wt, sc, cout, cin, R, S, coutT, n_off) in self.entries:
+            raw += struct.pack("<qqqqqiiiiii", src, wf, wt, begin, sc, cout, cin, R, S, coutT, n_off)
             begin += cout * cin * R * S
         self.total = begin
         self.table = torch.frombuffer(raw, dtype=torch.uint8).clone().to(dev)
@@ -143,4 +144,4 @@ class PackPlan:
         from . import _C
         from ._C import i64
         _C.counted_call("ut2_pack_conv_weights_batched", self.table, len(self.entries), i64(self.total),
-                        self.arena.data, self.packed)
+                        self.arena.data, self.scales, self.packed)

@@ -30,7 +30,7 @@ class Conv:
     def __init__(self, name, cin, cout, k, stride, pad, bn=False, bias=False, trainable=True, need_dgrad=True):
         self.name, self.cin, self.cout, self.k, self.stride, self.pad = name, cin, cout, k, stride, pad
         self.bn, self.bias, self.trainable, self.need_dgrad = bn, bias, trainable, need_dgrad
-        self.wf = self.wt = self.scale = self.shift = self.dw = self.db = None
+        self.wf = self.wt = self.scale = self.shift = self.dw = self.db = self.bn_scale = None
         self.cout_store = 0
 
     def fwd(self, x, residual=None, relu=False, res_up2=False, out=None):
@@ -40,8 +40,7 @@ class Conv:
     def wgrad(self, x, g):
         if not self.trainable:
             return
-        ops.conv2d_wgrad(x, g, self.cout, self.k, self.k, self.stride, self.pad, self.dw, self.scale if self.bn else None,
-                         self.cout_store)
+        ops.conv2d_wgrad(x, g, self.cout, self.k, self.k, self.stride, self.pad, self.dw, self.bn_scale, self.cout_store)
         if self.bias:
             ops.colsum(g.view(-1, self.cout), self.db)
 
@@ -184,7 +183,8 @@ class FcosEngine:
             coutT = (c.cout + 7) // 8 * 8
             if c.trainable and c.need_dgrad:
                 wt = plan.alloc(c.cin * c.k * c.k * coutT)
-            plan.add(name + ".weight", wf, wt, c.cout, c.cin, c.k, c.k, coutT)
+            plan.add(name + ".weight", wf, wt, c.cout, c.cin, c.k, c.k, coutT,
+                     scale_off=bn_off[name + ".norm"] if c.bn else -1)
             c._wf_off, c._wt_off, c._coutT = wf, wt, coutT
         # fused box predictor operands
         K = 9 * 256
@@ -197,6 +197,7 @@ class FcosEngine:
             plan.add(hd + nm + ".weight", bp._wf_off + row * K, bp._wt_off, rows, 256, 3, 3, 80, row)
             row += rows
         plan.finalize()
+        plan.scales = self.bn_fold[0]
         for name, c in list(convs.items()) + [(bp.name, bp)]:
             if name == self.stem.name:
                 continue
@@ -206,8 +207,12 @@ class FcosEngine:
                 c.wt = plan.view(c._wt_off, (c.cin, c.k, c.k, c._coutT))
         for name, c in convs.items():
             if c.bn:
+                # the FrozenBN scale is folded into the packed bf16 weights (forward and dgrad operands); the epilogue
+                # only adds the shift. The weight gradient still needs the scale: d/dW = scale * (dY^T X).
                 o = bn_off[name + ".norm"]
-                c.scale, c.shift = self.bn_fold[0, o:o + c.cout], self.bn_fold[1, o:o + c.cout]
+                c.bn_scale, c.shift = self.bn_fold[0, o:o + c.cout], self.bn_fold[1, o:o + c.cout]
+                if name == self.stem.name:
+                    c.scale = c.bn_scale      # the stem kernel packs its own fp32 filter
             elif c.bias:
                 c.shift = A.flat(name + ".bias")
                 c.db = A.gflat(name + ".bias")
@@ -269,11 +274,11 @@ class FcosEngine:
     def refresh_operands(self):
         """Re-derive everything the kernels read from the fp32 arena: packed bf16 weights (one launch),
         FrozenBN scale/shift (one launch), the stem filter in [R,S,C,K] order."""
-        self.plan.run()
         A = self.arena
         b, n = self.bn_base, self.bn_total
         _C.counted_call("ut2_frozen_bn_fold", A.data[b:b + n], A.data[b + n:b + 2 * n], A.data[b + 2 * n:b + 3 * n],
                         A.data[b + 3 * n:b + 4 * n], _C.f32(BN_EPS), self.bn_fold[0], self.bn_fold[1], n)
+        self.plan.run()        # after the fold: the packer multiplies the FrozenBN scale into the bf16 weights
         self.stem_w.copy_(A.views[self.stem.name + ".weight"].permute(2, 3, 1, 0))
 
     # ------------------------------------------------------------------------------------ geometry
