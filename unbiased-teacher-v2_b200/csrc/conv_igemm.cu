@@ -311,6 +311,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
 // ------------------------------------------------------------------------------------ wgrad
 constexpr int STAGES = 4;                       // wgrad operand ring depth
+constexpr int WG_THREADS = 192;                 // warp0 TMA, warp1 MMA, warps2-5 epilogue
 constexpr int WG_PIX = 64;                      // pixels (GEMM-K) per stage
 constexpr int WG_BLK_BYTES = WG_PIX * 64 * 2;   // one [64 pix][64 ch] swizzled block = 8 KiB
 constexpr int WG_A_BYTES = 2 * WG_BLK_BYTES;    // 128 output channels
@@ -328,7 +329,7 @@ struct ConvWgradArgs {
   int cout_store;       // rows >= cout_store are not written (zero-padded fused predictors)
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
                   const ConvWgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -572,7 +573,7 @@ extern "C" int ut2_conv2d_nhwc_bf16_wgrad(const void* x, int N, int H, int W, in
     attr_set = true;
   }
   dim3 grid(out_tiles, splits);
-  conv_wgrad_kernel<<<grid, NUM_THREADS, WG_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tg, tx, a);
+  conv_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tg, tx, a);
   return ut2_check_launch("conv_wgrad");
 }
 
