@@ -70,8 +70,8 @@ int ut2_cast_f32_bf16(const float* x, void* y, long long n, void* stream);
 int ut2_groupnorm_relu_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, double* stats,
                            int N, int HW, int C, int G, int relu, void* stream);
 int ut2_groupnorm_relu_bwd(const void* dy, const void* x, const double* stats, const float* gamma, const float* beta,
-                           float eps, void* dx, float* dgamma, float* dbeta, double* ws, int N, int HW, int C, int G,
-                           int relu, void* stream);
+                           float eps, void* dx, float* dgamma, float* dbeta, float* dbias_prev /* += colsum(dx), optional */,
+                           double* ws, int N, int HW, int C, int G, int relu, void* stream);
 
 /* ---------------------------------------------------------------- FCOS targets and losses
  * ut2_fcos_assign_targets: FCOSOutputs._get_ground_truth + compute_targets_for_locations

@@ -104,7 +104,9 @@ def test_groupnorm_relu_fwd_bwd():
     yr.backward(dy.float().permute(0, 3, 1, 2))
     dgam = torch.zeros(C, device="cuda")
     dbet = torch.zeros(C, device="cuda")
-    dx = ops.groupnorm_relu_bwd(dy.cuda(), x.cuda(), stats, gamma.cuda(), beta.cuda(), dgam, dbet)
+    dbias = torch.zeros(C, device="cuda")
+    dx = ops.groupnorm_relu_bwd(dy.cuda(), x.cuda(), stats, gamma.cuda(), beta.cuda(), dgam, dbet, dbias_prev=dbias)
+    torch.testing.assert_close(dbias.cpu(), dx.float().cpu().sum((0, 1, 2)), rtol=1e-4, atol=1e-3)   # fused bias grad
     torch.testing.assert_close(dx.float().cpu(), xr.grad.permute(0, 2, 3, 1), rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(dgam.cpu(), gr.grad, rtol=1e-3, atol=1e-2)
     torch.testing.assert_close(dbet.cpu(), br.grad, rtol=1e-3, atol=1e-2)

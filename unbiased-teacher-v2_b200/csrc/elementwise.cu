@@ -250,11 +250,19 @@ colsum_kernel(const bf16* __restrict__ g, float* __restrict__ db, int M, int C8,
   const int m1 = min(M, m0 + rows_per_block);
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (ro < rpp) {
-    for (int m = m0 + ro; m < m1; m += rpp) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(g) + (size_t)m * C8 + cg);
-      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    for (int m = m0 + ro; m < m1; m += 4 * rpp) {
+      uint4 v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { s[2 * j] += bflo(u[j]); s[2 * j + 1] += bfhi(u[j]); }
+      for (int q = 0; q < 4; ++q) {
+        const int mm = m + q * rpp;
+        v[q] = mm < m1 ? __ldg(reinterpret_cast<const uint4*>(g) + (size_t)mm * C8 + cg) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t u[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s[2 * j] += bflo(u[j]); s[2 * j + 1] += bfhi(u[j]); }
+      }
     }
   }
   __shared__ float red[256][8];

@@ -32,6 +32,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 constexpr int GN_G = 32;          // groups (== vectors per pixel)
 constexpr int GN_ROWS = 8;        // pixel rows per block iteration (256 threads)
+constexpr int GN_UNROLL = 4;      // independent 16-byte loads in flight per thread
 
 // stats[n][g] = {sum, sumsq} over HW x 8 channels
 __global__ void __launch_bounds__(256)
@@ -41,11 +42,20 @@ gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats, int HW, 
   const int p1 = min(HW, p0 + pix_per_block);
   const uint4* xv = reinterpret_cast<const uint4*>(x) + (size_t)n * HW * GN_G;
   float s1 = 0.f, s2 = 0.f;
-  for (int p = p0 + row; p < p1; p += GN_ROWS) {
-    float f[8];
-    unpack8(__ldg(xv + (size_t)p * GN_G + g), f);
+  for (int p = p0 + row; p < p1; p += GN_ROWS * GN_UNROLL) {
+    uint4 v[GN_UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
+    for (int u = 0; u < GN_UNROLL; ++u) {       // all loads first: GN_UNROLL x 16 B in flight per thread
+      const int pp = p + u * GN_ROWS;
+      v[u] = pp < p1 ? __ldg(xv + (size_t)pp * GN_G + g) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
+    }
   }
   __shared__ float red[GN_ROWS][GN_G][2];
   red[row][g][0] = s1;
@@ -83,15 +93,27 @@ gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ stats, co
   const int p1 = min(HW, p0 + pix_per_block);
   const uint4* xv = reinterpret_cast<const uint4*>(x) + (size_t)n * HW * GN_G;
   uint4* yv = reinterpret_cast<uint4*>(y) + (size_t)n * HW * GN_G;
-  for (int p = p0 + row; p < p1; p += GN_ROWS) {
-    float f[8];
-    unpack8(__ldg(xv + (size_t)p * GN_G + g), f);
+  for (int p = p0 + row; p < p1; p += GN_ROWS * GN_UNROLL) {
+    uint4 v[GN_UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      f[j] = fmaf(f[j], ga[j], be[j]);
-      if (relu) f[j] = fmaxf(f[j], 0.f);
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      const int pp = p + u * GN_ROWS;
+      v[u] = pp < p1 ? __ldg(xv + (size_t)pp * GN_G + g) : make_uint4(0, 0, 0, 0);
     }
-    yv[(size_t)p * GN_G + g] = pack8(f);
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      const int pp = p + u * GN_ROWS;
+      if (pp < p1) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[j] = fmaf(f[j], ga[j], be[j]);
+          if (relu) f[j] = fmaxf(f[j], 0.f);
+        }
+        yv[(size_t)pp * GN_G + g] = pack8(f);
+      }
+    }
   }
 }
 
@@ -114,20 +136,30 @@ gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
   float dg[8], db[8], s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) { dg[j] = 0.f; db[j] = 0.f; }
-  for (int p = p0 + row; p < p1; p += GN_ROWS) {
-    float f[8], d[8];
-    unpack8(__ldg(xv + (size_t)p * GN_G + g), f);
-    unpack8(__ldg(dv + (size_t)p * GN_G + g), d);
+  for (int p = p0 + row; p < p1; p += GN_ROWS * GN_UNROLL) {
+    uint4 vx[GN_UNROLL], vd[GN_UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (f[j] - mean) * rstd;
-      float gj = d[j];
-      if (relu && !(fmaf(xh, ga[j], be[j]) > 0.f)) gj = 0.f;
-      dg[j] = fmaf(gj, xh, dg[j]);
-      db[j] += gj;
-      const float gg = gj * ga[j];
-      s1 += gg;
-      s2 = fmaf(gg, xh, s2);
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      const int pp = p + u * GN_ROWS;
+      vx[u] = pp < p1 ? __ldg(xv + (size_t)pp * GN_G + g) : make_uint4(0, 0, 0, 0);
+      vd[u] = pp < p1 ? __ldg(dv + (size_t)pp * GN_G + g) : make_uint4(0, 0, 0, 0);   // zero gradient: no contribution
+    }
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      float f[8], d[8];
+      unpack8(vx[u], f);
+      unpack8(vd[u], d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (f[j] - mean) * rstd;
+        float gj = d[j];
+        if (relu && !(fmaf(xh, ga[j], be[j]) > 0.f)) gj = 0.f;
+        dg[j] = fmaf(gj, xh, dg[j]);
+        db[j] += gj;
+        const float gg = gj * ga[j];
+        s1 += gg;
+        s2 = fmaf(gg, xh, s2);
+      }
     }
   }
   __shared__ float red[GN_ROWS][GN_G][18];
@@ -157,7 +189,7 @@ gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const double* __restrict__ stats,
                     const double* __restrict__ ws, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    float eps, bf16* __restrict__ dx, int HW, int pix_per_block, int relu) {
+                    float eps, bf16* __restrict__ dx, float* __restrict__ dbias, int HW, int pix_per_block, int relu) {
   const int n = blockIdx.y, g = threadIdx.x & 31, row = threadIdx.x >> 5;
   float mean, rstd;
   mean_rstd(stats, n, g, HW, eps, mean, rstd);
@@ -172,18 +204,53 @@ gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, con
   const uint4* xv = reinterpret_cast<const uint4*>(x) + (size_t)n * HW * GN_G;
   const uint4* dv = reinterpret_cast<const uint4*>(dy) + (size_t)n * HW * GN_G;
   uint4* ov = reinterpret_cast<uint4*>(dx) + (size_t)n * HW * GN_G;
-  for (int p = p0 + row; p < p1; p += GN_ROWS) {
-    float f[8], d[8];
-    unpack8(__ldg(xv + (size_t)p * GN_G + g), f);
-    unpack8(__ldg(dv + (size_t)p * GN_G + g), d);
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // column sums of dx (the bias gradient of the conv before)
+  for (int p = p0 + row; p < p1; p += GN_ROWS * GN_UNROLL) {
+    uint4 vx[GN_UNROLL], vd[GN_UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (f[j] - mean) * rstd;
-      float gj = d[j];
-      if (relu && !(fmaf(xh, ga[j], be[j]) > 0.f)) gj = 0.f;
-      f[j] = rstd * (gj * ga[j] - a1 - xh * a2);
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      const int pp = p + u * GN_ROWS;
+      vx[u] = pp < p1 ? __ldg(xv + (size_t)pp * GN_G + g) : make_uint4(0, 0, 0, 0);
+      vd[u] = pp < p1 ? __ldg(dv + (size_t)pp * GN_G + g) : make_uint4(0, 0, 0, 0);
     }
-    ov[(size_t)p * GN_G + g] = pack8(f);
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      const int pp = p + u * GN_ROWS;
+      if (pp < p1) {
+        float f[8], d[8];
+        unpack8(vx[u], f);
+        unpack8(vd[u], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (f[j] - mean) * rstd;
+          float gj = d[j];
+          if (relu && !(fmaf(xh, ga[j], be[j]) > 0.f)) gj = 0.f;
+          f[j] = rstd * (gj * ga[j] - a1 - xh * a2);
+        }
+        const uint4 o = pack8(f);
+        ov[(size_t)pp * GN_G + g] = o;
+        if (dbias) {                 // sum what was actually stored (bf16), like a separate column-sum pass would
+          float r8[8];
+          unpack8(o, r8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cs[j] += r8[j];
+        }
+      }
+    }
+  }
+  if (dbias) {
+    __shared__ float red[GN_ROWS][GN_G][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[row][g][j] = cs[j];
+    __syncthreads();
+    if (row == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = 0.f;
+        for (int k = 0; k < GN_ROWS; ++k) t += red[k][g][j];
+        atomicAdd(dbias + g * 8 + j, t);
+      }
+    }
   }
 }
 
@@ -212,10 +279,12 @@ extern "C" int ut2_groupnorm_relu_fwd(const void* x, const float* gamma, const f
   return ut2_check_launch("groupnorm_fwd");
 }
 
-// ws: double[N*32*2] scratch; dgamma/dbeta are accumulated (+=) in fp32.
+// ws: double[N*32*2] scratch; dgamma/dbeta are accumulated (+=) in fp32. dbias_prev (optional, float[256]) receives
+// += the column sums of dx, i.e. the bias gradient of the convolution that feeds this GroupNorm.
 extern "C" int ut2_groupnorm_relu_bwd(const void* dy, const void* x, const double* stats, const float* gamma,
                                       const float* beta, float eps, void* dx, float* dgamma, float* dbeta,
-                                      double* ws, int N, int HW, int C, int G, int relu, void* stream) {
+                                      float* dbias_prev, double* ws, int N, int HW, int C, int G, int relu,
+                                      void* stream) {
   if (C != 256 || G != 32) return ut2_fail(-2, "groupnorm: only GroupNorm(32, 256) is supported");
   cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * N * GN_G * 2, STREAM);
   if (e != cudaSuccess) return ut2_fail((int)e, "groupnorm: memset failed");
@@ -224,6 +293,6 @@ extern "C" int ut2_groupnorm_relu_bwd(const void* dy, const void* x, const doubl
   gn_bwd_reduce_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats, gamma,
                                                  beta, eps, ws, dgamma, dbeta, HW, ppb, relu);
   gn_bwd_apply_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats, ws, gamma,
-                                                beta, eps, static_cast<bf16*>(dx), HW, ppb, relu);
+                                                beta, eps, static_cast<bf16*>(dx), dbias_prev, HW, ppb, relu);
   return ut2_check_launch("groupnorm_bwd");
 }

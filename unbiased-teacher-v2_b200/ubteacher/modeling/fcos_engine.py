@@ -37,11 +37,11 @@ class Conv:
         return ops.conv2d(x, self.wf, self.cout, self.k, self.k, self.stride, self.pad, self.scale, self.shift,
                           residual, relu, out, res_up2)
 
-    def wgrad(self, x, g):
+    def wgrad(self, x, g, bias_done=False):
         if not self.trainable:
             return
         ops.conv2d_wgrad(x, g, self.cout, self.k, self.k, self.stride, self.pad, self.dw, self.bn_scale, self.cout_store)
-        if self.bias:
+        if self.bias and not bias_done:
             ops.colsum(g.view(-1, self.cout), self.db)
 
     def dgrad(self, g, in_hw, residual=None, relu_mask=None):
@@ -386,8 +386,8 @@ class FcosEngine:
                     conv, gname = self.towers[t][i]
                     xin, c, stats = saved[i]
                     gam, bet, dgam, dbet = self.gn[gname]
-                    dc = ops.groupnorm_relu_bwd(dx, c, stats, gam, bet, dgam, dbet)
-                    conv.wgrad(xin, dc)
+                    dc = ops.groupnorm_relu_bwd(dx, c, stats, gam, bet, dgam, dbet, dbias_prev=conv.db)
+                    conv.wgrad(xin, dc, bias_done=True)       # bias gradient came out of the GroupNorm backward
                     dx = conv.dgrad(dc, (h, w), residual=acc if i == 0 else None)
                 acc = dx
             dfeat.append(acc)

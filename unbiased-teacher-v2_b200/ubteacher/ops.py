@@ -63,12 +63,12 @@ def groupnorm_relu_fwd(x, gamma, beta, eps=1e-5, relu=True):
     return y, stats
 
 
-def groupnorm_relu_bwd(dy, x, stats, gamma, beta, dgamma, dbeta, eps=1e-5, relu=True):
+def groupnorm_relu_bwd(dy, x, stats, gamma, beta, dgamma, dbeta, eps=1e-5, relu=True, dbias_prev=None):
     N, H, W, C = x.shape
     dx = torch.empty_like(x)
     ws = torch.empty((N, 32, 2), dtype=torch.float64, device=x.device)
-    _C.counted_call("ut2_groupnorm_relu_bwd", dy, x, stats, gamma, beta, f32(eps), dx, dgamma, dbeta, ws, N, H * W, C,
-                    32, int(relu))
+    _C.counted_call("ut2_groupnorm_relu_bwd", dy, x, stats, gamma, beta, f32(eps), dx, dgamma, dbeta, dbias_prev, ws, N,
+                    H * W, C, 32, int(relu))
     _C.launch_count += 1
     return dx
 
