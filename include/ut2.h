@@ -131,6 +131,84 @@ int ut2_pack_conv_weight(const float* w, void* wf, void* wt, int Cout, int Cin, 
 int ut2_pack_conv_weights_batched(const void* descs, int num, long long total, const float* arena, const float* scales,
                                   void* packed, void* stream);
 
+/* ================================================================ Faster R-CNN half
+ * [D2] = Detectron2 v0.6 (not on disk; behaviour restated in SURVEY.md appendix B). */
+
+/* ---------------------------------------------------------------- generic batched NMS
+ * [D2] batched_nms -> [tv] batched_nms/nms as called by [D2] find_top_rpn_proposals (modeling/proposal_generator/
+ * rpn.py:72-74) and [D2] fast_rcnn_inference (modeling/roi_heads/fast_rcnn.py:1112-1119). boxes [N,M,4], scores [N,M]
+ * (non-finite = dropped), tie [N,M] tie-break key (NULL: slot index), cls [N,M], cnt [N] used slots. Visits candidates
+ * by (score desc, tie asc); coordinate trick iff 4*n_valid <= trick_limit else per-class on raw boxes (torchvision's
+ * switch). keep_idx [N,max_keep] = slot indices of the first max_keep survivors, keep_cnt [N]. M <= 16384. */
+long long ut2_nms_workspace_bytes(int N, int M);
+int ut2_nms_batched(int N, int M, const float* boxes, const float* scores, const int* tie, const int* cls, const int* cnt,
+                    float thr, int trick_limit, int max_keep, void* workspace, long long workspace_bytes, int* keep_idx,
+                    int* keep_cnt, void* stream);
+/* dst[img,k,:] = src[img, idx[img,k], :] for k < cnt[img], else 0; rows of W elements of elem_bytes (4 | 8) */
+int ut2_gather_rows(int N, int M, int K, int W, int elem_bytes, const void* src, const int* idx, const int* cnt, void* dst,
+                    void* stream);
+
+/* ---------------------------------------------------------------- RPN (modeling/proposal_generator/rpn.py)
+ * rpn_out: fused predictor output, level-major [N*sum(H_l*W_l), 16] bf16 (0..2 objectness, 3+4a+k deltas, 15 pad);
+ * hw / strides / cell (cell anchors [levels][3][4], [D2] DefaultAnchorGenerator) are HOST arrays.
+ * ut2_rpn_label_anchors: label_and_sample_anchors[_pseudo] (rpn.py:78-150): [D2] pairwise_iou + Matcher(lo, hi,
+ * allow_low_quality) + subsample_labels; the randperm draw is a per-anchor uint32 key (keys [N,A] or hashed from seed):
+ * the smallest (key, index) win. labels int8 [N,A] in {-1,0,1}; matched int32 [N,A] = argmax ground truth. */
+long long ut2_rpn_label_workspace_bytes(int N, long long A, int G);
+int ut2_rpn_label_anchors(int num_levels, const int* hw, const int* strides, const float* cell, int N, int G,
+                          const float* gt_boxes, const int* gt_cnt, const unsigned int* keys, unsigned int seed,
+                          int batch_per_image, float pos_fraction, float lo_thr, float hi_thr, void* workspace,
+                          long long workspace_bytes, signed char* labels, int* matched, void* stream);
+/* PseudoLabRPN.losses (rpn.py:153-225): BCE-with-logits over sampled anchors (x matched teacher score when gt_scores
+ * is given) and L1 on the positives' deltas ([D2] _dense_box_regression_loss, Box2BoxTransform weights 1), both
+ * / (batch_per_image * N). acc double[2]; losses float[2] = {loss_rpn_cls, loss_rpn_loc}; gout float[2]. */
+int ut2_rpn_loss_fwd(int num_levels, const int* hw, const int* strides, const float* cell, int N, int G, const void* rpn_out,
+                     const signed char* labels, const int* matched, const float* gt_boxes, const float* gt_scores,
+                     const int* gt_cnt, int batch_per_image, double* acc, float* losses, void* stream);
+int ut2_rpn_loss_bwd(int num_levels, const int* hw, const int* strides, const float* cell, int N, int G, const void* rpn_out,
+                     const signed char* labels, const int* matched, const float* gt_boxes, const float* gt_scores,
+                     const int* gt_cnt, int batch_per_image, const float* gout, void* drpn, void* stream);
+/* first half of [D2] find_top_rpn_proposals (rpn.py:72-74): per (image, level) top pre_topk logits (ties: lower anchor
+ * index), Box2BoxTransform.apply_deltas, clip to image_hw [N,2] (device), invalid -> score -inf. Feed to ut2_nms_batched. */
+int ut2_rpn_select_decode(int num_levels, const int* hw, const int* strides, const float* cell, int N, const void* rpn_out,
+                          const float* image_hw, int pre_topk, float scale_clamp, int Mcap, float* cand_box,
+                          float* cand_score, int* cand_canon, int* cand_lvl, int* cand_cnt, void* stream);
+
+/* ---------------------------------------------------------------- ROI heads (modeling/roi_heads/roi_heads.py, fast_rcnn.py)
+ * ut2_roi_sample: label_and_sample_proposals[_pseudo] (roi_heads.py:138-270) — append GT, Matcher(iou_thr), sample Rcap
+ * ROIs with <= pos_fraction foreground by (key, index); copies gt class / box and, for pseudo labels, the teacher score
+ * (gt_confid) and box std (gt_loc_std). Outputs [N,Rcap,...] fg first; rows >= roi_cnt[img] have class -1. */
+int ut2_roi_sample(int N, int Pcap, int G, int Rcap, const float* prop_boxes, const int* prop_cnt, const float* gt_boxes,
+                   const long long* gt_classes, const int* gt_cnt, const float* gt_scores, const float* gt_std,
+                   const unsigned int* keys, int key_ld, unsigned int seed, float pos_fraction, float iou_thr, int num_classes,
+                   int append_gt, float* roi_box, long long* roi_cls, float* roi_gtbox, float* roi_conf, float* roi_std,
+                   int* roi_src, int* roi_cnt, void* stream);
+/* [D2] ROIPooler(7x7, ROIAlignV2, sampling_ratio 0) -> [tv] roi_align(aligned=True) (roi_heads.py:118). feats / dfeats:
+ * HOST arrays of per-level device pointers (NHWC bf16 / fp32 accumulators); out / dout [N*Rcap, 7, 7, C] bf16. */
+int ut2_roi_align_fwd(int num_levels, const void* const* feats, const int* hw, const float* scales, int N, int C, int Rcap,
+                      const float* rois, const int* roi_cnt, void* out, void* stream);
+int ut2_roi_align_bwd(int num_levels, float* const* dfeats, const int* hw, const float* scales, int N, int C, int Rcap,
+                      const float* rois, const int* roi_cnt, const void* dout, void* stream);
+/* FastRCNNFocaltLossBoundaryVarOutputLayers.losses (fast_rcnn.py:834-1084): FocalLoss(gamma)/R; mode 0 'nlloss' box loss
+ * [L1 + nll_w * NLL * IoU(pred, gt)]/R, mode 1 'tsbetter' teacher-better-than-student masked L1 / R. pred [N*Rcap, 96]
+ * bf16 (0..80 scores | 81..84 deltas | 85..88 std). acc double[2], losses float[2] = {loss_cls, loss_box_reg}. */
+int ut2_fastrcnn_loss_fwd(int N, int Rcap, const void* pred, const float* rois, const long long* gt_cls, const float* gt_box,
+                          const float* gt_std, const int* roi_cnt, int mode, float wx, float wy, float clamp, float gamma,
+                          float nll_w, float ts_better, float t_cert, double* acc, float* losses, void* stream);
+int ut2_fastrcnn_loss_bwd(int N, int Rcap, const void* pred, const float* rois, const long long* gt_cls, const float* gt_box,
+                          const float* gt_std, const int* roi_cnt, int mode, float wx, float wy, float clamp, float gamma,
+                          float nll_w, float ts_better, float t_cert, const float* gout, void* dpred, void* stream);
+/* inference (fast_rcnn.py:1086-1125 -> [D2] fast_rcnn_inference): softmax, Box2BoxXYXYTransform.apply_deltas, clip,
+ * p > score_thr -> candidates (then ut2_nms_batched by class) -> ut2_fastrcnn_gather (adds pred_boxes_std, :1122-1123). */
+int ut2_fastrcnn_candidates(int N, int Rcap, const void* pred, const float* rois, const int* roi_cnt, const float* image_hw,
+                            float wx, float wy, float clamp, float score_thr, int Ccap, float* cand_box, float* cand_score,
+                            int* cand_cls, int* cand_canon, int* cand_cnt, int* overflow, void* stream);
+int ut2_fastrcnn_gather(int N, int Ccap, int K, int Rcap, const int* keep_idx, const int* keep_cnt, const float* cand_box,
+                        const float* cand_score, const int* cand_canon, const void* pred, float* out_box, float* out_score,
+                        long long* out_cls, float* out_std, int* out_roi, int* out_cnt, void* stream);
+int ut2_add_f32_bf16(const float* a, const void* b /* bf16, optional */, void* out, long long n, void* stream);
+int ut2_subsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream);   /* [D2] LastLevelMaxPool */
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,8 +119,7 @@ def _smallest_by_key(cand: torch.Tensor, keys: torch.Tensor, n: int) -> torch.Te
     """The n entries of `cand` (index tensor) with the smallest (key, index), in that order."""
     if n <= 0 or cand.numel() == 0:
         return cand[:0]
-    k = keys[cand].to(torch.int64) * (1 << 32) + cand.to(torch.int64)
-    return cand[torch.argsort(k)[:n]]
+    return cand[torch.argsort(keys[cand].to(torch.int64), stable=True)[:n]]      # cand is ascending: ties -> lower index
 
 
 def subsample_labels(labels: torch.Tensor, num: int, pos_frac: float, bg_label: int, keys: torch.Tensor):

@@ -44,7 +44,7 @@ def _conv(a):
         return ctypes.c_void_p(0)
     if isinstance(a, torch.Tensor):
         return ctypes.c_void_p(a.data_ptr())
-    if isinstance(a, ctypes.Array):
+    if isinstance(a, (ctypes.Array, ctypes._SimpleCData)):
         return a
     if isinstance(a, bool):
         return ctypes.c_int(int(a))
