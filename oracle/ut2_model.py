@@ -26,8 +26,8 @@ def conv_bn(x, sd, p, stride=1, pad=0):
     return frozen_bn(F.conv2d(x, sd[p + ".weight"], None, stride, pad), sd, p + ".norm")
 
 
-def backbone(sd, x):
-    """[D2] BasicStem + 4 bottleneck stages (STRIDE_IN_1X1) -> res3, res4, res5; FPN + LastLevelP6P7(p5)."""
+def trunk(sd, x):
+    """[D2] BasicStem + 4 bottleneck stages (STRIDE_IN_1X1) -> {"res2".."res5"}."""
     bu = "backbone.bottom_up."
     x = F.relu(conv_bn(x, sd, bu + "stem.conv1", 2, 3))
     x = F.max_pool2d(x, 3, 2, 1)
@@ -42,12 +42,25 @@ def backbone(sd, x):
             out = conv_bn(out, sd, p + "conv3")
             x = F.relu(out + sc)
         feats[stage] = x
+    return feats
+
+
+def fpn_topdown(sd, feats, levels):
+    """[D2] FPN (fuse "sum", nearest 2x top-down): returns {level: output} for the given level numbers (descending)."""
     lat = lambda l, c: F.conv2d(c, sd[f"backbone.fpn_lateral{l}.weight"], sd[f"backbone.fpn_lateral{l}.bias"])
     outc = lambda l, t: F.conv2d(t, sd[f"backbone.fpn_output{l}.weight"], sd[f"backbone.fpn_output{l}.bias"], 1, 1)
-    l5 = lat(5, feats["res5"])
-    l4 = lat(4, feats["res4"]) + F.interpolate(l5, scale_factor=2.0, mode="nearest")
-    l3 = lat(3, feats["res3"]) + F.interpolate(l4, scale_factor=2.0, mode="nearest")
-    p5, p4, p3 = outc(5, l5), outc(4, l4), outc(3, l3)
+    prev, outs = None, {}
+    for l in levels:
+        cur = lat(l, feats[f"res{l}"])
+        prev = cur if prev is None else cur + F.interpolate(prev, scale_factor=2.0, mode="nearest")
+        outs[l] = outc(l, prev)
+    return outs
+
+
+def backbone(sd, x):
+    """FCOS backbone: trunk -> FPN p3..p5 + LastLevelP6P7(p5) (backbone/fpn.py:11-78)."""
+    o = fpn_topdown(sd, trunk(sd, x), (5, 4, 3))
+    p5, p4, p3 = o[5], o[4], o[3]
     p6 = F.conv2d(p5, sd["backbone.top_block.p6.weight"], sd["backbone.top_block.p6.bias"], 2, 1)
     p7 = F.conv2d(F.relu(p6), sd["backbone.top_block.p7.weight"], sd["backbone.top_block.p7.bias"], 2, 1)
     return [p3, p4, p5, p6, p7]

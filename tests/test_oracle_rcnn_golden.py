@@ -129,3 +129,26 @@ def test_rpn_proposals_shape_and_order():
         assert len(s) <= 50 and (s[:-1] >= s[1:]).all()
         assert (b[:, 0] >= 0).all() and (b[:, 2] <= w).all() and (b[:, 3] <= h).all()
         assert ((b[:, 2] - b[:, 0]) > 0).all()
+
+
+def test_oracle_model_runs_end_to_end_on_cpu():
+    """The restated detector + step (oracle/ut2_rcnn_model.py) on a tiny input: losses finite, gradients reach the trunk,
+    the teacher branch yields <= 100 detections per image."""
+    from oracle import ut2_rcnn_model as RM
+    sd = RM.init_state_dict(3)
+    n = sum(v.numel() for k, v in sd.items() if ".norm." not in k)
+    assert abs(n - 41.38e6) < 0.05e6                    # SURVEY.md A.5
+    g = torch.Generator().manual_seed(4)
+    imgs = [torch.randint(0, 256, (3, 64, 96), generator=g, dtype=torch.uint8)]
+    gt = {"boxes": [torch.tensor([[8.0, 10.0, 60.0, 50.0], [30.0, 5.0, 90.0, 40.0]])], "classes": [torch.tensor([3, 17])]}
+    A = 3 * (16 * 24 + 8 * 12 + 4 * 6 + 2 * 3 + 1 * 2)
+    keys = [torch.randint(0, 2 ** 32, (A,), generator=g, dtype=torch.int64)]
+    kroi = [torch.randint(0, 2 ** 32, (1200,), generator=g, dtype=torch.int64)]
+    w = sd["backbone.bottom_up.res3.0.conv1.weight"].requires_grad_(True)
+    losses, aux = RM.forward_train(sd, imgs, gt, "supervised", keys, kroi)
+    assert set(losses) == {"loss_rpn_cls", "loss_rpn_loc", "loss_cls", "loss_box_reg"}
+    sum(losses.values()).backward()
+    assert all(torch.isfinite(v) for v in losses.values()) and w.grad is not None and float(w.grad.abs().sum()) > 0
+    sd["backbone.bottom_up.res3.0.conv1.weight"] = w.detach()
+    props, dets, _ = RM.forward_teacher(sd, imgs)
+    assert len(dets[0]["scores"]) <= 100 and props[0].shape[0] <= 1000

@@ -71,6 +71,7 @@ class ParamArena:
         self.views = OrderedDict((n, _view(self.data, self.offset[n], sp.shape)) for n, sp in self.specs.items())
         self.gviews = OrderedDict((n, _view(self.grad, self.offset[n], sp.shape)) for n, sp in self.specs.items()
                                   if sp.group in ("decay", "nodecay"))
+        self.export_shape = {}     # name -> checkpoint shape where it differs from the logical view (fc1: [1024, 12544])
 
     def flat(self, name):
         """Flat fp32 slice of one entry (physical order)."""
@@ -82,8 +83,8 @@ class ParamArena:
         return self.grad[o:o + self.specs[name].numel]
 
     def state_dict(self, prefix=""):
-        return OrderedDict((prefix + n, v) for n, v in self.views.items()
-                           if self.specs[n].persistent and not n.startswith("_"))
+        return OrderedDict((prefix + n, v.reshape(self.export_shape[n]) if n in self.export_shape else v)
+                           for n, v in self.views.items() if self.specs[n].persistent and not n.startswith("_"))
 
     def load_state_dict(self, sd, strict=True):
         missing = []

@@ -1,1 +1,1 @@
-from .trainer import UBTeacherTrainer  # noqa: F401
+from .trainer import UBRCNNTeacherTrainer, UBTeacherTrainer  # noqa: F401

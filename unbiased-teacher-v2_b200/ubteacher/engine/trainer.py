@@ -78,14 +78,14 @@ class UBTeacherTrainer:
         self.optimizer = self.build_optimizer(cfg, model)
         model_teacher = self.build_model(cfg)
         self.model_teacher = model_teacher
-        self.model_teacher.eval()                       # trainer.py:55
+        self._set_teacher_mode(model_teacher)
         self.model = model
         self.model.train()
         self.data_loader = data_loader if data_loader is not None else self.build_train_loader(cfg)
         self._data_loader_iter = iter(self.data_loader)
         self.scheduler = self.build_lr_scheduler(cfg, self.optimizer)
         self.ensem_ts_model = EnsembleTSModel(model_teacher, model)
-        self.pseudo_generator = PseudoGenerator(cfg)
+        self.pseudo_generator = self._make_pseudo_generator(cfg)
         self.start_iter = 0
         self.iter = 0
         self.max_iter = cfg.SOLVER.MAX_ITER
@@ -100,6 +100,12 @@ class UBTeacherTrainer:
             torch.distributed.broadcast(model.engine.arena.data, 0)
             model.engine.refresh_operands()
             self.optimizer.grad_scale = 1.0 / comm.get_world_size()
+
+    def _make_pseudo_generator(self, cfg):
+        return PseudoGenerator(cfg)
+
+    def _set_teacher_mode(self, model_teacher):
+        model_teacher.eval()                            # trainer.py:55
 
     # ---------------------------------------------------------------- builders ([D2] DefaultTrainer API)
     @classmethod
@@ -316,3 +322,78 @@ class UBTeacherTrainer:
     def _copy_main_model(self):
         self.model_teacher.engine.arena.copy_from(self.model.engine.arena)
         self.model_teacher.engine.refresh_operands()
+
+
+class UBRCNNTeacherTrainer(UBTeacherTrainer):
+    """The Faster R-CNN Unbiased-Teacher-v2 loop (reference: ubteacher/engine/trainer.py:613-968): same surface as
+    ``UBTeacherTrainer``; ``run_step_full_semisup`` follows :786-912 (teacher on the weak views -> threshold_bbox at
+    BBOX_THRESHOLD -> student on labeled (strong + weak) and on strongly augmented unlabeled images with the pseudo
+    labels; loss weights :880-905). Teacher and student are ``RcnnEngine`` replicas; pseudo labels stay on the device."""
+
+    def _make_pseudo_generator(self, cfg):
+        return None           # the R-CNN trainer thresholds the ROI-head detections itself (trainer.py:727-769)
+
+    def _set_teacher_mode(self, model_teacher):
+        model_teacher.train()  # the reference never switches the R-CNN teacher to eval (trainer.py:628-629)
+
+    def enable_cuda_graph(self, flag=True):
+        if flag:
+            raise NotImplementedError("R-CNN step: the anchor / proposal sampling keys are per-launch parameters; "
+                                      "graph replay would freeze the draw (planned: device-resident seed)")
+        self.use_cuda_graph = False
+
+    # ---------------------------------------------------------------- pseudo-labeling (trainer.py:727-769)
+    def threshold_bbox(self, dets, thres=0.7, proposal_type="roih"):
+        from .. import ops
+        from ..modeling.fcos.fcos_outputs import BoxSet
+        if proposal_type != "roih":
+            raise ValueError("Error in proposal type.")
+        o = ops.threshold_scatter(dets, 0, float(thres))
+        return BoxSet(o["pred_boxes"], o["pred_classes"], o["count"], o["reg_pred_std"], o["scores"])
+
+    def process_pseudo_label(self, proposals_rpn_unsup_k, cur_threshold, proposal_type, psedo_label_method=""):
+        if psedo_label_method != "thresholding":
+            raise ValueError("Unkown pseudo label boxes methods")
+        out = self.threshold_bbox(proposals_rpn_unsup_k, thres=cur_threshold, proposal_type=proposal_type)
+        return out, out.counts.float().mean()
+
+    def add_label(self, unlabled_data, label, labeltype=""):
+        for d in unlabled_data:
+            d["instances"] = label          # the whole batch's device-resident pseudo-label BoxSet
+        return unlabled_data
+
+    # ---------------------------------------------------------------- the step (trainer.py:786-912)
+    def _step_body(self, data, data_time, device_lr=False, bookkeeping=True):
+        ss = self.cfg.SEMISUPNET
+        label_data_q, label_data_k, unlabel_data_q, unlabel_data_k = data
+        all_label_data = label_data_q + label_data_k if ss.USE_SUP_STRONG == "both" else label_data_k
+        record = {}
+        if self.iter < ss.BURN_UP_STEP:
+            losses, pending = self.model.forward_train(all_label_data, "supervised")
+            record.update(losses)
+            self.model.backward_pending(pending, [1.0, 1.0, 1.0, 1.0])
+        else:
+            if self.iter == ss.BURN_UP_STEP:
+                self._update_teacher_model(keep_rate=0.0)                     # copy, then the EMA below (SURVEY A.3 #9)
+            if (self.iter - ss.BURN_UP_STEP) % ss.TEACHER_UPDATE_ITER == 0:
+                self._update_teacher_model(keep_rate=ss.EMA_KEEP_RATE)
+            record["EMA_rate"] = ss.EMA_KEEP_RATE
+            # teacher on the weak views; never switched to eval (trainer.py:830-837)
+            _, proposals_rpn_unsup_k, proposals_roih_unsup_k, _ = self.model_teacher(unlabel_data_k, branch="unsup_data_weak")
+            pseudo, _ = self.process_pseudo_label(proposals_roih_unsup_k, ss.BBOX_THRESHOLD, "roih", "thresholding")
+            unlabel_data_q = self.add_label(self.remove_label(unlabel_data_q), pseudo)
+            unlabel_data_k = self.add_label(self.remove_label(unlabel_data_k), pseudo)
+            lam, mu = ss.UNSUP_LOSS_WEIGHT, ss.UNSUP_REG_LOSS_WEIGHT
+            losses, pending = self.model.forward_train(all_label_data, "supervised")
+            record.update(losses)
+            self.model.backward_pending(pending, [1.0, 1.0, 1.0, 1.0])
+            losses_u, pending_u = self.model.forward_train(unlabel_data_q, "unsup_data_train")
+            record.update({k + "_pseudo": v for k, v in losses_u.items()})
+            # loss_rpn_loc_pseudo * 0, loss_box_reg_pseudo * UNSUP_REG_LOSS_WEIGHT, the two classification terms * UNSUP_LOSS_WEIGHT
+            self.model.backward_pending(pending_u, [lam, 0.0, lam, mu])
+        record["data_time"] = data_time
+        self._write_metrics(record, bookkeeping)
+        if comm.get_world_size() > 1:
+            torch.distributed.all_reduce(self.model.engine.arena.grad)
+        self.optimizer.zero_grad()
+        self.optimizer.step(use_device_lr=device_lr)
