@@ -167,7 +167,7 @@ def init_state_dict(seed=0):
         if bias:
             sd[name + ".bias"] = torch.zeros(cout)
         if bn:
-            sd[name + ".norm.weight"] = torch.ones(cout)
+            sd[name + ".norm.weight"] = torch.full((cout,), 0.04 if "stem." in name else 0.25 if name.endswith("conv3") else 1.0)
             sd[name + ".norm.bias"] = torch.zeros(cout)
             sd[name + ".norm.running_mean"] = torch.zeros(cout)
             sd[name + ".norm.running_var"] = torch.ones(cout) - M.BN_EPS
@@ -185,7 +185,7 @@ def init_state_dict(seed=0):
             conv(p + "conv3", cout, mid, 1, bn=True)
             cin = cout
     for l, c in ((2, 256), (3, 512), (4, 1024), (5, 2048)):
-        conv(f"backbone.fpn_lateral{l}", 256, c, 1, bias=True, std=math.sqrt(1.0 / c))
+        conv(f"backbone.fpn_lateral{l}", 256, c, 1, bias=True, std=math.sqrt(1.0 / c))      # c2_xavier-like
         conv(f"backbone.fpn_output{l}", 256, 256, 3, bias=True, std=math.sqrt(1.0 / 2304))
     rp = "proposal_generator.rpn_head."
     conv(rp + "conv", 256, 256, 3, bias=True, std=0.01)

@@ -199,7 +199,10 @@ class EngineBase:
             fan_out = v.shape[0] * v.shape[2] * v.shape[3]
             return t.normal_(0, math.sqrt(2.0 / fan_out), generator=g)           # MSRA fill
         if ".norm.weight" in name:
-            return t.fill_(1.0)
+            # FrozenBN gamma. The pretrained R-50 (MSRA pickle, unreachable offline) carries statistics that keep the
+            # residual stream O(1); with identity FrozenBN a randomly initialised trunk grows to ~3e3 by res5 and one SGD
+            # step diverges. Offline stand-in: damp the stem (pixel-scale input) and each block's residual branch.
+            return t.fill_(0.04 if "stem." in name else 0.25 if ".conv3." in name else 1.0)
         if ".norm.running_var" in name:
             return t.fill_(1.0 - BN_EPS)
         if ".norm." in name:
