@@ -24,17 +24,20 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-FLOP_PER_11 = 4063.6e9      # algorithmic FLOPs of one FCOS step at B_l = B_u = 1, 800x1344
+FLOP_PER_11 = {"fcos": 4063.6e9, "rcnn": 3888.2e9}   # algorithmic FLOPs of one step at B_l = B_u = 1, 800x1344
+RECIPE = {"fcos": "configs/FCOS/coco-standard/fcos_R_50_ut2_sup1_run0.yaml",
+          "rcnn": "configs/Faster-RCNN/coco-standard/faster_rcnn_R_50_FPN_ut2_sup1_run0.yaml"}
+ARCH_NAME = {"fcos": "FCOS R50-FPN", "rcnn": "Faster-RCNN R50-FPN"}
 METRIC = "images/sec per UT2 train step (teacher fwd + student fwd/bwd)"
 FULL_PIXELS = 800 * 1344
 
 
-def build_cfg(n_label, n_unlabel, device="cuda"):
+def build_cfg(n_label, n_unlabel, device="cuda", arch="fcos"):
     from ubteacher.config import add_ubteacher_config
     from ubteacher.d2compat.config import get_cfg
     cfg = get_cfg()
     add_ubteacher_config(cfg)
-    cfg.merge_from_file(os.path.join(PKG, "configs/FCOS/coco-standard/fcos_R_50_ut2_sup1_run0.yaml"))
+    cfg.merge_from_file(os.path.join(PKG, RECIPE[arch]))
     cfg.merge_from_list(["SEMISUPNET.BURN_UP_STEP", 0, "SOLVER.IMG_PER_BATCH_LABEL", n_label,
                          "SOLVER.IMG_PER_BATCH_UNLABEL", n_unlabel, "MODEL.DEVICE", device, "SEED", 7])
     return cfg
@@ -196,6 +199,35 @@ def cpu_step_runner(cfg, h, w, n_label=1, n_unlabel=1):
     return step, torch.get_num_threads()
 
 
+def cpu_step_runner_rcnn(cfg, h, w, n_label=1, n_unlabel=1):
+    """One oracle UT2 Faster R-CNN step (oracle/ut2_rcnn_model.py:ut2_rcnn_step) on the host cores."""
+    import torch
+    from oracle import ut2_rcnn_model as RM
+    student = RM.init_state_dict(7)
+    teacher = {k: v.clone() for k, v in student.items()}
+    mom = {}
+    s = cfg.SEMISUPNET
+    ocfg = {"UNSUP_LOSS_WEIGHT": s.UNSUP_LOSS_WEIGHT, "UNSUP_REG_LOSS_WEIGHT": s.UNSUP_REG_LOSS_WEIGHT,
+            "EMA_KEEP_RATE": s.EMA_KEEP_RATE, "BBOX_THRESHOLD": s.BBOX_THRESHOLD, "WEIGHT_DECAY": cfg.SOLVER.WEIGHT_DECAY,
+            "MOMENTUM": cfg.SOLVER.MOMENTUM, "LR": 1e-5}
+    state = {"i": 0}
+    Hp, Wp = (h + 31) // 32 * 32, (w + 31) // 32 * 32
+    A, hh, ww = 0, Hp // 4, Wp // 4
+    for _ in range(5):
+        A += 3 * hh * ww
+        hh, ww = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+
+    def step():
+        g = torch.Generator().manual_seed(77 + state["i"])
+        batch = cpu_batch(n_label, n_unlabel, h, w, 20260 + state["i"])
+        rk = lambda n, m: [torch.randint(0, 2 ** 32, (m,), generator=g, dtype=torch.int64) for _ in range(n)]
+        keys = {"rpn_sup": rk(2 * n_label, A), "roi_sup": rk(2 * n_label, 1200), "rpn_unsup": rk(n_unlabel, A),
+                "roi_unsup": rk(n_unlabel, 1200)}
+        RM.ut2_rcnn_step(student, teacher, mom, batch, ocfg, state["i"] == 0, keys)
+        state["i"] += 1
+    return step, torch.get_num_threads()
+
+
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the step cannot run (Detectron2 absent, hard-coded
     .cuda(): BASELINE.md §2), so this arm times the oracle port of it on the host cores. Each step is a bounded sample:
@@ -206,10 +238,12 @@ def run_reference(args):
         return
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg = build_cfg(1, 1, device="cpu")
+    cfg = build_cfg(1, 1, device="cpu", arch=args.arch)
+    runner = cpu_step_runner if args.arch == "fcos" else cpu_step_runner_rcnn
+    port = "oracle/ut2_model.py:ut2_step" if args.arch == "fcos" else "oracle/ut2_rcnn_model.py:ut2_rcnn_step"
     budget = 240.0
     # calibrate on a 256x320 step, cost ~ linear in pixels
-    step, cores = cpu_step_runner(cfg, 256, 320)
+    step, cores = runner(cfg, 256, 320)
     t0 = time.perf_counter()
     step()
     t_small = time.perf_counter() - t0
@@ -220,7 +254,7 @@ def run_reference(args):
         h, w = (800, 1333) if scale == 1.0 else (int(800 * scale) // 32 * 32, int(1333 * scale) // 32 * 32)
         if per_pixel * h * w * total <= budget:
             break
-    step, cores = cpu_step_runner(cfg, h, w)
+    step, cores = runner(cfg, h, w)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -229,12 +263,12 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     eq_images = 2.0 * (((h + 31) // 32 * 32) * ((w + 31) // 32 * 32)) / FULL_PIXELS
     v = eq_images * args.steps / dt
-    sample = (f"oracle port (oracle/ut2_model.py:ut2_step, fp32 torch CPU), 1 labeled + 1 unlabeled image of {h}x{w} per step "
+    sample = (f"oracle port ({port}, fp32 torch CPU), 1 labeled + 1 unlabeled image of {h}x{w} per step "
               f"({eq_images:.3f} full-size-image equivalents), {args.steps} timed steps")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"FCOS R50-FPN UT2 run_step_full_semisup, label {args.label} + unlabel {args.unlabel} per GPU, "
+            "config": {"workload": f"{ARCH_NAME[args.arch]} UT2 run_step_full_semisup, label {args.label} + unlabel {args.unlabel} per GPU, "
                                    "synthetic 3x800x1333 (reference arm: bounded CPU sample, see cpu_baseline.sample)"},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -252,6 +286,8 @@ def main():
     ap.add_argument("--unlabel", type=int, default=8, help="unlabeled images per GPU per step (B_u)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--arch", default="fcos", choices=["fcos", "rcnn"],
+                    help="fcos = BASELINE config #2 (the headline workload); rcnn = the Faster R-CNN recipe (configs #3 / #5)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -270,9 +306,12 @@ def main():
     from ubteacher import _C, ops
     from ubteacher.d2compat.events import EventStorage
     from ubteacher.data.synthetic import SyntheticTwoCropLoader
-    from ubteacher.engine import UBTeacherTrainer
+    from ubteacher.engine import UBRCNNTeacherTrainer, UBTeacherTrainer
 
-    cfg = build_cfg(args.label * world, args.unlabel * world)
+    Trainer = UBTeacherTrainer if args.arch == "fcos" else UBRCNNTeacherTrainer
+    if args.arch == "rcnn":
+        args.no_graph = True       # sampling keys are per-launch parameters (UBRCNNTeacherTrainer.enable_cuda_graph)
+    cfg = build_cfg(args.label * world, args.unlabel * world, arch=args.arch)
     dev = torch.device("cuda", local)
 
     def barrier():
@@ -308,7 +347,7 @@ def main():
     images_per_step = world * (args.label + args.unlabel)
     # ---- arm 1: inputs resident in HBM ---------------------------------------------------------------------
     loader = SyntheticTwoCropLoader(args.label, args.unlabel, rank=rank, device=dev)
-    tr = UBTeacherTrainer(cfg, data_loader=loader)
+    tr = Trainer(cfg, data_loader=loader)
     tr.storage = EventStorage(0)
     tr.metrics_period = 10 ** 9
     tr.iter = -1
@@ -316,7 +355,8 @@ def main():
     timed(tr, max(args.warmup, 3), False)
     _, _, _, prof, _ = timed(tr, 2, False, profile=True)
     prof_steps = 2
-    tr.enable_cuda_graph(not args.no_graph)
+    if not args.no_graph:
+        tr.enable_cuda_graph(True)
     timed(tr, args.warmup, False)
     clocks = ClockSampler(local) if rank == 0 else None
     secs, launches, _, _, wall = timed(tr, args.steps, False)
@@ -336,7 +376,7 @@ def main():
                 "flops_per_launch_avg": fl / max(len(prof["conv_fwd"]), 1),
                 "wgrad": {"achieved": flw / (msw * 1e-3) / 1e12 if msw > 0 else 0.0, "kernel_ms_per_step": msw / prof_steps,
                           "launches_per_step": len(prof["conv_wgrad"]) / prof_steps},
-                "step_flops_frac": FLOP_PER_11 * (args.label + args.unlabel) / 2.0 * world / secs * args.steps / (world * peak_tf * 1e12)
+                "step_flops_frac": FLOP_PER_11[args.arch] * (args.label + args.unlabel) / 2.0 * world / secs * args.steps / (world * peak_tf * 1e12)
                 if args.label == args.unlabel else None}
     del tr, loader
     torch.cuda.empty_cache()
@@ -344,11 +384,12 @@ def main():
     e2e = None
     if not args.no_e2e:
         loader = SyntheticTwoCropLoader(args.label, args.unlabel, rank=rank, device=None)
-        tr = UBTeacherTrainer(cfg, data_loader=loader)
+        tr = Trainer(cfg, data_loader=loader)
         tr.storage = EventStorage(0)
         tr.metrics_period = 10 ** 9
         tr.iter = -1
-        tr.enable_cuda_graph(not args.no_graph)
+        if not args.no_graph:
+            tr.enable_cuda_graph(True)
         timed(tr, max(args.warmup, 3), True)
         secs2, _, d2h, _, _ = timed(tr, args.steps, True)
         h2d = (2 * args.label + 2 * args.unlabel) * 3 * 800 * 1333 + 2 * args.label * (128 * 4 * 4 + 128 * 8 + 4)
@@ -357,18 +398,20 @@ def main():
         del tr, loader
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        step, cores = cpu_step_runner(build_cfg(1, 1, device="cpu"), 800, 1333)
+        runner = cpu_step_runner if args.arch == "fcos" else cpu_step_runner_rcnn
+        port = "oracle/ut2_model.py:ut2_step" if args.arch == "fcos" else "oracle/ut2_rcnn_model.py:ut2_rcnn_step"
+        step, cores = runner(build_cfg(1, 1, device="cpu", arch=args.arch), 800, 1333)
         t0 = time.perf_counter()
         step()
         dt = time.perf_counter() - t0
         cpu = {"value": 2.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": "oracle port (oracle/ut2_model.py:ut2_step, fp32 torch CPU): one full step with 1 labeled + 1 "
+               "sample": f"oracle port ({port}, fp32 torch CPU): one full step with 1 labeled + 1 "
                          f"unlabeled 3x800x1333 image, {dt:.1f} s, no warm-up"}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"FCOS R50-FPN UT2 run_step_full_semisup, IMG_PER_BATCH_LABEL={args.label} "
+                "config": {"workload": f"{ARCH_NAME[args.arch]} UT2 run_step_full_semisup, IMG_PER_BATCH_LABEL={args.label} "
                                        f"UNLABEL={args.unlabel} per GPU, synthetic uint8 3x800x1333 (padded 800x1344), "
                                        "BURN_UP_STEP=0, random init (cold pseudo-label regime)",
                            "global_batch": images_per_step, "parallelism": f"dp{world}",

@@ -6,10 +6,11 @@ import bench
 from ubteacher import _C
 from ubteacher.d2compat.events import EventStorage
 from ubteacher.data.synthetic import SyntheticTwoCropLoader
-from ubteacher.engine import UBTeacherTrainer
+from ubteacher.engine import UBRCNNTeacherTrainer, UBTeacherTrainer
 B = int(os.environ.get("B", 8))
-cfg = bench.build_cfg(B, B)
-tr = UBTeacherTrainer(cfg, data_loader=SyntheticTwoCropLoader(B, B, device=torch.device("cuda")))
+ARCH = os.environ.get("ARCH", "fcos")
+cfg = bench.build_cfg(B, B, arch=ARCH)
+tr = (UBTeacherTrainer if ARCH == "fcos" else UBRCNNTeacherTrainer)(cfg, data_loader=SyntheticTwoCropLoader(B, B, device=torch.device("cuda")))
 tr.storage = EventStorage(0); tr.metrics_period = 10**9; tr.iter = -1
 for _ in range(3):
     tr.iter += 1; tr.run_step_full_semisup()
