@@ -41,6 +41,14 @@ int ut2_conv2d_nhwc_bf16_fwd(const void* x, int N, int H, int W, int Cin, const 
  * Rows >= cout_store (if > 0) are not written (zero-padded fused predictors). Cin % 64 == 0, Cout % 8 == 0. */
 int ut2_conv2d_nhwc_bf16_wgrad(const void* x, int N, int H, int W, int Cin, const void* dy, int Cout, int R, int S,
                                int stride, int pad, const float* scale, float* dw, int cout_store, void* stream);
+/* The same two operators over a level-major pyramid in ONE launch: x = levels [N, H_l, W_l, Cin] laid back to back
+ * (rows sum_l N*H_l*W_l), y / dy likewise; hw = HOST array {H_0, W_0, H_1, W_1, ...}, <= 5 levels, stride 1. Used for the
+ * FCOS towers and predictors, which apply the same weights to all five FPN levels (fcos/fcos.py:338-376). */
+int ut2_conv2d_levels_bf16_fwd(const void* x, int num_levels, const int* hw, int N, int Cin, const void* w, int Cout, int R,
+                               int S, int pad, const float* scale, const float* shift, const void* residual,
+                               const void* relu_mask, int relu, void* y, void* stream);
+int ut2_conv2d_levels_bf16_wgrad(const void* x, int num_levels, const int* hw, int N, int Cin, const void* dy, int Cout,
+                                 int R, int S, int pad, const float* scale, float* dw, int cout_store, void* stream);
 /* test hook: one im2col-mode TMA load dumped from shared memory (pins the descriptor semantics) */
 int ut2_debug_im2col_probe(const void* x, int N, int H, int W, int C, int R, int S, int stride, int pad, int pixels,
                            int c, int w, int h, int n, int off_w, int off_h, void* out, void* stream);
@@ -72,6 +80,13 @@ int ut2_groupnorm_relu_fwd(const void* x, const float* gamma, const float* beta,
 int ut2_groupnorm_relu_bwd(const void* dy, const void* x, const double* stats, const float* gamma, const float* beta,
                            float eps, void* dx, float* dgamma, float* dbeta, float* dbias_prev /* += colsum(dx), optional */,
                            double* ws, int N, int HW, int C, int G, int relu, void* stream);
+
+/* level-major variants (hws = HOST array of H_l*W_l; statistics per (level, image, group); stats / ws double[levels*N*32*2]) */
+int ut2_groupnorm_relu_levels_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, double* stats,
+                                  int num_levels, const int* hws, int N, int C, int G, int relu, void* stream);
+int ut2_groupnorm_relu_levels_bwd(const void* dy, const void* x, const double* stats, const float* gamma, const float* beta,
+                                  float eps, void* dx, float* dgamma, float* dbeta, float* dbias_prev, double* ws,
+                                  int num_levels, const int* hws, int N, int C, int G, int relu, void* stream);
 
 /* ---------------------------------------------------------------- FCOS targets and losses
  * ut2_fcos_assign_targets: FCOSOutputs._get_ground_truth + compute_targets_for_locations

@@ -137,3 +137,93 @@ def test_conv_wgrad(case):
     ref = wr.grad.permute(0, 2, 3, 1)
     scale = ref.abs().max().item()
     torch.testing.assert_close(dw.cpu(), ref, rtol=2e-3, atol=2e-3 * scale)
+
+
+# --------------------------------------------------------------------------------------- level-major launches
+LEVEL_HW = [(25, 42), (13, 21), (7, 11), (4, 6), (2, 3)]
+
+
+def _level_geom():
+    from ubteacher import ops
+    return ops.LevelGeom(LEVEL_HW, [8, 16, 32, 64, 128])
+
+
+def _split(t, N, C):
+    out, off = [], 0
+    for h, w in LEVEL_HW:
+        out.append(t[off:off + N * h * w].view(N, h, w, C))
+        off += N * h * w
+    return out
+
+
+@pytest.mark.parametrize("cin,cout,aux", [(256, 256, None), (256, 80, None), (80, 256, "res"), (256, 256, "mask")])
+def test_conv_levels_equals_per_level_launches(cin, cout, aux):
+    """One launch over a level-major pyramid == five single-level launches of the same kernel (bit-exact)."""
+    from ubteacher import ops
+    geom, N = _level_geom(), 3
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(geom.L * N, cin, generator=g).bfloat16().cuda()
+    w = (torch.randn(cout, 3, 3, cin, generator=g) / (9 * cin) ** 0.5).bfloat16().cuda()
+    shift = torch.randn(cout, generator=g).cuda()
+    extra = torch.randn(geom.L * N, cout, generator=g).bfloat16().cuda()
+    res = extra if aux == "res" else None
+    mask = extra if aux == "mask" else None
+    y = ops.conv2d_levels(x, geom, N, w, cout, 3, 3, 1, None, shift, res, aux is None, None, mask)
+    xs, es = _split(x, N, cin), _split(extra, N, cout)
+    ys = _split(y, N, cout)
+    for l in range(5):
+        ref = ops.conv2d(xs[l].contiguous(), w, cout, 3, 3, 1, 1, None, shift, es[l] if aux == "res" else None, aux is None,
+                         None, False, es[l] if aux == "mask" else None)
+        assert torch.equal(ys[l], ref), l
+    # and against the fp32 reference of the op
+    ref0 = _ref_fwd(xs[0].cpu(), w.cpu(), 1, 1, None, shift.cpu(), es[0].cpu() if aux == "res" else None, aux is None)
+    if aux == "mask":
+        ref0 = ref0 * (es[0].cpu().float() > 0)
+    assert torch.allclose(ys[0].float().cpu(), ref0, rtol=RTOL, atol=ATOL)
+
+
+def test_wgrad_levels_equals_sum_of_levels():
+    from ubteacher import ops
+    geom, N = _level_geom(), 3
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(geom.L * N, 256, generator=g).bfloat16().cuda()
+    dy = torch.randn(geom.L * N, 80, generator=g).bfloat16().cuda()
+    dw = torch.zeros(80, 3, 3, 256, device="cuda")
+    ops.conv2d_wgrad_levels(x, dy, geom, N, 80, 3, 3, 1, dw, None, 73)
+    ref = torch.zeros_like(dw)
+    for xl, dl in zip(_split(x, N, 256), _split(dy, N, 80)):
+        ops.conv2d_wgrad(xl.contiguous(), dl.contiguous(), 80, 3, 3, 1, 1, ref, None, 73)
+    torch.cuda.synchronize()
+    assert (dw[73:] == 0).all()
+    # same products, different fp32 atomic accumulation order
+    assert torch.allclose(dw, ref, rtol=1e-3, atol=1e-3), (dw - ref).abs().max()
+    # fp32 reference of the op on the largest level
+    xl, dl = _split(x, N, 256)[0].float().cpu(), _split(dy, N, 80)[0].float().cpu()
+    xt = xl.permute(0, 3, 1, 2).requires_grad_(False)
+    wt = torch.zeros(80, 256, 3, 3, requires_grad=True)
+    F.conv2d(xt, wt, padding=1).backward(dl.permute(0, 3, 1, 2))
+    dw0 = torch.zeros(80, 3, 3, 256, device="cuda")
+    ops.conv2d_wgrad(_split(x, N, 256)[0].contiguous(), _split(dy, N, 80)[0].contiguous(), 80, 3, 3, 1, 1, dw0, None, 80)
+    assert torch.allclose(dw0.cpu(), wt.grad.permute(0, 2, 3, 1), rtol=2e-3, atol=2e-2)
+
+
+def test_groupnorm_levels_equals_per_level():
+    from ubteacher import ops
+    geom, N = _level_geom(), 3
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(geom.L * N, 256, generator=g).bfloat16().cuda()
+    dy = torch.randn(geom.L * N, 256, generator=g).bfloat16().cuda()
+    gam = (torch.rand(256, generator=g) + 0.5).cuda()
+    bet = torch.randn(256, generator=g).cuda()
+    y, stats = ops.groupnorm_relu_levels_fwd(x, geom, N, gam, bet)
+    dgam, dbet, dbias = [torch.zeros(256, device="cuda") for _ in range(3)]
+    dx = ops.groupnorm_relu_levels_bwd(dy, x, geom, N, stats, gam, bet, dgam, dbet, dbias_prev=dbias)
+    rg, rb, rbias = [torch.zeros(256, device="cuda") for _ in range(3)]
+    for l, (xl, dl, yl, dxl) in enumerate(zip(_split(x, N, 256), _split(dy, N, 256), _split(y, N, 256), _split(dx, N, 256))):
+        yr, st = ops.groupnorm_relu_fwd(xl.contiguous(), gam, bet)
+        dr = ops.groupnorm_relu_bwd(dl.contiguous(), xl.contiguous(), st, gam, bet, rg, rb, dbias_prev=rbias)
+        # same arithmetic; only the order of the fp64 / fp32 atomics differs -> at most one bf16 ulp
+        assert torch.allclose(yl.float(), yr.float(), rtol=1 / 128, atol=1e-3), l
+        assert torch.allclose(dxl.float(), dr.float(), rtol=1 / 64, atol=2e-3), l
+    assert torch.allclose(dgam, rg, rtol=1e-3, atol=1e-2) and torch.allclose(dbet, rb, rtol=1e-3, atol=1e-2)
+    assert torch.allclose(dbias, rbias, rtol=1e-3, atol=1e-2)

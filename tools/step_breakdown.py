@@ -37,7 +37,11 @@ for k, v in sorted(tot.items(), key=lambda x: -x[1])[:45]:
     if k.startswith("conv"):
         n = len(prof[k]) / STEPS
         kind, shp, flt = k.split(" ")
-        dims, cout = shp.split("->"); N_, H, W, C = map(int, dims.split("x")); R = int(flt[0]); st = int(flt.split("/")[1])
-        P, Q = (H + 2*(R//2) - R)//st + 1, (W + 2*(R//2) - R)//st + 1
-        fl = 2.0 * N_ * P * Q * int(cout) * C * R * R * n
+        dims, cout = shp.split("->"); R = int(flt[0]); st = int(flt.split("/")[1])
+        if "L" in dims:      # level-major launch: N x L<locations> x C
+            N_, L_, C = dims.split("x"); N_, C, PQ = int(N_), int(C), int(L_[1:])
+        else:
+            N_, H, W, C = map(int, dims.split("x"))
+            PQ = ((H + 2*(R//2) - R)//st + 1) * ((W + 2*(R//2) - R)//st + 1)
+        fl = 2.0 * N_ * PQ * int(cout) * C * R * R * n
         print(f"  {v:8.3f} ms n={n:5.1f} {fl/v/1e9:7.1f} TF/s  {k}")

@@ -36,9 +36,33 @@ constexpr int smem_bytes(int stages, bool aux) {
   return 1024 + stages * STAGE_BYTES + BAR_BYTES + (aux ? 16 : 0) * EPI_TILE_BYTES;
 }
 
+constexpr int MAX_LV = 5;          // pyramid levels one launch can cover (shared-weight head convs)
+
+// Per-level geometry of a launch. An ordinary convolution is the 1-level case. Levels are laid back to back in one
+// "level-major" buffer: level l owns rows [row_off[l], row_off[l] + M[l]) of the [sum M, C] activation matrix and
+// m-tiles [tile_off[l], tile_off[l+1]) — tiles never straddle two levels (the last tile of a level is ragged).
+struct LevelTable {
+  int num;
+  int tile_off[MAX_LV + 1];
+  int row_off[MAX_LV];
+  int M[MAX_LV], P[MAX_LV], Q[MAX_LV];
+};
+struct TmapSet {
+  CUtensorMap m[MAX_LV];
+};
+
+__device__ __forceinline__ int level_of(const LevelTable& lt, int tile) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < MAX_LV; ++i)
+    if (i < lt.num && tile >= lt.tile_off[i]) l = i;
+  return l;
+}
+
 struct ConvFwdArgs {
   int M, Cout, ldo;
   int block_n, n_tiles, m_tiles;
+  LevelTable lt;
   int P, Q, stride, pad;
   int R, S, Cin;
   int relu;
@@ -68,7 +92,7 @@ __device__ __forceinline__ uint32_t mask_bf16x2(uint32_t o, uint32_t m) {
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__ CUtensorMap tmap_w,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
                 const ConvFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -93,7 +117,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const int num_kb = a.R * a.S * c_chunks;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmaps_x.m[0]);
     prefetch_tmap(&tmap_w);
     if (a.aux_kind) prefetch_tmap(&tmap_aux);
     for (int s = 0; s < STAGES; ++s) {
@@ -118,12 +142,14 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       // ------------------------------------------------ TMA producer
       uint32_t stage = 0, phase = 0;
       const uint32_t tx_bytes = A_BYTES + a.block_n * BK * 2;
-      const int PQ = a.P * a.Q;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
-        const int m0 = m_tile * BM;
+        const int lv = level_of(a.lt, m_tile);
+        const CUtensorMap* tmap_x = &tmaps_x.m[lv];
+        const int m0 = (m_tile - a.lt.tile_off[lv]) * BM;
+        const int Q = a.lt.Q[lv], PQ = a.lt.P[lv] * Q;
         const int img = m0 / PQ, rem = m0 - img * PQ;
-        const int p0 = rem / a.Q, q0 = rem - p0 * a.Q;
+        const int p0 = rem / Q, q0 = rem - p0 * Q;
         const int w0 = q0 * a.stride - a.pad, h0 = p0 * a.stride - a.pad;
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / c_chunks, c0 = (kb - tap * c_chunks) * BK;
@@ -131,7 +157,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          tma_load_im2col_4d(sa, &tmap_x, &full_bar[stage], c0, w0, h0, img, (uint16_t)s,
+          tma_load_im2col_4d(sa, tmap_x, &full_bar[stage], c0, w0, h0, img, (uint16_t)s,
                              (uint16_t)r);
           tma_load_2d(sa + A_BYTES, &tmap_w, &full_bar[stage], tap * a.Cin + c0,
                       n_tile * a.block_n);
@@ -188,14 +214,18 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     if (use_aux && lane == 0 && (int)blockIdx.x < num_tiles) {   // aux tiles of this CTA's first tile
       const int t = blockIdx.x;
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
+      const int lv = level_of(a.lt, m_tile);
       mbar_arrive_expect_tx(&aux_bar[ew], aux_bytes);
       for (int c = 0; c < my_chunks; ++c)
         tma_load_2d(astage + c * EPI_TILE_BYTES, &tmap_aux, &aux_bar[ew], n_tile * a.block_n + (half + 2 * c) * 64,
-                    m_tile * BM + quad * 32);
+                    a.lt.row_off[lv] + (m_tile - a.lt.tile_off[lv]) * BM + quad * 32);
     }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
-      const int m = m_tile * BM + quad * 32 + lane;
+      const int lv = level_of(a.lt, m_tile);
+      const int ml = (m_tile - a.lt.tile_off[lv]) * BM + quad * 32 + lane;     // row inside the level
+      const bool row_ok = ml < a.lt.M[lv];
+      const int m = a.lt.row_off[lv] + ml;                                      // row in the level-major buffer
       const int nbase = n_tile * a.block_n;
       if (n_tile != staged_n_tile) {            // (re)stage scale / shift of this n-tile: uniform across the 8 warps
         if (staged_n_tile >= 0) asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -206,7 +236,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         staged_n_tile = n_tile;
       }
       size_t rrow = (size_t)m;                 // residual row for the manual path
-      if (a.manual && a.residual && a.res_up2 && m < a.M) {
+      if (a.manual && a.residual && a.res_up2 && row_ok) {
         const int PQ = a.P * a.Q;
         const int img = m / PQ, rem = m - img * PQ;
         const int p = rem / a.Q, q = rem - p * a.Q;
@@ -229,7 +259,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         for (int j = 0; j < 4; ++j) {
           const int cj = c0 + j * 16;
           const int nj = nbase + cj;
-          if (j * 16 < cw && nj < a.Cout && m < a.M) {
+          if (j * 16 < cw && nj < a.Cout && row_ok) {
             float f[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -292,10 +322,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int tn = t + gridDim.x;
         if (lane == 0 && tn < num_tiles) {
           const int n_tile2 = tn % a.n_tiles, m_tile2 = tn / a.n_tiles;
+          const int lv2 = level_of(a.lt, m_tile2);
           mbar_arrive_expect_tx(&aux_bar[ew], aux_bytes);
           for (int c = 0; c < my_chunks; ++c)
             tma_load_2d(astage + c * EPI_TILE_BYTES, &tmap_aux, &aux_bar[ew],
-                        n_tile2 * a.block_n + (half + 2 * c) * 64, m_tile2 * BM + quad * 32);
+                        n_tile2 * a.block_n + (half + 2 * c) * 64,
+                        a.lt.row_off[lv2] + (m_tile2 - a.lt.tile_off[lv2]) * BM + quad * 32);
         }
       }
     }
@@ -320,6 +352,7 @@ constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
 constexpr int WG_SMEM_BYTES = STAGES * WG_STAGE_BYTES + 1024 + 256;
 
 struct ConvWgradArgs {
+  LevelTable lt;        // tile_off = prefix of 64-pixel blocks per level
   int Mpix, Cout, Cin, R, S, P, Q, stride, pad;
   int block_n;      // input-channel tile width (64 / 128 / 256)
   int c_tiles, n_tiles, taps;
@@ -330,7 +363,7 @@ struct ConvWgradArgs {
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ TmapSet tmaps_x,
                   const ConvWgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -353,7 +386,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_g);
-    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmaps_x.m[0]);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -372,21 +405,23 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       const uint32_t tx_bytes = (2 + nblk) * WG_BLK_BYTES;
-      const int PQ = a.P * a.Q;
       const int r = tap / a.S, s = tap - r * a.S;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const int pix0 = kb * WG_PIX;
+        const int lv = level_of(a.lt, kb);
+        const CUtensorMap* tmap_x = &tmaps_x.m[lv];
+        const int pix0 = (kb - a.lt.tile_off[lv]) * WG_PIX;        // first pixel of the block inside its level
+        const int Q = a.lt.Q[lv], PQ = a.lt.P[lv] * Q;
         const int img = pix0 / PQ, rem = pix0 - img * PQ;
-        const int p0 = rem / a.Q, q0 = rem - p0 * a.Q;
+        const int p0 = rem / Q, q0 = rem - p0 * Q;
         const int w0 = q0 * a.stride - a.pad, h0 = p0 * a.stride - a.pad;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * WG_STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
         for (int j = 0; j < 2; ++j)
           tma_load_2d(sa + j * WG_BLK_BYTES, &tmap_g, &full_bar[stage], n_tile * 128 + j * 64,
-                      pix0);
+                      a.lt.row_off[lv] + pix0);     // dY rows past the level's end meet zero-filled (OOB) X rows
         for (int j = 0; j < nblk; ++j)
-          tma_load_im2col_4d(sa + WG_A_BYTES + j * WG_BLK_BYTES, &tmap_x, &full_bar[stage],
+          tma_load_im2col_4d(sa + WG_A_BYTES + j * WG_BLK_BYTES, tmap_x, &full_bar[stage],
                              c_tile * a.block_n + j * 64, w0, h0, img, (uint16_t)s, (uint16_t)r);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -485,21 +520,46 @@ static int pick_block_n(int cout) {
 
 using namespace ut2;
 
-extern "C" int ut2_conv2d_nhwc_bf16_fwd(const void* x, int N, int H, int W, int Cin, const void* w,
-                                        int Cout, int R, int S, int stride, int pad,
-                                        const float* scale, const float* shift,
-                                        const void* residual, int res_up2, const void* relu_mask, int relu,
-                                        void* y, void* stream) {
+// Shared launcher. num_levels == 1: an ordinary convolution on [N, H, W, Cin]. num_levels > 1: one launch over a
+// level-major pyramid (levels [N, H_l, W_l, Cin] laid back to back in x, outputs laid back to back in y; stride 1).
+static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, int Cin, const void* w, int Cout, int R,
+                           int S, int stride, int pad, const float* scale, const float* shift, const void* residual,
+                           int res_up2, const void* relu_mask, int relu, void* y, void* stream) {
   if (!x || !w || !y) return ut2_fail(-1, "conv_fwd: null pointer");
   if (Cin % 8 || Cin <= 0) return ut2_fail(-2, "conv_fwd: Cin must be a multiple of 8");
   const int block_n = pick_block_n(Cout);
   if (block_n < 0) return ut2_fail(-3, "conv_fwd: unsupported Cout (need %16==0; >256 needs %128==0)");
   if (stride < 1 || stride > 8 || pad < 0 || R < 1 || S < 1) return ut2_fail(-4, "conv_fwd: bad geometry");
-  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
-  if (P <= 0 || Q <= 0) return ut2_fail(-4, "conv_fwd: empty output");
+  if (num_levels < 1 || num_levels > MAX_LV) return ut2_fail(-4, "conv_fwd: 1..5 levels");
+  if (num_levels > 1 && (stride != 1 || res_up2)) return ut2_fail(-4, "conv_fwd: multi-level launches are stride 1, no res_up2");
   ConvFwdArgs a;
-  a.M = N * P * Q; a.Cout = Cout; a.ldo = Cout;
-  a.block_n = block_n; a.n_tiles = (Cout + block_n - 1) / block_n; a.m_tiles = (a.M + BM - 1) / BM;
+  TmapSet tx;
+  a.lt.num = num_levels;
+  a.lt.tile_off[0] = 0;
+  long long in_rows = 0, out_rows = 0;
+  for (int l = 0; l < MAX_LV; ++l) {
+    const int ll = l < num_levels ? l : num_levels - 1;
+    const int H = hw[2 * ll], W = hw[2 * ll + 1];
+    const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+    if (P <= 0 || Q <= 0) return ut2_fail(-4, "conv_fwd: empty output");
+    if (l < num_levels) {
+      a.lt.P[l] = P; a.lt.Q[l] = Q; a.lt.M[l] = N * P * Q;
+      a.lt.row_off[l] = (int)out_rows;
+      a.lt.tile_off[l + 1] = a.lt.tile_off[l] + (a.lt.M[l] + BM - 1) / BM;
+      int rc = make_tmap_im2col_bf16(&tx.m[l], static_cast<const __nv_bfloat16*>(x) + in_rows * Cin, N, H, W, Cin, R, S,
+                                     stride, pad, 64, BM);
+      if (rc) return ut2_fail(rc, "conv_fwd: activation tensor map encode failed");
+      in_rows += (long long)N * H * W;
+      out_rows += a.lt.M[l];
+    } else {
+      a.lt.P[l] = a.lt.P[ll]; a.lt.Q[l] = a.lt.Q[ll]; a.lt.M[l] = 0; a.lt.row_off[l] = 0;
+      if (l + 1 <= MAX_LV) a.lt.tile_off[l + 1] = a.lt.tile_off[l];
+      tx.m[l] = tx.m[ll];
+    }
+  }
+  const int P = a.lt.P[0], Q = a.lt.Q[0];
+  a.M = (int)out_rows; a.Cout = Cout; a.ldo = Cout;
+  a.block_n = block_n; a.n_tiles = (Cout + block_n - 1) / block_n; a.m_tiles = a.lt.tile_off[num_levels];
   a.P = P; a.Q = Q; a.stride = stride; a.pad = pad; a.R = R; a.S = S; a.Cin = Cin;
   a.relu = relu; a.scale = scale; a.shift = shift;
   a.residual = static_cast<const __nv_bfloat16*>(residual); a.ldr = Cout;
@@ -509,10 +569,8 @@ extern "C" int ut2_conv2d_nhwc_bf16_fwd(const void* x, int N, int H, int W, int 
   a.manual = (Cout < 64 && (residual || relu_mask)) || (residual && res_up2) || (residual && relu_mask);
   a.aux_kind = a.manual ? 0 : (residual ? 1 : (relu_mask ? 2 : 0));
   a.stages = a.aux_kind ? 3 : 4;
-  CUtensorMap tx, tw, to, ta;
-  int rc = make_tmap_im2col_bf16(&tx, x, N, H, W, Cin, R, S, stride, pad, 64, BM);
-  if (rc) return ut2_fail(rc, "conv_fwd: activation tensor map encode failed");
-  rc = make_tmap_2d_bf16(&tw, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64, block_n);
+  CUtensorMap tw, to, ta;
+  int rc = make_tmap_2d_bf16(&tw, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64, block_n);
   if (rc) return ut2_fail(rc, "conv_fwd: weight tensor map encode failed");
   const uint32_t bc = Cout < 64 ? Cout : 64;
   rc = make_tmap_2d_bf16(&to, y, a.M, Cout, Cout, bc, 32);
@@ -536,21 +594,63 @@ extern "C" int ut2_conv2d_nhwc_bf16_fwd(const void* x, int N, int H, int W, int 
   return ut2_check_launch("conv_fwd");
 }
 
-extern "C" int ut2_conv2d_nhwc_bf16_wgrad(const void* x, int N, int H, int W, int Cin,
-                                          const void* dy, int Cout, int R, int S, int stride,
-                                          int pad, const float* scale, float* dw, int cout_store,
-                                          void* stream) {
+extern "C" int ut2_conv2d_nhwc_bf16_fwd(const void* x, int N, int H, int W, int Cin, const void* w,
+                                        int Cout, int R, int S, int stride, int pad,
+                                        const float* scale, const float* shift,
+                                        const void* residual, int res_up2, const void* relu_mask, int relu,
+                                        void* y, void* stream) {
+  const int hw[2] = {H, W};
+  return conv_fwd_launch(x, 1, hw, N, Cin, w, Cout, R, S, stride, pad, scale, shift, residual, res_up2, relu_mask, relu, y,
+                         stream);
+}
+
+// One launch over a level-major pyramid: x = levels [N, H_l, W_l, Cin] back to back, y likewise with Cout channels
+// (stride 1). hw is a HOST array [H_0, W_0, H_1, W_1, ...]. The shared-weight FCOS tower / predictor convolutions
+// (fcos/fcos.py:338-376 applies the same modules to all five FPN levels) run as one grid instead of five.
+extern "C" int ut2_conv2d_levels_bf16_fwd(const void* x, int num_levels, const int* hw, int N, int Cin, const void* w,
+                                          int Cout, int R, int S, int pad, const float* scale, const float* shift,
+                                          const void* residual, const void* relu_mask, int relu, void* y, void* stream) {
+  return conv_fwd_launch(x, num_levels, hw, N, Cin, w, Cout, R, S, 1, pad, scale, shift, residual, 0, relu_mask, relu, y,
+                         stream);
+}
+
+static int conv_wgrad_launch(const void* x, int num_levels, const int* hw, int N, int Cin, const void* dy, int Cout, int R,
+                             int S, int stride, int pad, const float* scale, float* dw, int cout_store, void* stream) {
   if (!x || !dy || !dw) return ut2_fail(-1, "conv_wgrad: null pointer");
   if (Cin % 64 || Cin <= 0) return ut2_fail(-2, "conv_wgrad: Cin must be a multiple of 64");
   if (Cout % 8) return ut2_fail(-3, "conv_wgrad: Cout must be a multiple of 8");
-  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
-  if (P <= 0 || Q <= 0) return ut2_fail(-4, "conv_wgrad: empty output");
+  if (num_levels < 1 || num_levels > MAX_LV) return ut2_fail(-4, "conv_wgrad: 1..5 levels");
+  if (num_levels > 1 && stride != 1) return ut2_fail(-4, "conv_wgrad: multi-level launches are stride 1");
   ConvWgradArgs a;
-  a.Mpix = N * P * Q; a.Cout = Cout; a.Cin = Cin; a.R = R; a.S = S; a.P = P; a.Q = Q;
+  TmapSet tx;
+  a.lt.num = num_levels;
+  a.lt.tile_off[0] = 0;
+  long long in_rows = 0, out_rows = 0;
+  for (int l = 0; l < MAX_LV; ++l) {
+    const int ll = l < num_levels ? l : num_levels - 1;
+    const int H = hw[2 * ll], W = hw[2 * ll + 1];
+    const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+    if (P <= 0 || Q <= 0) return ut2_fail(-4, "conv_wgrad: empty output");
+    if (l < num_levels) {
+      a.lt.P[l] = P; a.lt.Q[l] = Q; a.lt.M[l] = N * P * Q;
+      a.lt.row_off[l] = (int)out_rows;
+      a.lt.tile_off[l + 1] = a.lt.tile_off[l] + (a.lt.M[l] + WG_PIX - 1) / WG_PIX;
+      int rc = make_tmap_im2col_bf16(&tx.m[l], static_cast<const __nv_bfloat16*>(x) + in_rows * Cin, N, H, W, Cin, R, S,
+                                     stride, pad, 64, WG_PIX);
+      if (rc) return ut2_fail(rc, "conv_wgrad: activation tensor map encode failed");
+      in_rows += (long long)N * H * W;
+      out_rows += a.lt.M[l];
+    } else {
+      a.lt.P[l] = a.lt.P[ll]; a.lt.Q[l] = a.lt.Q[ll]; a.lt.M[l] = 0; a.lt.row_off[l] = 0;
+      if (l + 1 <= MAX_LV) a.lt.tile_off[l + 1] = a.lt.tile_off[l];
+      tx.m[l] = tx.m[ll];
+    }
+  }
+  a.Mpix = (int)out_rows; a.Cout = Cout; a.Cin = Cin; a.R = R; a.S = S; a.P = a.lt.P[0]; a.Q = a.lt.Q[0];
   a.stride = stride; a.pad = pad;
   a.block_n = Cin % 256 == 0 ? 256 : (Cin % 128 == 0 ? 128 : 64);
   a.c_tiles = Cin / a.block_n; a.n_tiles = (Cout + 127) / 128; a.taps = R * S;
-  a.kb_total = (a.Mpix + WG_PIX - 1) / WG_PIX;
+  a.kb_total = a.lt.tile_off[num_levels];
   const int out_tiles = a.c_tiles * a.n_tiles * a.taps;
   // split-K so that the grid is (at most) one full wave of CTAs, but keep >= 32 pixel blocks per CTA: the fp32
   // atomic epilogue (128 x block_n values per CTA) must stay small next to the main loop
@@ -561,11 +661,9 @@ extern "C" int ut2_conv2d_nhwc_bf16_wgrad(const void* x, int N, int H, int W, in
   splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
   a.scale = scale; a.dw = dw;
   a.cout_store = (cout_store > 0 && cout_store < Cout) ? cout_store : Cout;
-  CUtensorMap tg, tx;
+  CUtensorMap tg;
   int rc = make_tmap_2d_bf16(&tg, dy, a.Mpix, Cout, Cout, 64, WG_PIX);
   if (rc) return ut2_fail(rc, "conv_wgrad: dY tensor map encode failed");
-  rc = make_tmap_im2col_bf16(&tx, x, N, H, W, Cin, R, S, stride, pad, 64, WG_PIX);
-  if (rc) return ut2_fail(rc, "conv_wgrad: activation tensor map encode failed");
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
@@ -575,6 +673,22 @@ extern "C" int ut2_conv2d_nhwc_bf16_wgrad(const void* x, int N, int H, int W, in
   dim3 grid(out_tiles, splits);
   conv_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tg, tx, a);
   return ut2_check_launch("conv_wgrad");
+}
+
+extern "C" int ut2_conv2d_nhwc_bf16_wgrad(const void* x, int N, int H, int W, int Cin,
+                                          const void* dy, int Cout, int R, int S, int stride,
+                                          int pad, const float* scale, float* dw, int cout_store,
+                                          void* stream) {
+  const int hw[2] = {H, W};
+  return conv_wgrad_launch(x, 1, hw, N, Cin, dy, Cout, R, S, stride, pad, scale, dw, cout_store, stream);
+}
+
+// Weight gradient of a shared-weight convolution over a level-major pyramid in one launch (the reduction simply runs
+// over the pixels of all levels). Same layout contract as ut2_conv2d_levels_bf16_fwd.
+extern "C" int ut2_conv2d_levels_bf16_wgrad(const void* x, int num_levels, const int* hw, int N, int Cin, const void* dy,
+                                            int Cout, int R, int S, int pad, const float* scale, float* dw, int cout_store,
+                                            void* stream) {
+  return conv_wgrad_launch(x, num_levels, hw, N, Cin, dy, Cout, R, S, 1, pad, scale, dw, cout_store, stream);
 }
 
 extern "C" int ut2_debug_im2col_probe(const void* x, int N, int H, int W, int C, int R, int S,

@@ -34,13 +34,44 @@ constexpr int GN_G = 32;          // groups (== vectors per pixel)
 constexpr int GN_ROWS = 8;        // pixel rows per block iteration (256 threads)
 constexpr int GN_UNROLL = 4;      // independent 16-byte loads in flight per thread
 
+// One launch covers up to 5 pyramid levels of a level-major buffer (level l = [N, HW_l, 256] starting at pixel row
+// row_off[l]); a plain [N, HW, 256] tensor is the 1-level case. Blocks are enumerated (level, image, pixel chunk);
+// statistics live at stats[(l * N + n) * 32 + g].
+constexpr int GN_MAXL = 5;
+struct GnLevels {
+  int num, N;
+  int HW[GN_MAXL], row_off[GN_MAXL], ppb[GN_MAXL], bpi[GN_MAXL];
+  int blk_off[GN_MAXL + 1];
+};
+struct GnBlock {
+  int n_stat;        // l * N + n
+  int HW, p0, p1;
+  size_t base;       // first uint4 of image n in level l
+};
+__device__ __forceinline__ GnBlock gn_locate(const GnLevels& lv) {
+  const int b = blockIdx.x;
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < GN_MAXL; ++i)
+    if (i < lv.num && b >= lv.blk_off[i]) l = i;
+  const int rem = b - lv.blk_off[l];
+  const int n = rem / lv.bpi[l], chunk = rem - n * lv.bpi[l];
+  GnBlock r;
+  r.n_stat = l * lv.N + n;
+  r.HW = lv.HW[l];
+  r.p0 = chunk * lv.ppb[l];
+  r.p1 = min(r.HW, r.p0 + lv.ppb[l]);
+  r.base = ((size_t)lv.row_off[l] + (size_t)n * r.HW) * GN_G;
+  return r;
+}
+
 // stats[n][g] = {sum, sumsq} over HW x 8 channels
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats, int HW, int pix_per_block) {
-  const int n = blockIdx.y, g = threadIdx.x & 31, row = threadIdx.x >> 5;
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(HW, p0 + pix_per_block);
-  const uint4* xv = reinterpret_cast<const uint4*>(x) + (size_t)n * HW * GN_G;
+gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats, GnLevels lv) {
+  const GnBlock B = gn_locate(lv);
+  const int n = B.n_stat, g = threadIdx.x & 31, row = threadIdx.x >> 5;
+  const int p0 = B.p0, p1 = B.p1;
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + B.base;
   float s1 = 0.f, s2 = 0.f;
   for (int p = p0 + row; p < p1; p += GN_ROWS * GN_UNROLL) {
     uint4 v[GN_UNROLL];
@@ -81,18 +112,17 @@ __device__ __forceinline__ void mean_rstd(const double* stats, int n, int g, int
 
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
-                const float* __restrict__ beta, float eps, bf16* __restrict__ y, int HW, int pix_per_block,
-                int relu) {
-  const int n = blockIdx.y, g = threadIdx.x & 31, row = threadIdx.x >> 5;
+                const float* __restrict__ beta, float eps, bf16* __restrict__ y, GnLevels lv, int relu) {
+  const GnBlock B = gn_locate(lv);
+  const int n = B.n_stat, HW = B.HW, g = threadIdx.x & 31, row = threadIdx.x >> 5;
   float mean, rstd;
   mean_rstd(stats, n, g, HW, eps, mean, rstd);
   float ga[8], be[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { ga[j] = gamma[g * 8 + j] * rstd; be[j] = beta[g * 8 + j] - mean * ga[j]; }
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(HW, p0 + pix_per_block);
-  const uint4* xv = reinterpret_cast<const uint4*>(x) + (size_t)n * HW * GN_G;
-  uint4* yv = reinterpret_cast<uint4*>(y) + (size_t)n * HW * GN_G;
+  const int p0 = B.p0, p1 = B.p1;
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + B.base;
+  uint4* yv = reinterpret_cast<uint4*>(y) + B.base;
   for (int p = p0 + row; p < p1; p += GN_ROWS * GN_UNROLL) {
     uint4 v[GN_UNROLL];
 #pragma unroll
@@ -121,18 +151,18 @@ gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ stats, co
 __global__ void __launch_bounds__(256)
 gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const double* __restrict__ stats,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                     double* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int HW,
-                     int pix_per_block, int relu) {
-  const int n = blockIdx.y, g = threadIdx.x & 31, row = threadIdx.x >> 5;
+                     double* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, GnLevels lv,
+                     int relu) {
+  const GnBlock B = gn_locate(lv);
+  const int n = B.n_stat, HW = B.HW, g = threadIdx.x & 31, row = threadIdx.x >> 5;
   float mean, rstd;
   mean_rstd(stats, n, g, HW, eps, mean, rstd);
   float ga[8], be[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { ga[j] = gamma[g * 8 + j]; be[j] = beta[g * 8 + j]; }
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(HW, p0 + pix_per_block);
-  const uint4* xv = reinterpret_cast<const uint4*>(x) + (size_t)n * HW * GN_G;
-  const uint4* dv = reinterpret_cast<const uint4*>(dy) + (size_t)n * HW * GN_G;
+  const int p0 = B.p0, p1 = B.p1;
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + B.base;
+  const uint4* dv = reinterpret_cast<const uint4*>(dy) + B.base;
   float dg[8], db[8], s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) { dg[j] = 0.f; db[j] = 0.f; }
@@ -189,8 +219,9 @@ gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const double* __restrict__ stats,
                     const double* __restrict__ ws, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    float eps, bf16* __restrict__ dx, float* __restrict__ dbias, int HW, int pix_per_block, int relu) {
-  const int n = blockIdx.y, g = threadIdx.x & 31, row = threadIdx.x >> 5;
+                    float eps, bf16* __restrict__ dx, float* __restrict__ dbias, GnLevels lv, int relu) {
+  const GnBlock B = gn_locate(lv);
+  const int n = B.n_stat, HW = B.HW, g = threadIdx.x & 31, row = threadIdx.x >> 5;
   float mean, rstd;
   mean_rstd(stats, n, g, HW, eps, mean, rstd);
   const double m = (double)HW * 8.0;
@@ -199,11 +230,10 @@ gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, con
   float ga[8], be[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { ga[j] = gamma[g * 8 + j]; be[j] = beta[g * 8 + j]; }
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(HW, p0 + pix_per_block);
-  const uint4* xv = reinterpret_cast<const uint4*>(x) + (size_t)n * HW * GN_G;
-  const uint4* dv = reinterpret_cast<const uint4*>(dy) + (size_t)n * HW * GN_G;
-  uint4* ov = reinterpret_cast<uint4*>(dx) + (size_t)n * HW * GN_G;
+  const int p0 = B.p0, p1 = B.p1;
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + B.base;
+  const uint4* dv = reinterpret_cast<const uint4*>(dy) + B.base;
+  uint4* ov = reinterpret_cast<uint4*>(dx) + B.base;
   float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // column sums of dx (the bias gradient of the conv before)
   for (int p = p0 + row; p < p1; p += GN_ROWS * GN_UNROLL) {
     uint4 vx[GN_UNROLL], vd[GN_UNROLL];
@@ -254,29 +284,68 @@ gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, con
   }
 }
 
-inline int pix_per_block(int HW, int N) {
-  // aim for ~148*4 blocks in total, at least 64 pixels each
-  int blocks_per_img = (148 * 4 + N - 1) / N;
-  int ppb = (HW + blocks_per_img - 1) / blocks_per_img;
-  if (ppb < 64) ppb = 64;
-  return (ppb + GN_ROWS - 1) / GN_ROWS * GN_ROWS;
+inline int fill_gn_levels(GnLevels& lv, int num_levels, const int* hws, int N) {
+  if (num_levels < 1 || num_levels > GN_MAXL) return -1;
+  lv.num = num_levels;
+  lv.N = N;
+  long long total = 0;
+  for (int l = 0; l < num_levels; ++l) total += hws[l];
+  // aim for ~148*4 blocks in total, spread over the levels by size, at least 64 pixels each
+  const long long target = (total * N + 148 * 4 - 1) / (148 * 4);
+  int row = 0;
+  lv.blk_off[0] = 0;
+  for (int l = 0; l < GN_MAXL; ++l) {
+    if (l < num_levels) {
+      const int HW = hws[l];
+      int ppb = (int)(target < 64 ? 64 : target);
+      ppb = (ppb + GN_ROWS - 1) / GN_ROWS * GN_ROWS;
+      lv.HW[l] = HW; lv.row_off[l] = row; lv.ppb[l] = ppb; lv.bpi[l] = (HW + ppb - 1) / ppb;
+      lv.blk_off[l + 1] = lv.blk_off[l] + lv.bpi[l] * N;
+      row += N * HW;
+    } else {
+      lv.HW[l] = 1; lv.row_off[l] = 0; lv.ppb[l] = GN_ROWS; lv.bpi[l] = 1;
+      lv.blk_off[l + 1] = lv.blk_off[l];
+    }
+  }
+  return 0;
 }
 }  // namespace
 
 #define STREAM static_cast<cudaStream_t>(stream)
 
+static int gn_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, double* stats, int num_levels,
+                  const int* hws, int N, int C, int G, int relu, void* stream) {
+  if (C != 256 || G != 32) return ut2_fail(-2, "groupnorm: only GroupNorm(32, 256) is supported");
+  GnLevels lv;
+  if (fill_gn_levels(lv, num_levels, hws, N)) return ut2_fail(-3, "groupnorm: 1..5 levels");
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * num_levels * N * GN_G * 2, STREAM);
+  if (e != cudaSuccess) return ut2_fail((int)e, "groupnorm: memset failed");
+  const int grid = lv.blk_off[num_levels];
+  gn_stats_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(x), stats, lv);
+  gn_apply_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(x), stats, gamma, beta, eps, static_cast<bf16*>(y), lv, relu);
+  return ut2_check_launch("groupnorm_fwd");
+}
+
+static int gn_bwd(const void* dy, const void* x, const double* stats, const float* gamma, const float* beta, float eps,
+                  void* dx, float* dgamma, float* dbeta, float* dbias_prev, double* ws, int num_levels, const int* hws, int N,
+                  int C, int G, int relu, void* stream) {
+  if (C != 256 || G != 32) return ut2_fail(-2, "groupnorm: only GroupNorm(32, 256) is supported");
+  GnLevels lv;
+  if (fill_gn_levels(lv, num_levels, hws, N)) return ut2_fail(-3, "groupnorm: 1..5 levels");
+  cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * num_levels * N * GN_G * 2, STREAM);
+  if (e != cudaSuccess) return ut2_fail((int)e, "groupnorm: memset failed");
+  const int grid = lv.blk_off[num_levels];
+  gn_bwd_reduce_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats, gamma, beta,
+                                                 eps, ws, dgamma, dbeta, lv, relu);
+  gn_bwd_apply_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats, ws, gamma, beta,
+                                                eps, static_cast<bf16*>(dx), dbias_prev, lv, relu);
+  return ut2_check_launch("groupnorm_bwd");
+}
+
 // stats: double[N*32*2] workspace owned by the caller (kept for backward).
 extern "C" int ut2_groupnorm_relu_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y,
                                       double* stats, int N, int HW, int C, int G, int relu, void* stream) {
-  if (C != 256 || G != 32) return ut2_fail(-2, "groupnorm: only GroupNorm(32, 256) is supported");
-  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * N * GN_G * 2, STREAM);
-  if (e != cudaSuccess) return ut2_fail((int)e, "groupnorm: memset failed");
-  const int ppb = pix_per_block(HW, N);
-  dim3 grid((HW + ppb - 1) / ppb, N);
-  gn_stats_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(x), stats, HW, ppb);
-  gn_apply_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(x), stats, gamma, beta, eps,
-                                            static_cast<bf16*>(y), HW, ppb, relu);
-  return ut2_check_launch("groupnorm_fwd");
+  return gn_fwd(x, gamma, beta, eps, y, stats, 1, &HW, N, C, G, relu, stream);
 }
 
 // ws: double[N*32*2] scratch; dgamma/dbeta are accumulated (+=) in fp32. dbias_prev (optional, float[256]) receives
@@ -285,14 +354,21 @@ extern "C" int ut2_groupnorm_relu_bwd(const void* dy, const void* x, const doubl
                                       const float* beta, float eps, void* dx, float* dgamma, float* dbeta,
                                       float* dbias_prev, double* ws, int N, int HW, int C, int G, int relu,
                                       void* stream) {
-  if (C != 256 || G != 32) return ut2_fail(-2, "groupnorm: only GroupNorm(32, 256) is supported");
-  cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * N * GN_G * 2, STREAM);
-  if (e != cudaSuccess) return ut2_fail((int)e, "groupnorm: memset failed");
-  const int ppb = pix_per_block(HW, N);
-  dim3 grid((HW + ppb - 1) / ppb, N);
-  gn_bwd_reduce_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats, gamma,
-                                                 beta, eps, ws, dgamma, dbeta, HW, ppb, relu);
-  gn_bwd_apply_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats, ws, gamma,
-                                                beta, eps, static_cast<bf16*>(dx), dbias_prev, HW, ppb, relu);
-  return ut2_check_launch("groupnorm_bwd");
+  return gn_bwd(dy, x, stats, gamma, beta, eps, dx, dgamma, dbeta, dbias_prev, ws, 1, &HW, N, C, G, relu, stream);
+}
+
+// The same two operators over a level-major pyramid (hws: HOST array of H_l*W_l): GroupNorm statistics stay per
+// (level, image, group) exactly as when fcos.py:338-376 applies the tower to each level separately; stats / ws are
+// double[num_levels*N*32*2].
+extern "C" int ut2_groupnorm_relu_levels_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y,
+                                             double* stats, int num_levels, const int* hws, int N, int C, int G, int relu,
+                                             void* stream) {
+  return gn_fwd(x, gamma, beta, eps, y, stats, num_levels, hws, N, C, G, relu, stream);
+}
+
+extern "C" int ut2_groupnorm_relu_levels_bwd(const void* dy, const void* x, const double* stats, const float* gamma,
+                                             const float* beta, float eps, void* dx, float* dgamma, float* dbeta,
+                                             float* dbias_prev, double* ws, int num_levels, const int* hws, int N, int C,
+                                             int G, int relu, void* stream) {
+  return gn_bwd(dy, x, stats, gamma, beta, eps, dx, dgamma, dbeta, dbias_prev, ws, num_levels, hws, N, C, G, relu, stream);
 }

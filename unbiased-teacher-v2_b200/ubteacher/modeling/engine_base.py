@@ -52,6 +52,19 @@ class Conv:
         return ops.conv2d(gz, self.wt, self.cin, k, k, 1, k - 1 - self.pad, None, None, residual, False, None, False,
                           relu_mask, alg)
 
+    # ---- level-major pyramid variants (stride-1 convs whose weights are shared by all levels)
+    def fwd_levels(self, x, geom, N, relu=False, out=None):
+        return ops.conv2d_levels(x, geom, N, self.wf, self.cout, self.k, self.k, self.pad, self.scale, self.shift, None, relu, out)
+
+    def wgrad_levels(self, x, g, geom, N, bias_done=False):
+        ops.conv2d_wgrad_levels(x, g, geom, N, self.cout, self.k, self.k, self.pad, self.dw, self.bn_scale, self.cout_store)
+        if self.bias and not bias_done:
+            ops.colsum(g.view(-1, self.cout), self.db)
+
+    def dgrad_levels(self, g, geom, N, residual=None, relu_mask=None):
+        return ops.conv2d_levels(g, geom, N, self.wt, self.cin, self.k, self.k, self.k - 1 - self.pad, None, None, residual,
+                                 False, None, relu_mask)
+
     def dgrad_compact(self, g, residual=None):
         """stride-2 1x1 only: the un-stuffed [N, P, Q, Cin] gradient (so two of them can be summed first)."""
         return ops.conv2d(g, self.wt, self.cin, 1, 1, 1, 0, None, None, residual)

@@ -122,35 +122,35 @@ class FcosEngine(EngineBase):
         lat5 = self.fpn_lat[5].fwd(c5)
         lat4 = self.fpn_lat[4].fwd(c4, residual=lat5, res_up2=True)
         lat3 = self.fpn_lat[3].fwd(c3, residual=lat4, res_up2=True)
-        p5 = self.fpn_out[5].fwd(lat5)
-        p4 = self.fpn_out[4].fwd(lat4)
-        p3 = self.fpn_out[3].fwd(lat3)
-        p6 = self.p6.fwd(p5)
+        # FPN outputs p3..p7 go straight into ONE level-major buffer [N * 22400, 256] (level, image, h, w): the towers
+        # and predictors share their weights across levels (fcos.py:338-376), so every head layer below is a single
+        # launch over the whole pyramid instead of five (the 273- and 77-location levels cannot fill 148 SMs alone).
+        feat = torch.empty((geom.L * N, 256), dtype=BF16, device=self.device)
+        lv = [feat[geom.off[l] * N: geom.off[l + 1] * N].view(N, geom.hw[l][0], geom.hw[l][1], 256) for l in range(5)]
+        p3 = self.fpn_out[3].fwd(lat3, out=lv[0])
+        p4 = self.fpn_out[4].fwd(lat4, out=lv[1])
+        p5 = self.fpn_out[5].fwd(lat5, out=lv[2])
+        p6 = self.p6.fwd(p5, out=lv[3])
         p6r = ops.relu_bwd(p6, p6)              # relu(p6) = p6 * (p6 > 0)
-        p7 = self.p7.fwd(p6r)
+        self.p7.fwd(p6r, out=lv[4])
         if train:
             tape["fpn"] = (c3, c4, c5, lat3, lat4, lat5, p5, p6, p6r)
         # head
         Ptot = geom.L * N
         cls_out = torch.empty((Ptot, 80), dtype=BF16, device=self.device)
         box_out = torch.empty((Ptot, 80), dtype=BF16, device=self.device)
-        head_tape = []
-        for l, feat in enumerate((p3, p4, p5, p6, p7)):
-            h, w = geom.hw[l]
-            lo, hi = geom.off[l] * N, geom.off[l + 1] * N
-            ctx = {"feat": feat}
-            for t, pred, out in (("cls_tower", self.cls_logits, cls_out), ("bbox_tower", self.box_pred, box_out)):
-                xx = feat
-                saved = []
-                for conv, gname in self.towers[t]:
-                    c = conv.fwd(xx)
-                    gam, bet, _, _ = self.gn[gname]
-                    y, stats = ops.groupnorm_relu_fwd(c, gam, bet)
-                    saved.append((xx, c, stats))
-                    xx = y
-                pred.fwd(xx, out=out[lo:hi].view(N, h, w, 80))
-                ctx[t] = (saved, xx)
-            head_tape.append(ctx)
+        head_tape = {"feat": feat}
+        for t, pred, out in (("cls_tower", self.cls_logits, cls_out), ("bbox_tower", self.box_pred, box_out)):
+            xx = feat
+            saved = []
+            for conv, gname in self.towers[t]:
+                c = conv.fwd_levels(xx, geom, N)
+                gam, bet, _, _ = self.gn[gname]
+                y, stats = ops.groupnorm_relu_levels_fwd(c, geom, N, gam, bet)
+                saved.append((xx, c, stats))
+                xx = y
+            pred.fwd_levels(xx, geom, N, out=out)
+            head_tape[t] = (saved, xx)
         if train:
             tape["head"] = head_tape
             tape["N"] = N
@@ -162,26 +162,22 @@ class FcosEngine(EngineBase):
         """Back-propagate d(loss)/d(cls_out), d(loss)/d(box_out) through head, FPN and res5..res3,
         accumulating into the gradient arena (wgrad uses fp32 atomics, so repeated calls add up)."""
         tape, geom, N = fwd["tape"], fwd["geom"], fwd["N"]
-        dfeat = []
-        for l, ctx in enumerate(tape["head"]):
-            h, w = geom.hw[l]
-            lo, hi = geom.off[l] * N, geom.off[l + 1] * N
-            acc = None
-            for t, pred, dout in (("cls_tower", self.cls_logits, dcls), ("bbox_tower", self.box_pred, dbox)):
-                saved, top = ctx[t]
-                g = dout[lo:hi].view(N, h, w, 80)
-                pred.wgrad(top, g)
-                dx = pred.dgrad(g, (h, w))
-                for i in range(3, -1, -1):
-                    conv, gname = self.towers[t][i]
-                    xin, c, stats = saved[i]
-                    gam, bet, dgam, dbet = self.gn[gname]
-                    dc = ops.groupnorm_relu_bwd(dx, c, stats, gam, bet, dgam, dbet, dbias_prev=conv.db)
-                    conv.wgrad(xin, dc, bias_done=True)       # bias gradient came out of the GroupNorm backward
-                    dx = conv.dgrad(dc, (h, w), residual=acc if i == 0 else None)
-                acc = dx
-            dfeat.append(acc)
-        d3, d4, d5, d6, d7 = dfeat
+        ctx = tape["head"]
+        acc = None
+        for t, pred, dout in (("cls_tower", self.cls_logits, dcls), ("bbox_tower", self.box_pred, dbox)):
+            saved, top = ctx[t]
+            pred.wgrad_levels(top, dout, geom, N)
+            dx = pred.dgrad_levels(dout, geom, N)
+            for i in range(3, -1, -1):
+                conv, gname = self.towers[t][i]
+                xin, c, stats = saved[i]
+                gam, bet, dgam, dbet = self.gn[gname]
+                dc = ops.groupnorm_relu_levels_bwd(dx, c, geom, N, stats, gam, bet, dgam, dbet, dbias_prev=conv.db)
+                conv.wgrad_levels(xin, dc, geom, N, bias_done=True)   # bias gradient came out of the GroupNorm backward
+                dx = conv.dgrad_levels(dc, geom, N, residual=acc if i == 0 else None)
+            acc = dx
+        d3, d4, d5, d6, d7 = [acc[geom.off[l] * N: geom.off[l + 1] * N].view(N, geom.hw[l][0], geom.hw[l][1], 256)
+                              for l in range(5)]
         c3, c4, c5, lat3, lat4, lat5, p5, p6, p6r = tape["fpn"]
         hw = geom.hw
         self.p7.wgrad(p6r, d7)

@@ -126,23 +126,23 @@ class RcnnEngine(EngineBase):
         lat4 = self.fpn_lat[4].fwd(c4, residual=lat5, res_up2=True)
         lat3 = self.fpn_lat[3].fwd(c3, residual=lat4, res_up2=True)
         lat2 = self.fpn_lat[2].fwd(c2, residual=lat3, res_up2=True)
-        p5 = self.fpn_out[5].fwd(lat5)
-        p4 = self.fpn_out[4].fwd(lat4)
-        p3 = self.fpn_out[3].fwd(lat3)
-        p2 = self.fpn_out[2].fwd(lat2)
-        p6 = R.subsample2x(p5)                       # [D2] LastLevelMaxPool: max_pool2d(kernel 1, stride 2)
-        levels = [p2, p3, p4, p5, p6]
+        # FPN outputs p2..p6 live in ONE level-major buffer [N * sum(H_l W_l), 256]: the RPN head shares its weights
+        # across levels (rpn.py:31), so its 3x3 conv and the fused predictor are one launch each over the pyramid.
+        feat = torch.empty((geom.L * N, 256), dtype=BF16, device=self.device)
+        levels = [feat[geom.off[l] * N: geom.off[l + 1] * N].view(N, geom.hw[l][0], geom.hw[l][1], 256) for l in range(5)]
+        self.fpn_out[5].fwd(lat5, out=levels[3])
+        self.fpn_out[4].fwd(lat4, out=levels[2])
+        self.fpn_out[3].fwd(lat3, out=levels[1])
+        self.fpn_out[2].fwd(lat2, out=levels[0])
+        R.subsample2x(levels[3], out=levels[4])      # [D2] LastLevelMaxPool: max_pool2d(kernel 1, stride 2)
+        hidden = self.rpn_conv.fwd_levels(feat, geom, N, relu=True)
         rpn_out = torch.empty((geom.L * N, R.RPN_LD), dtype=BF16, device=self.device)
-        hidden = []
-        for l, feat in enumerate(levels):
-            h, w = geom.hw[l]
-            lo, hi = geom.off[l] * N, geom.off[l + 1] * N
-            t = self.rpn_conv.fwd(feat, relu=True)
-            self.rpn_pred.fwd(t, out=rpn_out[lo:hi].view(N, h, w, R.RPN_LD))
-            hidden.append(t)
+        self.rpn_pred.fwd_levels(hidden, geom, N, out=rpn_out)
+        fwd_feat = feat
         if train:
             tape["fpn"] = (c2, c3, c4, c5, lat2, lat3, lat4, lat5)
             tape["rpn_hidden"] = hidden
+            tape["feat"] = fwd_feat
         image_hw = torch.tensor(sizes, dtype=torch.float32).pin_memory().to(self.device, non_blocking=True)
         return {"rpn_out": rpn_out, "levels": levels, "geom": geom, "rgeom": rgeom, "N": N, "image_sizes": sizes,
                 "image_hw": image_hw, "tape": tape, "padded": (Hp, Wp)}
@@ -217,17 +217,15 @@ class RcnnEngine(EngineBase):
         gt = ctx["gt"]
         drpn = R.rpn_loss_bwd(geom, N, fwd["rpn_out"], ctx["labels"], ctx["matched"], gt.boxes, ctx["scores"], gt.counts,
                               gout_rpn, self.rpn_batch)
+        t = tape["rpn_hidden"]
+        self.rpn_pred.wgrad_levels(t, drpn, geom, N)
+        dt = self.rpn_pred.dgrad_levels(drpn, geom, N, relu_mask=t)
+        self.rpn_conv.wgrad_levels(tape["feat"], dt, geom, N)
+        dfe = self.rpn_conv.dgrad_levels(dt, geom, N)
         dP = []
-        for l, feat in enumerate(fwd["levels"]):
-            h, w = geom.hw[l]
-            lo, hi = geom.off[l] * N, geom.off[l + 1] * N
-            g = drpn[lo:hi].view(N, h, w, R.RPN_LD)
-            t = tape["rpn_hidden"][l]
-            self.rpn_pred.wgrad(t, g)
-            dt = self.rpn_pred.dgrad(g, (h, w), relu_mask=t)
-            self.rpn_conv.wgrad(feat, dt)
-            dfe = self.rpn_conv.dgrad(dt, (h, w))
-            dP.append(R.add_f32_bf16(dlev[l], dfe) if l < 4 else dfe)
+        for l in range(5):
+            g = dfe[geom.off[l] * N: geom.off[l + 1] * N].view(N, geom.hw[l][0], geom.hw[l][1], 256)
+            dP.append(R.add_f32_bf16(dlev[l], g) if l < 4 else g)
         d2, d3, d4, d5, d6 = dP
         hw = geom.hw
         d5 = ops.add_bf16(d5, ops.zero_stuff_s2(d6, hw[3][0], hw[3][1]))              # p6 = p5[:, ::2, ::2]

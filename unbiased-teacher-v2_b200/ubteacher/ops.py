@@ -54,6 +54,60 @@ def conv2d_wgrad(x, dy, cout, R, S, stride, pad, dw, scale=None, cout_store=0):
            cout_store)
 
 
+def conv2d_levels(x, geom, N, w, cout, R, S, pad, scale=None, shift=None, residual=None, relu=False, out=None, relu_mask=None):
+    """x: level-major [N*L, Cin] bf16 (levels of `geom` back to back); returns level-major [N*L, cout] bf16."""
+    Cin = x.shape[-1]
+    rows = geom.L * N
+    if out is None:
+        out = torch.empty((rows, cout), dtype=BF16, device=x.device)
+    flops = 2.0 * rows * cout * Cin * R * S
+    args = ("ut2_conv2d_levels_bf16_fwd", x, geom.num, geom.c_hw, N, Cin, w, cout, R, S, pad, scale, shift, residual, relu_mask,
+            int(relu), out)
+    if PROFILE is None:
+        tag = f"conv_fwd {N}xL{geom.L}x{Cin}->{cout} {R}x{S}/1" if _C.EVENT_PROFILE is not None else None
+        _C.counted_call(*args, tag=tag)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _C.counted_call(*args)
+        e1.record()
+        PROFILE["conv_fwd"].append((e0, e1, flops))
+    return out
+
+
+def conv2d_wgrad_levels(x, dy, geom, N, cout, R, S, pad, dw, scale=None, cout_store=0):
+    Cin = x.shape[-1]
+    flops = 2.0 * geom.L * N * (cout_store or cout) * Cin * R * S
+    args = ("ut2_conv2d_levels_bf16_wgrad", x, geom.num, geom.c_hw, N, Cin, dy, cout, R, S, pad, scale, dw, cout_store)
+    if PROFILE is None:
+        tag = f"conv_wgrad {N}xL{geom.L}x{Cin}->{cout} {R}x{S}/1" if _C.EVENT_PROFILE is not None else None
+        _C.counted_call(*args, tag=tag)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _C.counted_call(*args)
+        e1.record()
+        PROFILE["conv_wgrad"].append((e0, e1, flops))
+
+
+def groupnorm_relu_levels_fwd(x, geom, N, gamma, beta, eps=1e-5, relu=True):
+    y = torch.empty_like(x)
+    stats = torch.empty((geom.num * N, 32, 2), dtype=torch.float64, device=x.device)
+    _C.counted_call("ut2_groupnorm_relu_levels_fwd", x, gamma, beta, f32(eps), y, stats, geom.num, geom.c_hws, N, x.shape[-1], 32,
+                    int(relu))
+    _C.launch_count += 1  # two kernels
+    return y, stats
+
+
+def groupnorm_relu_levels_bwd(dy, x, geom, N, stats, gamma, beta, dgamma, dbeta, eps=1e-5, relu=True, dbias_prev=None):
+    dx = torch.empty_like(x)
+    ws = torch.empty((geom.num * N, 32, 2), dtype=torch.float64, device=x.device)
+    _C.counted_call("ut2_groupnorm_relu_levels_bwd", dy, x, stats, gamma, beta, f32(eps), dx, dgamma, dbeta, dbias_prev, ws,
+                    geom.num, geom.c_hws, N, x.shape[-1], 32, int(relu))
+    _C.launch_count += 1
+    return dx
+
+
 def groupnorm_relu_fwd(x, gamma, beta, eps=1e-5, relu=True):
     N, H, W, C = x.shape
     y = torch.empty_like(x)
@@ -150,6 +204,7 @@ class LevelGeom:
         self.L = sum(h * w for h, w in self.hw)
         self.c_hw = (ctypes.c_int * (2 * self.num))(*[v for x in self.hw for v in x])
         self.c_strides = (ctypes.c_int * self.num)(*self.strides)
+        self.c_hws = (ctypes.c_int * self.num)(*[h * w for h, w in self.hw])
         if sizes_of_interest is not None:
             INF = 100000000.0
             rng, prev = [], -1.0

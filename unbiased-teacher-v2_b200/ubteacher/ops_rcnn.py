@@ -231,8 +231,8 @@ def add_f32_bf16(a_f32, b_bf16=None):
     return out
 
 
-def subsample2x(x):
+def subsample2x(x, out=None):
     N, H, W, C = x.shape
-    y = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=BF16, device=x.device)
+    y = out if out is not None else torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=BF16, device=x.device)
     _C.counted_call("ut2_subsample2x_nhwc", x, y, N, H, W, C)
     return y
