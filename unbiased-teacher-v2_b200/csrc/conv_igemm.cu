@@ -22,18 +22,24 @@ namespace ut2 {
 
 constexpr int BM = 128;          // output pixels per tile (UMMA M)
 constexpr int BK = 64;           // K elements per pipeline stage (128 B rows, SWIZZLE_128B)
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KiB
-constexpr int B_BYTES = 256 * BK * 2;       // 32 KiB (block_n <= 256)
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_LIMIT = 232448;          // 227 KiB of dynamic shared memory per CTA on sm_100a
 constexpr int BAR_BYTES = 3072;             // 1 KiB mbarriers + TMEM slot | 1 KiB scale[256] | 1 KiB shift[256]
 constexpr int EPI_TILE_BYTES = 32 * 128;    // one 32-row x 64-col bf16 staging tile, 128B-swizzled
 constexpr int NUM_THREADS = 320;            // warp0 TMA, warp1 MMA, warps2-9 epilogue (two per TMEM lane quadrant)
 constexpr int TMEM_COLS = 512;              // 2 accumulator buffers x 256 fp32 columns
 
-// shared memory: [stages x 48 KiB operands][barriers, scale, shift][8 warps x 2 aux tiles of 4 KiB (only with aux)]
-constexpr int smem_bytes(int stages, bool aux) {
-  return 1024 + stages * STAGE_BYTES + BAR_BYTES + (aux ? 16 : 0) * EPI_TILE_BYTES;
+// shared memory: [stages x (16 KiB A + block_n x 128 B of B)][barriers, scale, shift][8 warps x 2 aux tiles of 4 KiB
+// (only with aux)]. The ring is as deep as the 227 KiB allow (<= 8): narrow-N tiles move few bytes per stage, and with
+// only 4 stages in flight they are bound by TMA latency, not by bandwidth or the tensor pipe.
+__host__ __device__ constexpr int stage_bytes(int block_n) { return A_BYTES + block_n * BK * 2; }
+constexpr int smem_bytes(int stages, int block_n, bool aux) {
+  return 1024 + stages * stage_bytes(block_n) + BAR_BYTES + (aux ? 16 : 0) * EPI_TILE_BYTES;
+}
+inline int pick_stages(int block_n, bool aux) {
+  int s = (SMEM_LIMIT - 1024 - BAR_BYTES - (aux ? 16 : 0) * EPI_TILE_BYTES) / stage_bytes(block_n);
+  return s > MAX_STAGES ? MAX_STAGES : s;
 }
 
 constexpr int MAX_LV = 5;          // pyramid levels one launch can cover (shared-weight head convs)
@@ -66,7 +72,7 @@ struct ConvFwdArgs {
   int P, Q, stride, pad;
   int R, S, Cin;
   int relu;
-  int stages;                       // operand ring depth: 4, or 3 when the aux tiles take their shared memory
+  int stages;                       // operand ring depth (pick_stages)
   int aux_kind;                     // 0 none, 1 residual tile via TMA, 2 relu-mask tile via TMA
   int manual;                       // 1: epilogue with plain loads/stores (res_up2, residual+mask, Cout < 64)
   const float* scale;
@@ -99,6 +105,7 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int STAGES = a.stages;
+  const int STAGE_BYTES = stage_bytes(a.block_n);
   uint8_t* bar_base = smem + STAGES * STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -151,17 +158,27 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
         const int img = m0 / PQ, rem = m0 - img * PQ;
         const int p0 = rem / Q, q0 = rem - p0 * Q;
         const int w0 = q0 * a.stride - a.pad, h0 = p0 * a.stride - a.pad;
+        // The producer is ONE thread: its per-k-block instruction count bounds the rate of narrow-N tiles (the tensor
+        // pipe needs only 32 / 64 cycles per MMA at N = 64 / 128), so the (tap, channel) walk is incremental — no
+        // divisions in the loop.
+        int r = 0, sft = 0, c0 = 0, kcol = 0, tapcol = 0;
+        const int ncol = n_tile * a.block_n;
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / c_chunks, c0 = (kb - tap * c_chunks) * BK;
-          const int r = tap / a.S, s = tap - r * a.S;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          tma_load_im2col_4d(sa, tmap_x, &full_bar[stage], c0, w0, h0, img, (uint16_t)s,
+          tma_load_im2col_4d(sa, tmap_x, &full_bar[stage], c0, w0, h0, img, (uint16_t)sft,
                              (uint16_t)r);
-          tma_load_2d(sa + A_BYTES, &tmap_w, &full_bar[stage], tap * a.Cin + c0,
-                      n_tile * a.block_n);
+          tma_load_2d(sa + A_BYTES, &tmap_w, &full_bar[stage], kcol, ncol);
           if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
+          c0 += BK;
+          kcol += BK;
+          if (c0 >= a.Cin) {
+            c0 = 0;
+            tapcol += a.Cin;
+            kcol = tapcol;
+            if (++sft == a.S) { sft = 0; ++r; }
+          }
         }
       }
     }
@@ -306,9 +323,11 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 8; ++i) ow[i] = mask_bf16x2(ow[i], yw[i]);
             }
-            uint4* op = reinterpret_cast<uint4*>(a.out + (size_t)m * a.ldo + nj);
-            op[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-            op[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+            // one 256-bit store per lane (STG.256): half the LSU wavefronts of two 128-bit stores — the epilogue of the
+            // memory-bound 1x1 convolutions is limited by the L1/LSU pipe, not by DRAM
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(a.out + (size_t)m * a.ldo + nj),
+                         "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7])
+                         : "memory");
           }
         }
       }
@@ -342,14 +361,16 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------ wgrad
-constexpr int STAGES = 4;                       // wgrad operand ring depth
+constexpr int WG_MAX_STAGES = 8;                // wgrad operand ring depth: as deep as shared memory allows (<= 8)
 constexpr int WG_THREADS = 192;                 // warp0 TMA, warp1 MMA, warps2-5 epilogue
 constexpr int WG_PIX = 64;                      // pixels (GEMM-K) per stage
 constexpr int WG_BLK_BYTES = WG_PIX * 64 * 2;   // one [64 pix][64 ch] swizzled block = 8 KiB
 constexpr int WG_A_BYTES = 2 * WG_BLK_BYTES;    // 128 output channels
-constexpr int WG_B_BYTES = 4 * WG_BLK_BYTES;    // up to 256 input channels
-constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
-constexpr int WG_SMEM_BYTES = STAGES * WG_STAGE_BYTES + 1024 + 256;
+__host__ __device__ constexpr int wg_stage_bytes(int block_n) { return WG_A_BYTES + (block_n / 64) * WG_BLK_BYTES; }
+inline int wg_pick_stages(int block_n) {
+  int s = (SMEM_LIMIT - 1024 - 256) / wg_stage_bytes(block_n);
+  return s > WG_MAX_STAGES ? WG_MAX_STAGES : s;
+}
 
 struct ConvWgradArgs {
   LevelTable lt;        // tile_off = prefix of 64-pixel blocks per level
@@ -357,6 +378,7 @@ struct ConvWgradArgs {
   int block_n;      // input-channel tile width (64 / 128 / 256)
   int c_tiles, n_tiles, taps;
   int kb_total, kb_per_split;
+  int stages;
   const float* scale;   // optional per-Cout factor (FrozenBN scale)
   float* dw;            // [Cout, R*S*Cin] fp32, accumulated
   int cout_store;       // rows >= cout_store are not written (zero-padded fused predictors)
@@ -368,9 +390,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  const int STAGES = a.stages;
+  const int WG_STAGE_BYTES = wg_stage_bytes(a.block_n);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * WG_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + WG_MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + WG_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -406,24 +430,41 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
       uint32_t stage = 0, phase = 0;
       const uint32_t tx_bytes = (2 + nblk) * WG_BLK_BYTES;
       const int r = tap / a.S, s = tap - r * a.S;
+      // incremental pixel walk (no divisions per 64-pixel block: the producer thread must issue 2 + nblk TMA loads
+      // every ~500 tensor-pipe cycles)
+      int lv = level_of(a.lt, kb_begin);
+      const CUtensorMap* tmap_x = &tmaps_x.m[lv];
+      int Q = a.lt.Q[lv], P = a.lt.P[lv];
+      int pix0 = (kb_begin - a.lt.tile_off[lv]) * WG_PIX;
+      int img = pix0 / (P * Q), rem = pix0 - img * (P * Q);
+      int p0 = rem / Q, q0 = rem - p0 * Q;
+      int next_lv_kb = a.lt.tile_off[lv + 1];
+      int grow = a.lt.row_off[lv] + pix0;
+      const int c_base = c_tile * a.block_n, ncol = n_tile * 128;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const int lv = level_of(a.lt, kb);
-        const CUtensorMap* tmap_x = &tmaps_x.m[lv];
-        const int pix0 = (kb - a.lt.tile_off[lv]) * WG_PIX;        // first pixel of the block inside its level
-        const int Q = a.lt.Q[lv], PQ = a.lt.P[lv] * Q;
-        const int img = pix0 / PQ, rem = pix0 - img * PQ;
-        const int p0 = rem / Q, q0 = rem - p0 * Q;
+        if (kb == next_lv_kb) {                      // first block of the next pyramid level
+          ++lv;
+          tmap_x = &tmaps_x.m[lv];
+          Q = a.lt.Q[lv]; P = a.lt.P[lv];
+          img = 0; p0 = 0; q0 = 0;
+          next_lv_kb = a.lt.tile_off[lv + 1];
+          grow = a.lt.row_off[lv];
+        }
         const int w0 = q0 * a.stride - a.pad, h0 = p0 * a.stride - a.pad;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * WG_STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
         for (int j = 0; j < 2; ++j)
-          tma_load_2d(sa + j * WG_BLK_BYTES, &tmap_g, &full_bar[stage], n_tile * 128 + j * 64,
-                      a.lt.row_off[lv] + pix0);     // dY rows past the level's end meet zero-filled (OOB) X rows
+          tma_load_2d(sa + j * WG_BLK_BYTES, &tmap_g, &full_bar[stage], ncol + j * 64,
+                      grow);     // dY rows past the level's end meet zero-filled (OOB) X rows
         for (int j = 0; j < nblk; ++j)
           tma_load_im2col_4d(sa + WG_A_BYTES + j * WG_BLK_BYTES, tmap_x, &full_bar[stage],
-                             c_tile * a.block_n + j * 64, w0, h0, img, (uint16_t)s, (uint16_t)r);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                             c_base + j * 64, w0, h0, img, (uint16_t)s, (uint16_t)r);
+        if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
+        grow += WG_PIX;
+        q0 += WG_PIX;
+        while (q0 >= Q) { q0 -= Q; ++p0; }
+        while (p0 >= P) { p0 -= P; ++img; }
       }
     }
   } else if (warp == 1) {
@@ -443,7 +484,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
           umma_bf16(tmem_base, ad, bd, idesc, (kb != kb_begin) || (k != 0));
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(tfull_bar);
     }
@@ -568,7 +609,7 @@ static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, 
   a.out = static_cast<__nv_bfloat16*>(y);
   a.manual = (Cout < 64 && (residual || relu_mask)) || (residual && res_up2) || (residual && relu_mask);
   a.aux_kind = a.manual ? 0 : (residual ? 1 : (relu_mask ? 2 : 0));
-  a.stages = a.aux_kind ? 3 : 4;
+  a.stages = pick_stages(block_n, a.aux_kind != 0);
   CUtensorMap tw, to, ta;
   int rc = make_tmap_2d_bf16(&tw, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64, block_n);
   if (rc) return ut2_fail(rc, "conv_fwd: weight tensor map encode failed");
@@ -582,14 +623,13 @@ static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         smem_bytes(3, true) > smem_bytes(4, false) ? smem_bytes(3, true) : smem_bytes(4, false));
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return ut2_fail((int)e, "conv_fwd: cudaFuncSetAttribute");
     attr_set = true;
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_fwd_kernel<<<grid, NUM_THREADS, smem_bytes(a.stages, a.aux_kind != 0), static_cast<cudaStream_t>(stream)>>>(
+  conv_fwd_kernel<<<grid, NUM_THREADS, smem_bytes(a.stages, block_n, a.aux_kind != 0), static_cast<cudaStream_t>(stream)>>>(
       tx, tw, to, ta, a);
   return ut2_check_launch("conv_fwd");
 }
@@ -660,18 +700,20 @@ static int conv_wgrad_launch(const void* x, int num_levels, const int* hw, int N
   a.kb_per_split = (a.kb_total + splits - 1) / splits;
   splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
   a.scale = scale; a.dw = dw;
+  a.stages = wg_pick_stages(a.block_n);
+  const int wg_smem = a.stages * wg_stage_bytes(a.block_n) + 1024 + 256;
   a.cout_store = (cout_store > 0 && cout_store < Cout) ? cout_store : Cout;
   CUtensorMap tg;
   int rc = make_tmap_2d_bf16(&tg, dy, a.Mpix, Cout, Cout, 64, WG_PIX);
   if (rc) return ut2_fail(rc, "conv_wgrad: dY tensor map encode failed");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return ut2_fail((int)e, "conv_wgrad: cudaFuncSetAttribute");
     attr_set = true;
   }
   dim3 grid(out_tiles, splits);
-  conv_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tg, tx, a);
+  conv_wgrad_kernel<<<grid, WG_THREADS, wg_smem, static_cast<cudaStream_t>(stream)>>>(tg, tx, a);
   return ut2_check_launch("conv_wgrad");
 }
 
