@@ -501,9 +501,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
       tmem_ld_32x16(taddr + c, v);
       tmem_ld_wait();
       if (n < a.cout_store) {
+        // 128-bit vector reductions (RED.128): a quarter of the L2 atomic transactions of scalar adds — with split-K
+        // every CTA flushes a 128 x block_n fp32 tile, which is a visible tail for the shorter reductions
         float* dst = a.dw + (size_t)n * K + (size_t)tap * a.Cin + c_tile * a.block_n + c;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) atomicAdd(dst + i, __uint_as_float(v[i]) * sc);
+        for (int i = 0; i < 16; i += 4)
+          atomicAdd(reinterpret_cast<float4*>(dst + i),
+                    make_float4(__uint_as_float(v[i]) * sc, __uint_as_float(v[i + 1]) * sc, __uint_as_float(v[i + 2]) * sc,
+                                __uint_as_float(v[i + 3]) * sc));
       }
     }
   }
