@@ -309,8 +309,6 @@ def main():
     from ubteacher.engine import UBRCNNTeacherTrainer, UBTeacherTrainer
 
     Trainer = UBTeacherTrainer if args.arch == "fcos" else UBRCNNTeacherTrainer
-    if args.arch == "rcnn":
-        args.no_graph = True       # sampling keys are per-launch parameters (UBRCNNTeacherTrainer.enable_cuda_graph)
     cfg = build_cfg(args.label * world, args.unlabel * world, arch=args.arch)
     dev = torch.device("cuda", local)
 

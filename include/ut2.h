@@ -140,11 +140,12 @@ int ut2_sgd_step(float* p, float* g, float* buf, long long n, float lr, const fl
                  float momentum, float weight_decay, int first_step, int zero_grad, float grad_scale, void* stream);
 /* fp32 master weights (channels-last) -> bf16 forward operand [Cout,R,S,Cin] and dgrad operand [Cin,R,S,CoutT]
  * (taps flipped). The batched form takes a device table of 64-byte records
- * {int64 src, wf, wt, begin, scale; int32 Cout, Cin, R, S, CoutT, n_off}; scale >= 0 folds scales[scale + co]
- * (the FrozenBN scale) into the packed weights. */
+ * {int64 src, wf, wt, begin, scale; int32 Cout, Cin, R, S, CoutT, n_off}; begin = prefix sum of the records' tile counts
+ * R*S*ceil(Cout/64)*ceil(Cin/32), total_tiles its end; scale >= 0 folds scales[scale + co] (the FrozenBN scale) into
+ * the packed weights; write_dgrad = 0 leaves the dgrad operands untouched (inference-only replica: the EMA teacher). */
 int ut2_pack_conv_weight(const float* w, void* wf, void* wt, int Cout, int Cin, int R, int S, int CoutT, void* stream);
-int ut2_pack_conv_weights_batched(const void* descs, int num, long long total, const float* arena, const float* scales,
-                                  void* packed, void* stream);
+int ut2_pack_conv_weights_batched(const void* descs, int num, long long total_tiles, const float* arena,
+                                  const float* scales, void* packed, int write_dgrad, void* stream);
 
 /* ================================================================ Faster R-CNN half
  * [D2] = Detectron2 v0.6 (not on disk; behaviour restated in SURVEY.md appendix B). */
@@ -167,12 +168,13 @@ int ut2_gather_rows(int N, int M, int K, int W, int elem_bytes, const void* src,
  * rpn_out: fused predictor output, level-major [N*sum(H_l*W_l), 16] bf16 (0..2 objectness, 3+4a+k deltas, 15 pad);
  * hw / strides / cell (cell anchors [levels][3][4], [D2] DefaultAnchorGenerator) are HOST arrays.
  * ut2_rpn_label_anchors: label_and_sample_anchors[_pseudo] (rpn.py:78-150): [D2] pairwise_iou + Matcher(lo, hi,
- * allow_low_quality) + subsample_labels; the randperm draw is a per-anchor uint32 key (keys [N,A] or hashed from seed):
+ * allow_low_quality) + subsample_labels; the randperm draw is a per-anchor uint32 key (keys [N,A] or hashed from seed;
+ * seed_dev: optional DEVICE word mixed into the seed so that a captured CUDA graph draws afresh on every replay):
  * the smallest (key, index) win. labels int8 [N,A] in {-1,0,1}; matched int32 [N,A] = argmax ground truth. */
 long long ut2_rpn_label_workspace_bytes(int N, long long A, int G);
 int ut2_rpn_label_anchors(int num_levels, const int* hw, const int* strides, const float* cell, int N, int G,
                           const float* gt_boxes, const int* gt_cnt, const unsigned int* keys, unsigned int seed,
-                          int batch_per_image, float pos_fraction, float lo_thr, float hi_thr, void* workspace,
+                          const unsigned int* seed_dev, int batch_per_image, float pos_fraction, float lo_thr, float hi_thr, void* workspace,
                           long long workspace_bytes, signed char* labels, int* matched, void* stream);
 /* PseudoLabRPN.losses (rpn.py:153-225): BCE-with-logits over sampled anchors (x matched teacher score when gt_scores
  * is given) and L1 on the positives' deltas ([D2] _dense_box_regression_loss, Box2BoxTransform weights 1), both
@@ -195,8 +197,8 @@ int ut2_rpn_select_decode(int num_levels, const int* hw, const int* strides, con
  * (gt_confid) and box std (gt_loc_std). Outputs [N,Rcap,...] fg first; rows >= roi_cnt[img] have class -1. */
 int ut2_roi_sample(int N, int Pcap, int G, int Rcap, const float* prop_boxes, const int* prop_cnt, const float* gt_boxes,
                    const long long* gt_classes, const int* gt_cnt, const float* gt_scores, const float* gt_std,
-                   const unsigned int* keys, int key_ld, unsigned int seed, float pos_fraction, float iou_thr, int num_classes,
-                   int append_gt, float* roi_box, long long* roi_cls, float* roi_gtbox, float* roi_conf, float* roi_std,
+                   const unsigned int* keys, int key_ld, unsigned int seed, const unsigned int* seed_dev, float pos_fraction,
+                   float iou_thr, int num_classes, int append_gt, float* roi_box, long long* roi_cls, float* roi_gtbox, float* roi_conf, float* roi_std,
                    int* roi_src, int* roi_cnt, void* stream);
 /* [D2] ROIPooler(7x7, ROIAlignV2, sampling_ratio 0) -> [tv] roi_align(aligned=True) (roi_heads.py:118). feats / dfeats:
  * HOST arrays of per-level device pointers (NHWC bf16 / fp32 accumulators); out / dout [N*Rcap, 7, 7, C] bf16. */

@@ -180,6 +180,42 @@ def test_pack_weight():
     assert float(wt.cpu()[..., Cout:].float().abs().max()) == 0.0
 
 
+def test_pack_plan_batched():
+    """Table-driven tiled packer (PackPlan / ut2_pack_conv_weights_batched): ragged channel counts, a FrozenBN scale
+    folded in, fused predictors sharing one dgrad operand, and write_dgrad=0 leaving the transposed operands alone."""
+    from ubteacher.arena import PackPlan, ParamArena, Spec
+    gen = torch.Generator().manual_seed(9)
+    shapes = {"a.weight": (100, 72, 3, 3), "b.weight": (24, 64, 1, 1), "p0.weight": (3, 40, 3, 3), "p1.weight": (12, 40, 3, 3)}
+    A = ParamArena([Spec(n, sh, "decay") for n, sh in shapes.items()], torch.device("cuda"))
+    w = {n: torch.randn(sh, generator=gen) for n, sh in shapes.items()}
+    for n in shapes:
+        A.views[n].copy_(w[n].cuda())
+    scales = torch.rand(128, generator=gen) + 0.5
+    plan = PackPlan(A)
+    offs = {}
+    for n, coutT in (("a.weight", 104), ("b.weight", 24)):
+        co, ci, R, _ = shapes[n]
+        offs[n] = (plan.alloc(co * ci * R * R), plan.alloc(ci * R * R * coutT) if n == "a.weight" else -1, coutT)
+        plan.add(n, offs[n][0], offs[n][1], co, ci, R, R, coutT, scale_off=8 if n == "a.weight" else -1)
+    wf_f, wt_f = plan.alloc(16 * 9 * 40), plan.alloc(40 * 9 * 16)
+    plan.add("p0.weight", wf_f, wt_f, 3, 40, 3, 3, 16, 0)
+    plan.add("p1.weight", wf_f + 3 * 360, wt_f, 12, 40, 3, 3, 16, 3)
+    plan.finalize()
+    plan.scales = scales.cuda()
+    plan.run(dgrad=False)
+    assert float(plan.view(offs["a.weight"][1], (72, 3, 3, 104)).float().abs().max()) == 0.0
+    plan.run()
+    wa = w["a.weight"] * scales[8:108].view(-1, 1, 1, 1)
+    assert torch.equal(plan.view(offs["a.weight"][0], (100, 3, 3, 72)).cpu(), wa.permute(0, 2, 3, 1).bfloat16())
+    ta = plan.view(offs["a.weight"][1], (72, 3, 3, 104)).cpu()
+    assert torch.equal(ta[..., :100], wa.flip(2, 3).permute(1, 2, 3, 0).bfloat16()) and float(ta[..., 100:].float().abs().max()) == 0
+    assert torch.equal(plan.view(offs["b.weight"][0], (24, 1, 1, 64)).cpu(), w["b.weight"].permute(0, 2, 3, 1).bfloat16())
+    wp = torch.cat([w["p0.weight"], w["p1.weight"]])
+    assert torch.equal(plan.view(wf_f, (15, 3, 3, 40)).cpu(), wp.permute(0, 2, 3, 1).bfloat16())
+    tp = plan.view(wt_f, (40, 3, 3, 16)).cpu()
+    assert torch.equal(tp[..., :15], wp.flip(2, 3).permute(1, 2, 3, 0).bfloat16()) and float(tp[..., 15].float().abs().max()) == 0
+
+
 # --------------------------------------------------------------------------------------- FCOS targets / losses
 @pytest.mark.parametrize("name", ["fcos_targets_labeled.pt", "fcos_targets_pseudo.pt"])
 def test_assign_targets_golden(name):

@@ -143,6 +143,15 @@ def test_rpn_label_anchors_golden_bit_exact():
         iou = OR.pairwise_iou(g["gt_boxes"][i], anchors)
         _, pre = OR.matcher(iou, (0.3, 0.7), (0, -1, 1), True)
         assert ((l2 == 1) <= (pre == 1)).all() and ((l2 == 0) <= (pre == 0)).all()
+    # device-resident draw counter (CUDA-graph replay): word 0 = the plain seed, another word = another draw
+    word = torch.zeros(1, dtype=torch.int32, device="cuda")
+    labels3, _ = R.rpn_label_anchors(gm, N, gb, cnt, keys=None, seed=123, seed_dev=word)
+    assert torch.equal(labels3, labels2)
+    word.fill_(5)
+    labels4, _ = R.rpn_label_anchors(gm, N, gb, cnt, keys=None, seed=123, seed_dev=word)
+    assert not torch.equal(labels4, labels2)
+    for i in range(N):
+        assert int((labels4[i] >= 0).sum()) == 256 and int((labels4[i] == 1).sum()) == int((labels2[i] == 1).sum())
 
 
 @pytest.mark.parametrize("tag", ["pseudo", "sup"])

@@ -252,3 +252,40 @@ def test_trainer_steps():
     ref = O.ema_update(s1.cpu(), t1.cpu(), tr.cfg.SEMISUPNET.EMA_KEEP_RATE)
     assert torch.equal(t2.cpu(), ref)
     assert torch.isfinite(tr.last_losses[1]).all()
+
+
+def test_cuda_graph_step_matches_eager():
+    """The captured-and-replayed R-CNN step (device-resident sampling counter) against the eager schedule on the same
+    injected sampling keys. The learning rate is tiny so that the discrete choices downstream of the weights (top-k, NMS,
+    fg/bg matching) do not amplify the fp32-atomic accumulation-order noise two eager runs already show; the parameter
+    UPDATE (not the parameters) is what gets compared."""
+    from util_cfg import rcnn_cfg
+    from ubteacher.d2compat.events import EventStorage
+    from ubteacher.data.synthetic import SyntheticTwoCropLoader
+    from ubteacher.engine import UBRCNNTeacherTrainer
+
+    def run(graph):
+        tr = UBRCNNTeacherTrainer(rcnn_cfg(**{"SOLVER.BASE_LR": 1e-5}),
+                                  data_loader=SyntheticTwoCropLoader(1, 2, h=128, w=160, boxes_per_image=3, pool=2))
+        diversify(tr.model)
+        s0 = tr.model.engine.arena.data.clone()
+        geom, _ = tr.model.engine.level_geom(128, 160)
+        _inject_keys(tr.model, 2, geom.A, 11)
+        tr.enable_cuda_graph(graph)
+        out = []
+        with EventStorage(0) as tr.storage:
+            for it in range(4):
+                tr.iter = it
+                tr.run_step_full_semisup()
+                out.append(tr.last_losses[1].cpu().clone())
+                tr.scheduler.step()
+        return out, tr.model.engine.arena.data - s0, tr
+
+    eager, ps, _ = run(False)
+    graph, gs, tr = run(True)
+    assert tr._graph is not None, "the step was never captured"
+    assert int(tr.model.engine.seed_dev.item()) == 4      # advanced before every replay
+    for i, (a, b) in enumerate(zip(eager, graph)):
+        assert torch.isfinite(b).all()
+        torch.testing.assert_close(a, b, rtol=[1e-5, 5e-3, 5e-3, 5e-3][i], atol=1e-3)
+    assert rel(gs, ps) < 2e-2

@@ -32,8 +32,9 @@ for k, v in tot.items():
     grp[k.split(" ")[0]] += v
 for k, v in sorted(grp.items(), key=lambda x: -x[1]):
     print(f"  {v:8.3f} ms {100*v/T:5.1f}%  {k}")
-print("top conv shapes:")
-for k, v in sorted(tot.items(), key=lambda x: -x[1])[:45]:
+print("conv shapes (ms/step, launches/step, TF/s, min-traffic GB/s [in + out + weights, no residual], loss vs max(1450 TF/s, 6.0 TB/s) ideal):")
+rows = []
+for k, v in sorted(tot.items(), key=lambda x: -x[1]):
     if k.startswith("conv"):
         n = len(prof[k]) / STEPS
         kind, shp, flt = k.split(" ")
@@ -44,4 +45,9 @@ for k, v in sorted(tot.items(), key=lambda x: -x[1])[:45]:
             N_, H, W, C = map(int, dims.split("x"))
             PQ = ((H + 2*(R//2) - R)//st + 1) * ((W + 2*(R//2) - R)//st + 1)
         fl = 2.0 * N_ * PQ * int(cout) * C * R * R * n
-        print(f"  {v:8.3f} ms n={n:5.1f} {fl/v/1e9:7.1f} TF/s  {k}")
+        by = 2.0 * n * (N_ * PQ * (C * (1 if st == 1 else st * st if R > 1 else 1) + int(cout)) + int(cout) * C * R * R * (2 if kind == "conv_wgrad" else 1))
+        ideal = max(fl / 1450e9, by / 6.0e9)
+        rows.append((v - ideal, v, n, fl / v / 1e9, by / v / 1e6, ideal, k))
+for loss, v, n, tf, gbs, ideal, k in sorted(rows, key=lambda r: -r[0])[:int(os.environ.get("TOP", 60))]:
+    print(f"  {v:8.3f} ms n={n:5.1f} {tf:7.1f} TF/s {gbs:7.0f} GB/s  ideal {ideal:6.3f} loss {loss:6.3f}  {k}")
+print(f"  sum over conv shapes: {sum(r[1] for r in rows):.2f} ms, ideal {sum(r[5] for r in rows):.2f} ms")

@@ -49,34 +49,60 @@ struct PackDesc {          // one conv weight: master fp32 [Cout, R, S, Cin] (ch
   long long src;           // float offset in the parameter arena
   long long wf;            // bf16 offset of the forward operand [rows, R, S, Cin] in the pack arena, or -1
   long long wt;            // bf16 offset of the dgrad operand [Cin, R, S, CoutT] (flipped taps), or -1
-  long long begin;         // prefix sum of element counts (begin of this descriptor)
+  long long begin;         // prefix sum of TILE counts: R * S * ceil(Cout / 64) * ceil(Cin / 32) tiles per descriptor
   long long scale;         // float offset of a per-Cout scale folded into the packed weights (FrozenBN), or -1
   int Cout, Cin, R, S, CoutT, n_off;   // n_off: column offset inside wt rows (fused predictors)
 };
 
+// One CTA per (descriptor, tap, 64 output channels x 32 input channels) tile: the fp32 master tile is read along Cin
+// (128-byte rows), scaled, rounded to bf16 and written straight to the forward operand (same order); the dgrad operand
+// is its transpose with flipped taps, written along Cout from a padded shared-memory tile so both sides coalesce.
+constexpr int PACK_TN = 64, PACK_TC = 32;
+
 __global__ void __launch_bounds__(256)
-pack_batched_kernel(const PackDesc* __restrict__ descs, int num, long long total, const float* __restrict__ arena,
-                    const float* __restrict__ scales, bf16* __restrict__ packed) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+pack_tiles_kernel(const PackDesc* __restrict__ descs, int num, long long total_tiles, const float* __restrict__ arena,
+                  const float* __restrict__ scales, bf16* __restrict__ packed, int write_dgrad) {
+  __shared__ float tile[PACK_TN][PACK_TC + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int nl = threadIdx.x & 63, cb = threadIdx.x >> 6;
+  for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
     int lo = 0, hi = num - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (descs[mid].begin <= i) lo = mid; else hi = mid - 1;
+      if (descs[mid].begin <= t) lo = mid; else hi = mid - 1;
     }
     const PackDesc d = descs[lo];
-    const long long e = i - d.begin;
-    const int c = (int)(e % d.Cin);
-    long long t = e / d.Cin;
-    const int s = (int)(t % d.S); t /= d.S;
-    const int r = (int)(t % d.R);
-    const int n = (int)(t / d.R);
-    float wv = arena[d.src + e];
-    if (d.scale >= 0) wv *= scales[d.scale + n];
-    const bf16 v = __float2bfloat16_rn(wv);
-    if (d.wf >= 0) packed[d.wf + e] = v;
-    if (d.wt >= 0)
-      packed[d.wt + (((long long)c * d.R + (d.R - 1 - r)) * d.S + (d.S - 1 - s)) * d.CoutT + n + d.n_off] = v;
+    int e = (int)(t - d.begin);
+    const int ct = (d.Cin + PACK_TC - 1) / PACK_TC, nt = (d.Cout + PACK_TN - 1) / PACK_TN;
+    const int ci = e % ct; e /= ct;
+    const int ni = e % nt; e /= nt;
+    const int s = e % d.S, r = e / d.S;
+    const int c = ci * PACK_TC + tx;
+    const bool dg = write_dgrad && d.wt >= 0;
+#pragma unroll
+    for (int k = 0; k < PACK_TN / 8; ++k) {
+      const int n = ni * PACK_TN + ty + 8 * k;
+      if (n < d.Cout && c < d.Cin) {
+        const long long idx = (((long long)n * d.R + r) * d.S + s) * d.Cin + c;
+        float wv = __ldg(arena + d.src + idx);
+        if (d.scale >= 0) wv *= __ldg(scales + d.scale + n);
+        const bf16 v = __float2bfloat16_rn(wv);
+        if (d.wf >= 0) packed[d.wf + idx] = v;
+        tile[ty + 8 * k][tx] = __bfloat162float(v);
+      }
+    }
+    if (dg) {
+      __syncthreads();
+      const int n = ni * PACK_TN + nl;
+#pragma unroll
+      for (int k = 0; k < PACK_TC / 4; ++k) {
+        const int cl = cb + 4 * k, cc = ci * PACK_TC + cl;
+        if (n < d.Cout && cc < d.Cin)
+          packed[d.wt + (((long long)cc * d.R + (d.R - 1 - r)) * d.S + (d.S - 1 - s)) * d.CoutT + n + d.n_off] =
+              __float2bfloat16_rn(tile[nl][cl]);
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -109,11 +135,14 @@ extern "C" int ut2_sgd_step(float* p, float* g, float* buf, long long n, float l
   return ut2_check_launch("sgd_step");
 }
 
-// descs: device array of `num` 64-byte records {int64 src, wf, wt, begin, scale; int32 Cout, Cin, R, S, CoutT, n_off}.
-extern "C" int ut2_pack_conv_weights_batched(const void* descs, int num, long long total, const float* arena,
-                                             const float* scales, void* packed, void* stream) {
-  if (num <= 0 || total <= 0) return 0;
-  pack_batched_kernel<<<grid_for(total), 256, 0, STREAM>>>(static_cast<const PackDesc*>(descs), num, total, arena, scales,
-                                                           static_cast<bf16*>(packed));
+// descs: device array of `num` 64-byte records {int64 src, wf, wt, begin, scale; int32 Cout, Cin, R, S, CoutT, n_off};
+// begin = prefix sum of R * S * ceil(Cout / 64) * ceil(Cin / 32) (tiles), total_tiles = its end. write_dgrad = 0 skips the
+// transposed operands (an inference-only replica: the EMA teacher).
+extern "C" int ut2_pack_conv_weights_batched(const void* descs, int num, long long total_tiles, const float* arena,
+                                             const float* scales, void* packed, int write_dgrad, void* stream) {
+  if (num <= 0 || total_tiles <= 0) return 0;
+  const long long cap = 148 * 8;
+  pack_tiles_kernel<<<(int)(total_tiles < cap ? total_tiles : cap), 256, 0, STREAM>>>(
+      static_cast<const PackDesc*>(descs), num, total_tiles, arena, scales, static_cast<bf16*>(packed), write_dgrad);
   return ut2_check_launch("pack_conv_weights_batched");
 }

@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(1024)
 roi_sample_kernel(int Pcap, int G, int Rcap, const float* __restrict__ prop_boxes, const int* __restrict__ prop_cnt,
                   const float* __restrict__ gt_boxes, const long long* __restrict__ gt_classes, const int* __restrict__ gt_cnt,
                   const float* __restrict__ gt_scores, const float* __restrict__ gt_std, const uint32_t* __restrict__ keys,
-                  int key_ld, uint32_t seed, int max_fg, float iou_thr, int num_classes, int append_gt,
-                  float* __restrict__ roi_box, long long* __restrict__ roi_cls, float* __restrict__ roi_gtbox,
+                  int key_ld, uint32_t seed, const uint32_t* __restrict__ seed_dev, int max_fg, float iou_thr, int num_classes,
+                  int append_gt, float* __restrict__ roi_box, long long* __restrict__ roi_cls, float* __restrict__ roi_gtbox,
                   float* __restrict__ roi_conf, float* __restrict__ roi_std, int* __restrict__ roi_src, int* __restrict__ roi_cnt) {
   __shared__ float4 sg[GMAX];
   __shared__ unsigned long long skey[SAMPLE_CAP];
@@ -55,6 +55,7 @@ roi_sample_kernel(int Pcap, int G, int Rcap, const float* __restrict__ prop_boxe
   __shared__ unsigned char sfg[SAMPLE_CAP];
   __shared__ int s_nfg, s_nbg;
   const int img = blockIdx.x;
+  if (seed_dev) seed += seed_dev[0] * 0x9E3779B1u;     // device-resident draw counter (CUDA-graph replay)
   const int ng = min(gt_cnt[img], G);
   const int np = min(prop_cnt[img], Pcap);
   const int M = min(np + (append_gt ? ng : 0), SAMPLE_CAP);
@@ -517,18 +518,19 @@ __global__ void subsample2x_kernel(const bf16* __restrict__ in, bf16* __restrict
 
 // label_and_sample_proposals[_pseudo] (roi_heads.py:138-270). prop_boxes [N,Pcap,4] + prop_cnt [N]; ground truth
 // [N,G,...] + gt_cnt [N]; gt_scores / gt_std NULL for the supervised branch. keys: optional uint32 [N,key_ld] indexed by
-// position in [proposals | gt]. Outputs are [N,Rcap,...] (fg first, ordered by key, then bg), roi_cnt [N].
+// position in [proposals | gt]; without keys the draw is hashed from seed (+ *seed_dev * 0x9E3779B1 when seed_dev, a
+// device word, is given: a captured CUDA graph then draws fresh samples on every replay). Outputs are [N,Rcap,...] (fg first, ordered by key, then bg), roi_cnt [N].
 extern "C" int ut2_roi_sample(int N, int Pcap, int G, int Rcap, const float* prop_boxes, const int* prop_cnt,
                               const float* gt_boxes, const long long* gt_classes, const int* gt_cnt, const float* gt_scores,
                               const float* gt_std, const unsigned int* keys, int key_ld, unsigned int seed,
-                              float pos_fraction, float iou_thr, int num_classes, int append_gt, float* roi_box,
+                              const unsigned int* seed_dev, float pos_fraction, float iou_thr, int num_classes, int append_gt, float* roi_box,
                               long long* roi_cls, float* roi_gtbox, float* roi_conf, float* roi_std, int* roi_src,
                               int* roi_cnt, void* stream) {
   if (N <= 0) return 0;
   if (G > GMAX) return ut2_fail(-3, "roi_sample: more than 128 ground-truth slots per image");
   if (Pcap + G > SAMPLE_CAP) return ut2_fail(-4, "roi_sample: proposals + ground truth exceed 2048 per image");
   roi_sample_kernel<<<N, 1024, 0, STREAM>>>(Pcap, G, Rcap, prop_boxes, prop_cnt, gt_boxes, gt_classes, gt_cnt, gt_scores, gt_std,
-                                            keys, key_ld, seed, (int)(Rcap * pos_fraction), iou_thr, num_classes, append_gt,
+                                            keys, key_ld, seed, seed_dev, (int)(Rcap * pos_fraction), iou_thr, num_classes, append_gt,
                                             roi_box, roi_cls, roi_gtbox, roi_conf, roi_std, roi_src, roi_cnt);
   return ut2_check_launch("roi_sample");
 }

@@ -154,12 +154,13 @@ __device__ __forceinline__ unsigned long long sel_key(const uint32_t* keys, uint
 
 __global__ void __launch_bounds__(1024)
 rpn_subsample_kernel(int A, int batch, int max_pos, const uint32_t* __restrict__ keys, uint32_t seed,
-                     const int* __restrict__ counts, signed char* __restrict__ labels) {
+                     const uint32_t* __restrict__ seed_dev, const int* __restrict__ counts, signed char* __restrict__ labels) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned long long s_prefix;
   __shared__ unsigned int s_need;
   __shared__ int s_done;
   const int img = blockIdx.x;
+  if (seed_dev) seed += seed_dev[0] * 0x9E3779B1u;     // device-resident draw counter (CUDA-graph replay)
   signed char* lab = labels + (size_t)img * A;
   const int npos = counts[img * 2 + 1], nneg = counts[img * 2];
   const int n_pos = min(npos, max_pos);
@@ -459,7 +460,8 @@ int fill_levels(RpnLevels& lv, int num_levels, const int* hw, const int* strides
 #define STREAM static_cast<cudaStream_t>(stream)
 
 // label_and_sample_anchors[_pseudo] (rpn.py:78-150). hw / strides / cell ([levels][3][4] cell anchors) are HOST arrays.
-// gt_boxes [N,G,4] f32, gt_cnt [N] i32; keys: optional uint32 [N,A] sampling keys (NULL -> hashed from seed).
+// gt_boxes [N,G,4] f32, gt_cnt [N] i32; keys: optional uint32 [N,A] sampling keys (NULL -> hashed from seed,
+// plus *seed_dev * 0x9E3779B1 when the optional device word seed_dev is given: fresh draws under CUDA-graph replay).
 // Outputs: labels int8 [N,A] in {-1,0,1}, matched int32 [N,A] (argmax GT), ws: float [N,A] + uint32 [N,G] + int32 [N,2].
 extern "C" long long ut2_rpn_label_workspace_bytes(int N, long long A, int G) {
   return N * A * 4 + (long long)N * G * 4 + (long long)N * 8 + 1024;
@@ -467,7 +469,7 @@ extern "C" long long ut2_rpn_label_workspace_bytes(int N, long long A, int G) {
 
 extern "C" int ut2_rpn_label_anchors(int num_levels, const int* hw, const int* strides, const float* cell, int N, int G,
                                      const float* gt_boxes, const int* gt_cnt, const unsigned int* keys, unsigned int seed,
-                                     int batch_per_image, float pos_fraction, float lo_thr, float hi_thr, void* workspace,
+                                     const unsigned int* seed_dev, int batch_per_image, float pos_fraction, float lo_thr, float hi_thr, void* workspace,
                                      long long workspace_bytes, signed char* labels, int* matched, void* stream) {
   RpnLevels lv;
   if (fill_levels(lv, num_levels, hw, strides, cell)) return ut2_fail(-2, "rpn_label: bad level count");
@@ -482,7 +484,7 @@ extern "C" int ut2_rpn_label_anchors(int num_levels, const int* hw, const int* s
   dim3 grid((A + 255) / 256, N);
   rpn_match_kernel<<<grid, 256, 0, STREAM>>>(lv, A, G, gt_boxes, gt_cnt, aval, matched, gt_best);
   rpn_label_kernel<<<grid, 256, 0, STREAM>>>(lv, A, G, gt_boxes, gt_cnt, aval, gt_best, lo_thr, hi_thr, labels, counts);
-  rpn_subsample_kernel<<<N, 1024, 0, STREAM>>>(A, batch_per_image, (int)(batch_per_image * pos_fraction), keys, seed,
+  rpn_subsample_kernel<<<N, 1024, 0, STREAM>>>(A, batch_per_image, (int)(batch_per_image * pos_fraction), keys, seed, seed_dev,
                                                counts, labels);
   return ut2_check_launch("rpn_label_anchors");
 }

@@ -130,7 +130,7 @@ class PackPlan:
         begin = 0
         for (src, wf, wt, sc, cout, cin, R, S, coutT, n_off) in self.entries:
             raw += struct.pack("<qqqqqiiiiii", src, wf, wt, begin, sc, cout, cin, R, S, coutT, n_off)
-            begin += cout * cin * R * S
+            begin += R * S * ((cout + 63) // 64) * ((cin + 31) // 32)      # 64 x 32 tiles per tap (csrc/optim.cu)
         self.total = begin
         self.table = torch.frombuffer(raw, dtype=torch.uint8).clone().to(dev)
         return self
@@ -141,8 +141,8 @@ class PackPlan:
             n *= s
         return self.packed[off:off + n].view(shape)
 
-    def run(self):
+    def run(self, dgrad=True):
         from . import _C
         from ._C import i64
         _C.counted_call("ut2_pack_conv_weights_batched", self.table, len(self.entries), i64(self.total),
-                        self.arena.data, self.scales, self.packed)
+                        self.arena.data, self.scales, self.packed, int(dgrad))

@@ -316,7 +316,7 @@ class UBTeacherTrainer:
     def _update_teacher_model(self, keep_rate=0.996):
         t = self.model_teacher.engine
         t.ema_from(self.model.engine, keep_rate)
-        t.refresh_operands()
+        t.refresh_operands(dgrad=False)        # the teacher is never back-propagated
 
     @torch.no_grad()
     def _copy_main_model(self):
@@ -336,11 +336,14 @@ class UBRCNNTeacherTrainer(UBTeacherTrainer):
     def _set_teacher_mode(self, model_teacher):
         model_teacher.train()  # the reference never switches the R-CNN teacher to eval (trainer.py:628-629)
 
-    def enable_cuda_graph(self, flag=True):
-        if flag:
-            raise NotImplementedError("R-CNN step: the anchor / proposal sampling keys are per-launch parameters; "
-                                      "graph replay would freeze the draw (planned: device-resident seed)")
-        self.use_cuda_graph = False
+    def _graph_step(self, data, data_time):
+        # the sampling seeds baked into the captured launches are constants: the draw counter lives in device memory
+        # (RcnnEngine.seed_dev, mixed into every anchor / proposal sampling key) and is advanced before each replay
+        if getattr(self, "_seed_host", None) is None:
+            self._seed_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._seed_host[0] = (self.iter + 1) & 0x7FFFFFFF
+        self.model.engine.seed_dev.copy_(self._seed_host, non_blocking=True)
+        return super()._graph_step(data, data_time)
 
     # ---------------------------------------------------------------- pseudo-labeling (trainer.py:727-769)
     def threshold_bbox(self, dets, thres=0.7, proposal_type="roih"):

@@ -230,14 +230,15 @@ class EngineBase:
             return torch.tensor(self.pixel_std).view(3, 1, 1)
         return None
 
-    def refresh_operands(self):
+    def refresh_operands(self, dgrad=True):
         """Re-derive everything the kernels read from the fp32 arena: packed bf16 weights (one launch),
-        FrozenBN scale/shift (one launch), the stem filter in [R,S,C,K] order."""
+        FrozenBN scale/shift (one launch), the stem filter in [R,S,C,K] order. dgrad=False skips the transposed
+        (data-gradient) operands: the EMA teacher never back-propagates."""
         A = self.arena
         b, n = self.bn_base, self.bn_total
         _C.counted_call("ut2_frozen_bn_fold", A.data[b:b + n], A.data[b + n:b + 2 * n], A.data[b + 2 * n:b + 3 * n],
                         A.data[b + 3 * n:b + 4 * n], _C.f32(BN_EPS), self.bn_fold[0], self.bn_fold[1], n)
-        self.plan.run()        # after the fold: the packer multiplies the FrozenBN scale into the bf16 weights
+        self.plan.run(dgrad)   # after the fold: the packer multiplies the FrozenBN scale into the bf16 weights
         self.stem_w.copy_(A.views[self.stem.name + ".weight"].permute(2, 3, 1, 0))
 
     # ------------------------------------------------------------------------------------ geometry

@@ -49,6 +49,10 @@ class RcnnEngine(EngineBase):
         self.ts_better, self.t_cert = cfg.SEMISUPNET.TS_BETTER, cfg.SEMISUPNET.T_CERT
         self.seed = int(seed)
         self.draws = 0           # sampling-key stream position ([D2] subsample_labels draws from the global torch RNG)
+        # device-resident word mixed into every sampling seed: a captured CUDA graph freezes the host-side `draws`
+        # values, the trainer bumps this word before each replay so the draws keep changing (include/ut2.h, seed_dev)
+        self.seed_dev = torch.zeros(1, dtype=torch.int32, device=device)
+        self._image_hw = {}
         self._build()
         if init:
             self.init_weights(seed)
@@ -143,7 +147,10 @@ class RcnnEngine(EngineBase):
             tape["fpn"] = (c2, c3, c4, c5, lat2, lat3, lat4, lat5)
             tape["rpn_hidden"] = hidden
             tape["feat"] = fwd_feat
-        image_hw = torch.tensor(sizes, dtype=torch.float32).pin_memory().to(self.device, non_blocking=True)
+        key = tuple(map(tuple, sizes))
+        if key not in self._image_hw:               # cached: no pinned temporary inside a graph capture
+            self._image_hw[key] = torch.tensor(sizes, dtype=torch.float32).pin_memory().to(self.device, non_blocking=True)
+        image_hw = self._image_hw[key]
         return {"rpn_out": rpn_out, "levels": levels, "geom": geom, "rgeom": rgeom, "N": N, "image_sizes": sizes,
                 "image_hw": image_hw, "tape": tape, "padded": (Hp, Wp)}
 
@@ -172,12 +179,13 @@ class RcnnEngine(EngineBase):
         scores = gt.scores if pseudo else None
         dk = getattr(self, "debug_keys", None) or {}       # parity tests inject the sampling draws (else: hashed seed)
         labels, matched = R.rpn_label_anchors(geom, N, gt.boxes, gt.counts, keys=dk.get("rpn"), seed=self._next_seed(), batch=self.rpn_batch,
-                                              pos_frac=self.rpn_pos_frac, lo=self.rpn_thr[0], hi=self.rpn_thr[1])
+                                              pos_frac=self.rpn_pos_frac, lo=self.rpn_thr[0], hi=self.rpn_thr[1], seed_dev=self.seed_dev)
         rpn_losses = R.rpn_loss_fwd(geom, N, fwd["rpn_out"], labels, matched, gt.boxes, scores, gt.counts, self.rpn_batch)
         props = self.proposals(fwd)
         s = R.roi_sample(props["proposal_boxes"], props["count"], gt.boxes, gt.classes, gt.counts, scores,
                          gt.reg_pred_std if pseudo else None, keys=dk.get("roi"), seed=self._next_seed(), batch=self.roi_batch,
-                         pos_frac=self.roi_pos_frac, iou_thr=self.roi_iou, num_classes=self.num_classes, append_gt=self.append_gt)
+                         pos_frac=self.roi_pos_frac, iou_thr=self.roi_iou, num_classes=self.num_classes, append_gt=self.append_gt,
+                         seed_dev=self.seed_dev)
         pred = self.box_head(fwd, s["proposal_boxes"], s["count"], True)
         mode = 1 if pseudo else 0
         roi_losses = R.fastrcnn_loss_fwd(pred, s, mode, self.box_w, ts_better=self.ts_better, t_cert=self.t_cert)

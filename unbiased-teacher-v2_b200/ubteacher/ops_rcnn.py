@@ -72,7 +72,7 @@ def gather_rows(src, idx, cnt, width):
     return out
 
 
-def rpn_label_anchors(geom, N, gt_boxes, gt_cnt, keys=None, seed=0, batch=256, pos_frac=0.25, lo=0.3, hi=0.7):
+def rpn_label_anchors(geom, N, gt_boxes, gt_cnt, keys=None, seed=0, batch=256, pos_frac=0.25, lo=0.3, hi=0.7, seed_dev=None):
     dev = gt_boxes.device
     G = gt_boxes.shape[1]
     wsb = _lib_ll("ut2_rpn_label_workspace_bytes")(N, ctypes.c_longlong(geom.A), G)
@@ -80,7 +80,7 @@ def rpn_label_anchors(geom, N, gt_boxes, gt_cnt, keys=None, seed=0, batch=256, p
     labels = torch.empty((N, geom.A), dtype=torch.int8, device=dev)
     matched = torch.empty((N, geom.A), dtype=torch.int32, device=dev)
     _C.counted_call("ut2_rpn_label_anchors", geom.num, geom.c_hw, geom.c_strides, geom.c_cell, N, G, gt_boxes, gt_cnt, keys,
-                    ctypes.c_uint(seed & 0xFFFFFFFF), batch, f32(pos_frac), f32(lo), f32(hi), ws, i64(wsb), labels, matched)
+                    ctypes.c_uint(seed & 0xFFFFFFFF), seed_dev, batch, f32(pos_frac), f32(lo), f32(hi), ws, i64(wsb), labels, matched)
     _C.launch_count += 2
     return labels, matched
 
@@ -125,7 +125,7 @@ def rpn_predict_proposals(geom, N, rpn_out, image_hw, pre_topk=2000, post_topk=1
 
 
 def roi_sample(prop_boxes, prop_cnt, gt_boxes, gt_classes, gt_cnt, gt_scores=None, gt_std=None, keys=None, seed=0,
-               batch=512, pos_frac=0.25, iou_thr=0.5, num_classes=80, append_gt=True):
+               batch=512, pos_frac=0.25, iou_thr=0.5, num_classes=80, append_gt=True, seed_dev=None):
     N, Pcap = prop_boxes.shape[:2]
     G = gt_boxes.shape[1]
     dev = prop_boxes.device
@@ -137,8 +137,8 @@ def roi_sample(prop_boxes, prop_cnt, gt_boxes, gt_classes, gt_cnt, gt_scores=Non
            "sampled_idxs": torch.empty((N, batch), dtype=torch.int32, device=dev),
            "count": torch.empty(N, dtype=torch.int32, device=dev)}
     _C.counted_call("ut2_roi_sample", N, Pcap, G, batch, prop_boxes, prop_cnt, gt_boxes, gt_classes, gt_cnt, gt_scores, gt_std,
-                    keys, keys.shape[1] if keys is not None else 0, ctypes.c_uint(seed & 0xFFFFFFFF), f32(pos_frac), f32(iou_thr),
-                    num_classes, int(append_gt), out["proposal_boxes"], out["gt_classes"], out["gt_boxes"], out["gt_confid"],
+                    keys, keys.shape[1] if keys is not None else 0, ctypes.c_uint(seed & 0xFFFFFFFF), seed_dev, f32(pos_frac),
+                    f32(iou_thr), num_classes, int(append_gt), out["proposal_boxes"], out["gt_classes"], out["gt_boxes"], out["gt_confid"],
                     out["gt_loc_std"], out["sampled_idxs"], out["count"])
     return out
 
