@@ -63,6 +63,11 @@ int ut2_stem_conv_u8(const void* img_chw, int h, int w, const float* wgt_rsck, c
 int ut2_stem_conv_u8_tc(const void* img_chw, int h, int w, const float* wgt_rsck, const float* scale, const float* shift,
                         float mean0, float mean1, float mean2, float std0, float std1, float std2, void* out, int P, int Q,
                         void* stream);
+/* the same over a batch in one launch: imgs / hs / ws are HOST arrays of N device pointers (uint8 CHW) and image sizes;
+ * out is [N, P, Q, 64] bf16 (P, Q = padded size / 2: ImageList.from_tensors zero padding after normalisation). */
+int ut2_stem_conv_u8_tc_batched(const void* const* imgs, const int* hs, const int* ws, int N, const float* wgt_rsck,
+                                const float* scale, const float* shift, float m0, float m1, float m2, float s0, float s1,
+                                float s2, void* out, int P, int Q, void* stream);
 int ut2_maxpool3x3s2_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream);          /* [D2] BasicStem max_pool2d */
 int ut2_upsample2x_add_nhwc(const void* lat, const void* top, void* out, int N, int H, int W, int C, void* stream); /* [D2] FPN top-down */
 int ut2_downsample2x_sum_nhwc(const void* g, const void* addend, void* gtop, int N, int Ht, int Wt, int C, void* stream);

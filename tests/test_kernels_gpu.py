@@ -139,6 +139,30 @@ def test_stem_maxpool(tensor_core):
     assert torch.equal(mp.float().cpu(), refp)
 
 
+def test_stem_batched_ragged():
+    """One launch over a batch of differently sized images (ImageList padding = zeros after normalisation), odd P / Q."""
+    from ubteacher import ops
+    gen = torch.Generator().manual_seed(12)
+    sizes = [(67, 293), (90, 250), (33, 300)]
+    Hp, Wp = 102, 302            # P = 51 (odd: ragged row pair), Q = 151 (ragged 64-pixel column tile)
+    imgs = [torch.randint(0, 256, (3, h, w), generator=gen, dtype=torch.uint8) for h, w in sizes]
+    wgt = torch.randn(64, 3, 7, 7, generator=gen) * 0.05
+    scale = torch.rand(64, generator=gen) + 0.5
+    shift = torch.randn(64, generator=gen) * 0.1
+    mean, std = [103.53, 116.28, 123.675], [57.375, 57.12, 58.395]
+    P, Q = Hp // 2, Wp // 2
+    out = torch.full((len(imgs), P, Q, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.stem_conv_batched([i.cuda() for i in imgs], wgt.permute(2, 3, 1, 0).contiguous().cuda(), scale.cuda(), shift.cuda(),
+                          mean, std, out, P, Q)
+    xp = torch.zeros(len(imgs), 3, Hp, Wp)
+    for i, (im, (h, w)) in enumerate(zip(imgs, sizes)):
+        xp[i, :, :h, :w] = (im.float() - torch.tensor(mean).view(3, 1, 1)) / torch.tensor(std).view(3, 1, 1)
+    ref = F.relu(F.conv2d(xp, wgt, stride=2, padding=3) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    assert ref.shape == out.shape and torch.isfinite(out.float()).all()
+    assert float((out.float().cpu() - ref).norm() / ref.norm()) < 6e-3
+    torch.testing.assert_close(out.float().cpu(), ref, rtol=1e-2, atol=5e-2)
+
+
 def test_fpn_and_grad_helpers():
     from ubteacher import ops
     gen = torch.Generator().manual_seed(4)

@@ -17,6 +17,7 @@
 #include "sm100_ptx.cuh"
 #include "tmap.cuh"
 #include "ut2_internal.h"
+#include <stdlib.h>
 
 namespace ut2 {
 
@@ -363,17 +364,18 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
 // ------------------------------------------------------------------------------------ wgrad
 constexpr int WG_MAX_STAGES = 8;                // wgrad operand ring depth: as deep as shared memory allows (<= 8)
 constexpr int WG_THREADS = 192;                 // warp0 TMA, warp1 MMA, warps2-5 epilogue
-constexpr int WG_PIX = 64;                      // pixels (GEMM-K) per stage
-constexpr int WG_BLK_BYTES = WG_PIX * 64 * 2;   // one [64 pix][64 ch] swizzled block = 8 KiB
-constexpr int WG_A_BYTES = 2 * WG_BLK_BYTES;    // 128 output channels
-__host__ __device__ constexpr int wg_stage_bytes(int block_n) { return WG_A_BYTES + (block_n / 64) * WG_BLK_BYTES; }
-inline int wg_pick_stages(int block_n) {
-  int s = (SMEM_LIMIT - 1024 - 256) / wg_stage_bytes(block_n);
+// Pixels (GEMM-K) per pipeline stage: a template parameter. One [PIX pix][64 ch] swizzled block is one TMA request; 64
+// pixels give the deepest ring (4 stages at block_n = 256) but twice the requests / barrier hand-offs of 128 pixels
+// (2 stages), which is what the 3x3 convolutions (operands re-read from L2 nine times) want; 96 sits between.
+__host__ __device__ constexpr int wg_blk_bytes(int pix) { return pix * 64 * 2; }
+__host__ __device__ constexpr int wg_stage_bytes(int block_n, int pix) { return (2 + block_n / 64) * wg_blk_bytes(pix); }
+inline int wg_pick_stages(int block_n, int pix) {
+  int s = (SMEM_LIMIT - 1024 - 256) / wg_stage_bytes(block_n, pix);
   return s > WG_MAX_STAGES ? WG_MAX_STAGES : s;
 }
 
 struct ConvWgradArgs {
-  LevelTable lt;        // tile_off = prefix of 64-pixel blocks per level
+  LevelTable lt;        // tile_off = prefix of WG_PIX-pixel blocks per level
   int Mpix, Cout, Cin, R, S, P, Q, stride, pad;
   int block_n;      // input-channel tile width (64 / 128 / 256)
   int c_tiles, n_tiles, taps;
@@ -384,6 +386,7 @@ struct ConvWgradArgs {
   int cout_store;       // rows >= cout_store are not written (zero-padded fused predictors)
 };
 
+template <int WG_PIX>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ TmapSet tmaps_x,
                   const ConvWgradArgs a) {
@@ -391,7 +394,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int STAGES = a.stages;
-  const int WG_STAGE_BYTES = wg_stage_bytes(a.block_n);
+  constexpr int WG_BLK_BYTES = wg_blk_bytes(WG_PIX);
+  constexpr int WG_A_BYTES = 2 * WG_BLK_BYTES;    // 128 output channels
+  const int WG_STAGE_BYTES = wg_stage_bytes(a.block_n, WG_PIX);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * WG_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + WG_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + WG_MAX_STAGES;
@@ -668,9 +673,26 @@ static int conv_wgrad_launch(const void* x, int num_levels, const int* hw, int N
   if (num_levels > 1 && stride != 1) return ut2_fail(-4, "conv_wgrad: multi-level launches are stride 1");
   ConvWgradArgs a;
   TmapSet tx;
+  // Stage size (measured over the R50-FPN / head shapes, tools/bench_conv.py): 256-wide input-channel tiles want 96
+  // pixels (3 stages of 72 KiB) unless the reduction is short and spread over few output tiles, everything narrower
+  // wants 128 pixels. UT2_WG_PIX=64|96|128 overrides for experiments.
+  static int pix_override = -1;
+  if (pix_override < 0) {
+    const char* e = getenv("UT2_WG_PIX");
+    pix_override = e ? atoi(e) : 0;
+    if (pix_override != 64 && pix_override != 96 && pix_override != 128) pix_override = 0;
+  }
   a.lt.num = num_levels;
   a.lt.tile_off[0] = 0;
   long long in_rows = 0, out_rows = 0;
+  a.block_n = Cin % 256 == 0 ? 256 : (Cin % 128 == 0 ? 128 : 64);
+  a.c_tiles = Cin / a.block_n; a.n_tiles = (Cout + 127) / 128; a.taps = R * S;
+  const int out_tiles = a.c_tiles * a.n_tiles * a.taps;
+  long long m_total = 0;
+  for (int l = 0; l < num_levels; ++l)
+    m_total += (long long)N * ((hw[2 * l] + 2 * pad - R) / stride + 1) * ((hw[2 * l + 1] + 2 * pad - S) / stride + 1);
+  int WG_PIX = a.block_n == 256 ? ((m_total < 32768 && out_tiles < 32) ? 128 : 96) : 128;
+  if (pix_override) WG_PIX = pix_override;
   for (int l = 0; l < MAX_LV; ++l) {
     const int ll = l < num_levels ? l : num_levels - 1;
     const int H = hw[2 * ll], W = hw[2 * ll + 1];
@@ -693,32 +715,36 @@ static int conv_wgrad_launch(const void* x, int num_levels, const int* hw, int N
   }
   a.Mpix = (int)out_rows; a.Cout = Cout; a.Cin = Cin; a.R = R; a.S = S; a.P = a.lt.P[0]; a.Q = a.lt.Q[0];
   a.stride = stride; a.pad = pad;
-  a.block_n = Cin % 256 == 0 ? 256 : (Cin % 128 == 0 ? 128 : 64);
-  a.c_tiles = Cin / a.block_n; a.n_tiles = (Cout + 127) / 128; a.taps = R * S;
   a.kb_total = a.lt.tile_off[num_levels];
-  const int out_tiles = a.c_tiles * a.n_tiles * a.taps;
   // split-K so that the grid is (at most) one full wave of CTAs, but keep >= 32 pixel blocks per CTA: the fp32
   // atomic epilogue (128 x block_n values per CTA) must stay small next to the main loop
   int splits = num_sms() / out_tiles;
-  if (splits > a.kb_total / 32) splits = a.kb_total / 32;
+  if (splits > a.kb_total / (2048 / WG_PIX)) splits = a.kb_total / (2048 / WG_PIX);
   if (splits < 1) splits = 1;
   a.kb_per_split = (a.kb_total + splits - 1) / splits;
   splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
   a.scale = scale; a.dw = dw;
-  a.stages = wg_pick_stages(a.block_n);
-  const int wg_smem = a.stages * wg_stage_bytes(a.block_n) + 1024 + 256;
+  a.stages = wg_pick_stages(a.block_n, WG_PIX);
+  const int wg_smem = a.stages * wg_stage_bytes(a.block_n, WG_PIX) + 1024 + 256;
   a.cout_store = (cout_store > 0 && cout_store < Cout) ? cout_store : Cout;
   CUtensorMap tg;
   int rc = make_tmap_2d_bf16(&tg, dy, a.Mpix, Cout, Cout, 64, WG_PIX);
   if (rc) return ut2_fail(rc, "conv_wgrad: dY tensor map encode failed");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wgrad_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return ut2_fail((int)e, "conv_wgrad: cudaFuncSetAttribute");
     attr_set = true;
   }
   dim3 grid(out_tiles, splits);
-  conv_wgrad_kernel<<<grid, WG_THREADS, wg_smem, static_cast<cudaStream_t>(stream)>>>(tg, tx, a);
+  if (WG_PIX == 128)
+    conv_wgrad_kernel<128><<<grid, WG_THREADS, wg_smem, static_cast<cudaStream_t>(stream)>>>(tg, tx, a);
+  else if (WG_PIX == 96)
+    conv_wgrad_kernel<96><<<grid, WG_THREADS, wg_smem, static_cast<cudaStream_t>(stream)>>>(tg, tx, a);
+  else
+    conv_wgrad_kernel<64><<<grid, WG_THREADS, wg_smem, static_cast<cudaStream_t>(stream)>>>(tg, tx, a);
   return ut2_check_launch("conv_wgrad");
 }
 

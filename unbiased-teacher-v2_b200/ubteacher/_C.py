@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libut2_sm100.so")
+LIB_PATH = os.environ.get("UT2_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libut2_sm100.so")
 
 _lib = None
 

@@ -256,8 +256,7 @@ class EngineBase:
         Hp, Wp = self.padded_size(sizes)
         P, Q = Hp // 2, Wp // 2
         x = torch.empty((N, P, Q, 64), dtype=BF16, device=self.device)
-        for i, im in enumerate(images):
-            ops.stem_conv(im, self.stem_w, self.stem.scale, self.stem.shift, self.pixel_mean, self.pixel_std, x[i], P, Q)
+        ops.stem_conv_batched(images, self.stem_w, self.stem.scale, self.stem.shift, self.pixel_mean, self.pixel_std, x, P, Q)
         x = ops.maxpool3x3s2(x)
         feats = {}
         for stage, blks in self.blocks:

@@ -134,6 +134,16 @@ def stem_conv(img_u8_chw, w_rsck, scale, shift, mean, std, out_slice, P, Q, tens
                     f32(mean[2]), f32(std[0]), f32(std[1]), f32(std[2]), out_slice, P, Q)
 
 
+def stem_conv_batched(images, w_rsck, scale, shift, mean, std, out, P, Q):
+    """images: list of uint8 CHW device tensors (sizes may differ); out [N, P, Q, 64] bf16. One launch per 32 images."""
+    n = len(images)
+    ptrs = (ctypes.c_void_p * n)(*[im.data_ptr() for im in images])
+    hs = (ctypes.c_int * n)(*[int(im.shape[1]) for im in images])
+    ws = (ctypes.c_int * n)(*[int(im.shape[2]) for im in images])
+    _C.counted_call("ut2_stem_conv_u8_tc_batched", ptrs, hs, ws, n, w_rsck, scale, shift, f32(mean[0]), f32(mean[1]), f32(mean[2]),
+                    f32(std[0]), f32(std[1]), f32(std[2]), out, P, Q)
+
+
 def maxpool3x3s2(x):
     N, H, W, C = x.shape
     P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
