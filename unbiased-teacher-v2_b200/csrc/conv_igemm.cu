@@ -103,8 +103,7 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
                 const ConvFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer: LDS / STS, not generic LD / ST
   const int STAGES = a.stages;
   const int STAGE_BYTES = stage_bytes(a.block_n);
   uint8_t* bar_base = smem + STAGES * STAGE_BYTES;
@@ -391,8 +390,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ TmapSet tmaps_x,
                   const ConvWgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer: LDS / STS, not generic LD / ST
   const int STAGES = a.stages;
   constexpr int WG_BLK_BYTES = wg_blk_bytes(WG_PIX);
   constexpr int WG_A_BYTES = 2 * WG_BLK_BYTES;    // 128 output channels
@@ -531,8 +529,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
 __global__ void im2col_probe_kernel(const __grid_constant__ CUtensorMap tmap, int c, int w, int h,
                                     int n, int off_w, int off_h, int bytes, uint8_t* out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer: LDS / STS, not generic LD / ST
   __shared__ uint64_t bar;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);

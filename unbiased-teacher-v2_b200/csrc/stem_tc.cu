@@ -25,7 +25,7 @@ constexpr int ST_PW = 2 * ST_TW + 8;           // patch width  (needs 2*63 + 8 =
 constexpr int ST_PR = 2 * ST_TR + 5;           // patch rows   (2*1 + 7 = 9)
 constexpr int ST_PATCH = 3 * ST_PR * ST_PW;    // 3672 bf16
 constexpr int ST_PATCH_BYTES = ((ST_PATCH * 2 + 127) / 128) * 128;
-constexpr int ST_SMEM = 1024 + ST_A_BYTES + ST_B_BYTES + ST_PATCH_BYTES + 64;
+constexpr int ST_SMEM = 1024 + ST_A_BYTES + ST_B_BYTES + ST_PATCH_BYTES + 64 + 512;   // + scale[64] | shift[64]
 constexpr int ST_PER = (ST_PATCH + 127) / 128; // patch elements per thread (29)
 constexpr int ST_MAX_IMG = 32;                 // images per launch
 
@@ -41,12 +41,13 @@ stem_tc_kernel(const __grid_constant__ StemBatch batch, const float* __restrict_
                float is0, float is1, float is2, __nv_bfloat16* __restrict__ out, int P, int Q, int tiles_q,
                int tiles_per_img) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer: LDS / STS, not generic LD / ST
   uint8_t* sA = smem;
   uint8_t* sB = smem + ST_A_BYTES;
   __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(sB + ST_B_BYTES);
   uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + ST_PATCH_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  float* s_ss = reinterpret_cast<float*>(bar + 8);      // scale[64] | shift[64]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -54,6 +55,7 @@ stem_tc_kernel(const __grid_constant__ StemBatch batch, const float* __restrict_
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 64);
+  s_ss[tid] = tid < 64 ? __ldg(scale + tid) : __ldg(shift + tid - 64);
   // B operand: W[n][k] bf16, K-major, 128B-swizzled, 3 k-blocks of [64 rows][128 B]. k = (c*7 + r)*8 + s: one 16-byte
   // chunk per (channel, filter row) holding the 7 taps of that row + one zero; chunks >= 21 are zero.
   for (int i = tid; i < 64 * ST_KB * 8; i += 128) {
@@ -175,8 +177,9 @@ stem_tc_kernel(const __grid_constant__ StemBatch batch, const float* __restrict_
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int n = j * 16 + 2 * i;
-            const float a = fmaxf(fmaf(__uint_as_float(v[j][2 * i]), __ldg(scale + n), __ldg(shift + n)), 0.f);
-            const float b = fmaxf(fmaf(__uint_as_float(v[j][2 * i + 1]), __ldg(scale + n + 1), __ldg(shift + n + 1)), 0.f);
+            const float2 sc2 = *reinterpret_cast<const float2*>(s_ss + n), sh2 = *reinterpret_cast<const float2*>(s_ss + 64 + n);
+            const float a = fmaxf(fmaf(__uint_as_float(v[j][2 * i]), sc2.x, sh2.x), 0.f);
+            const float b = fmaxf(fmaf(__uint_as_float(v[j][2 * i + 1]), sc2.y, sh2.y), 0.f);
             __nv_bfloat162 hv = __floats2bfloat162_rn(a, b);
             o[i] = *reinterpret_cast<uint32_t*>(&hv);
           }
