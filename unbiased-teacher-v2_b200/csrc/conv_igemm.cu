@@ -111,8 +111,8 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
-  uint64_t* aux_bar = tempty_bar + 2;             // [8] one per epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 8);
+  uint64_t* aux_bar = tempty_bar + 2;             // [16] two per epilogue warp (double-buffered aux tiles)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 16);
   float* s_scale = reinterpret_cast<float*>(bar_base + 1024);
   float* s_shift = reinterpret_cast<float*>(bar_base + 2048);
   uint8_t* aux_stage = bar_base + BAR_BYTES;                 // 8 warps x 2 tiles x 4 KiB (aux_kind != 0 only)
@@ -135,7 +135,7 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 256);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < 16; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -226,18 +226,36 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
     const int my_chunks = (nchunks - half + 1) / 2;           // chunks half, half+2, ...
     const uint32_t aux_bytes = my_chunks * EPI_TILE_BYTES;
     const bool use_aux = a.aux_kind != 0 && my_chunks > 0;
-    uint32_t acc = 0, acc_phase = 0, aux_phase = 0;
+    // One chunk per warp (block_n <= 128): the warp's two staging slots double-buffer, and the aux tile of tile i+1 is
+    // requested BEFORE tile i is processed. Memory-bound convolutions finish their MMAs long before the epilogue gets
+    // to the tile, so epilogues run back to back and a request issued only after tile i would expose the full DRAM
+    // latency on every tile (ncu: the epilogue warps sat in the aux mbarrier wait).
+    const bool dbl = use_aux && nchunks <= 2;
+    uint64_t* my_aux_bar = aux_bar + ew * 2;
+    uint32_t acc = 0, acc_phase = 0, aux_phase = 0, it = 0;
     int staged_n_tile = -1;
     if (use_aux && lane == 0 && (int)blockIdx.x < num_tiles) {   // aux tiles of this CTA's first tile
       const int t = blockIdx.x;
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
       const int lv = level_of(a.lt, m_tile);
-      mbar_arrive_expect_tx(&aux_bar[ew], aux_bytes);
+      mbar_arrive_expect_tx(&my_aux_bar[0], aux_bytes);
       for (int c = 0; c < my_chunks; ++c)
-        tma_load_2d(astage + c * EPI_TILE_BYTES, &tmap_aux, &aux_bar[ew], n_tile * a.block_n + (half + 2 * c) * 64,
+        tma_load_2d(astage + c * EPI_TILE_BYTES, &tmap_aux, &my_aux_bar[0], n_tile * a.block_n + (half + 2 * c) * 64,
                     a.lt.row_off[lv] + (m_tile - a.lt.tile_off[lv]) * BM + quad * 32);
     }
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      if (dbl) {                        // request tile t + grid's aux chunk into the other slot (read last in tile it-1)
+        __syncwarp();
+        const int tn = t + gridDim.x;
+        if (lane == 0 && tn < num_tiles) {
+          const int n_tile2 = tn % a.n_tiles, m_tile2 = tn / a.n_tiles;
+          const int lv2 = level_of(a.lt, m_tile2);
+          const uint32_t nb = (it + 1) & 1;
+          mbar_arrive_expect_tx(&my_aux_bar[nb], EPI_TILE_BYTES);
+          tma_load_2d(astage + nb * EPI_TILE_BYTES, &tmap_aux, &my_aux_bar[nb], n_tile2 * a.block_n + half * 64,
+                      a.lt.row_off[lv2] + (m_tile2 - a.lt.tile_off[lv2]) * BM + quad * 32);
+        }
+      }
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
       const int lv = level_of(a.lt, m_tile);
       const int ml = (m_tile - a.lt.tile_off[lv]) * BM + quad * 32 + lane;     // row inside the level
@@ -261,7 +279,10 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      if (use_aux) mbar_wait(&aux_bar[ew], aux_phase);
+      if (use_aux) {
+        if (dbl) mbar_wait(&my_aux_bar[it & 1], (it >> 1) & 1);
+        else mbar_wait(&my_aux_bar[0], aux_phase);
+      }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
       for (int c0 = half * 64, ci = 0; c0 < a.block_n; c0 += 128, ++ci) {
         const int cw = min(64, a.block_n - c0);
@@ -271,7 +292,7 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
         if (cw > 32) tmem_ld_32x16(taddr + c0 + 32, v[2]);
         if (cw > 48) tmem_ld_32x16(taddr + c0 + 48, v[3]);
         tmem_ld_wait();
-        const uint8_t* atile = astage + ci * EPI_TILE_BYTES;
+        const uint8_t* atile = astage + (dbl ? (it & 1) : ci) * EPI_TILE_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int cj = c0 + j * 16;
@@ -280,12 +301,22 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
             float f[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 sv = *reinterpret_cast<const float4*>(s_scale + cj + 4 * i);
+              // every broadcast LDS.128 costs four LSU wavefronts and the LSU data pipe is the busiest unit of the
+              // memory-bound 1x1 convolutions: the scale vector is only read when there is one (FrozenBN scales are
+              // folded into the packed weights, so the product path has none)
               const float4 hv = *reinterpret_cast<const float4*>(s_shift + cj + 4 * i);
-              f[4 * i] = fmaf(__uint_as_float(v[j][4 * i]), sv.x, hv.x);
-              f[4 * i + 1] = fmaf(__uint_as_float(v[j][4 * i + 1]), sv.y, hv.y);
-              f[4 * i + 2] = fmaf(__uint_as_float(v[j][4 * i + 2]), sv.z, hv.z);
-              f[4 * i + 3] = fmaf(__uint_as_float(v[j][4 * i + 3]), sv.w, hv.w);
+              if (a.scale) {
+                const float4 sv = *reinterpret_cast<const float4*>(s_scale + cj + 4 * i);
+                f[4 * i] = fmaf(__uint_as_float(v[j][4 * i]), sv.x, hv.x);
+                f[4 * i + 1] = fmaf(__uint_as_float(v[j][4 * i + 1]), sv.y, hv.y);
+                f[4 * i + 2] = fmaf(__uint_as_float(v[j][4 * i + 2]), sv.z, hv.z);
+                f[4 * i + 3] = fmaf(__uint_as_float(v[j][4 * i + 3]), sv.w, hv.w);
+              } else {
+                f[4 * i] = __uint_as_float(v[j][4 * i]) + hv.x;
+                f[4 * i + 1] = __uint_as_float(v[j][4 * i + 1]) + hv.y;
+                f[4 * i + 2] = __uint_as_float(v[j][4 * i + 2]) + hv.z;
+                f[4 * i + 3] = __uint_as_float(v[j][4 * i + 3]) + hv.w;
+              }
             }
             uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0, y0 = x0, y1 = x0;   // x: residual, y: mask
             int has_res = 0, has_mask = 0;
@@ -335,16 +366,16 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (use_aux) {
+      if (use_aux && !dbl) {
         aux_phase ^= 1;
         __syncwarp();                   // every lane finished reading the aux tiles
         const int tn = t + gridDim.x;
         if (lane == 0 && tn < num_tiles) {
           const int n_tile2 = tn % a.n_tiles, m_tile2 = tn / a.n_tiles;
           const int lv2 = level_of(a.lt, m_tile2);
-          mbar_arrive_expect_tx(&aux_bar[ew], aux_bytes);
+          mbar_arrive_expect_tx(&my_aux_bar[0], aux_bytes);
           for (int c = 0; c < my_chunks; ++c)
-            tma_load_2d(astage + c * EPI_TILE_BYTES, &tmap_aux, &aux_bar[ew],
+            tma_load_2d(astage + c * EPI_TILE_BYTES, &tmap_aux, &my_aux_bar[0],
                         n_tile2 * a.block_n + (half + 2 * c) * 64,
                         a.lt.row_off[lv2] + (m_tile2 - a.lt.tile_off[lv2]) * BM + quad * 32);
         }
