@@ -80,15 +80,13 @@ nms_sort_kernel(int M, const float* __restrict__ boxes, const float* __restrict_
   const int n = s_n;
   for (int k = 2; k <= CAP; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < CAP; i += blockDim.x) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const bool up = (i & k) == 0;
-          const unsigned long long a = skey[i], b = skey[ixj];
-          if ((a > b) == up) {
-            skey[i] = b; skey[ixj] = a;
-            const unsigned short t = sval[i]; sval[i] = sval[ixj]; sval[ixj] = t;
-          }
+      for (int t = threadIdx.x; t < CAP / 2; t += blockDim.x) {     // one compare-exchange pair per thread and pass
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), ixj = i | j;
+        const bool up = (i & k) == 0;
+        const unsigned long long a = skey[i], b = skey[ixj];
+        if ((a > b) == up) {
+          skey[i] = b; skey[ixj] = a;
+          const unsigned short v = sval[i]; sval[i] = sval[ixj]; sval[ixj] = v;
         }
       }
       __syncthreads();
@@ -108,6 +106,8 @@ nms_sort_kernel(int M, const float* __restrict__ boxes, const float* __restrict_
     nms_cls[(size_t)img * M + i] = trick ? 0 : c;
   }
 }
+
+constexpr int NMS_WPL = 4;      // mask words per lane and pass of the scan's OR phase
 
 // mask[img][i][cb] bit j: sorted box i suppresses sorted box cb*64+j (only j > i matters)
 __global__ void __launch_bounds__(64)
@@ -138,14 +138,17 @@ nms_mask_kernel(int M, int MW, const float* __restrict__ nms_box, const int* __r
   }
 }
 
-// Greedy scan in 64-box chunks: one warp resolves the dependencies inside a chunk from the diagonal mask words,
-// then the whole CTA ORs the rows of that chunk's survivors into the removal bitmap. Stops at max_keep survivors.
+// Greedy scan in 64-box chunks: one thread resolves the dependencies inside a chunk from the diagonal mask words,
+// then the whole CTA ORs the rows of that chunk's survivors into the removal bitmap: warp w takes survivors w, w+8, ...
+// and its lanes the words c+1+lane, +32, ... of each row, so every thread has up to 8 x NMS_WPL independent 8-byte loads
+// in flight (the kernel is one CTA per image and purely latency-bound). Stops at max_keep survivors.
 __global__ void __launch_bounds__(256)
 nms_scan_kernel(int M, int MW, int max_keep, const unsigned long long* __restrict__ mask, const int* __restrict__ order,
                 const int* __restrict__ n_valid, int* __restrict__ keep_idx, int* __restrict__ keep_cnt) {
   extern __shared__ unsigned long long remv[];       // MW words
-  __shared__ unsigned long long s_diag[64];
-  __shared__ unsigned long long s_keepbits;
+  __shared__ unsigned long long s_diag[2][64];      // diagonal words of chunk c / c+1 (fetched one chunk ahead)
+  __shared__ unsigned char s_rows[64];
+  __shared__ int s_nrows;
   __shared__ int s_nkeep;
   const int img = blockIdx.x;
   const int n = n_valid[img];
@@ -155,36 +158,52 @@ nms_scan_kernel(int M, int MW, int max_keep, const unsigned long long* __restric
   __syncthreads();
   const unsigned long long* mimg = mask + (size_t)img * M * MW;
   const int* ord = order + (size_t)img * M;
+  if (threadIdx.x < 64) s_diag[0][threadIdx.x] = (int)threadIdx.x < n ? mimg[(size_t)threadIdx.x * MW] : 0ull;
+  __syncthreads();
   for (int c = 0; c < nw; ++c) {
     const int cn = min(64, n - c * 64);
-    if (threadIdx.x < 64) s_diag[threadIdx.x] = threadIdx.x < cn ? mimg[(size_t)(c * 64 + threadIdx.x) * MW + c] : 0ull;
-    __syncthreads();
+    unsigned long long next_diag = 0ull;
+    if (threadIdx.x < 64 && (c + 1) * 64 + (int)threadIdx.x < n)
+      next_diag = __ldg(mimg + (size_t)((c + 1) * 64 + threadIdx.x) * MW + c + 1);
+    const unsigned long long* diag = s_diag[c & 1];
     if (threadIdx.x == 0) {
-      unsigned long long dead = remv[c], kb = 0;
-      int nk = s_nkeep;
+      unsigned long long dead = remv[c];
+      int nk = s_nkeep, nr = 0;
       for (int b = 0; b < cn && nk < max_keep; ++b) {
         if (!((dead >> b) & 1ull)) {
-          kb |= 1ull << b;
+          s_rows[nr++] = (unsigned char)b;
           keep_idx[(size_t)img * max_keep + nk] = ord[c * 64 + b];
           ++nk;
-          dead |= s_diag[b];
+          dead |= diag[b];
         }
       }
-      s_keepbits = kb;
+      s_nrows = nr;
       s_nkeep = nk;
     }
     __syncthreads();
-    const unsigned long long kb = s_keepbits;
     if (s_nkeep >= max_keep) break;
-    for (int w = c + 1 + threadIdx.x; w < nw; w += blockDim.x) {
-      unsigned long long acc = 0, bits = kb;
-      while (bits) {
-        const int b = __ffsll((long long)bits) - 1;
-        bits &= bits - 1;
-        acc |= mimg[(size_t)(c * 64 + b) * MW + w];
+    {
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nrows = s_nrows;
+      for (int w0 = c + 1; w0 < nw; w0 += 32 * NMS_WPL) {
+        unsigned long long acc[NMS_WPL];
+#pragma unroll
+        for (int k = 0; k < NMS_WPL; ++k) acc[k] = 0ull;
+        for (int r = warp; r < nrows; r += 8) {
+          const unsigned long long* row = mimg + (size_t)(c * 64 + s_rows[r]) * MW;
+#pragma unroll
+          for (int k = 0; k < NMS_WPL; ++k) {
+            const int w = w0 + lane + 32 * k;
+            if (w < nw) acc[k] |= __ldg(row + w);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < NMS_WPL; ++k) {
+          const int w = w0 + lane + 32 * k;
+          if (w < nw && acc[k]) atomicOr(&remv[w], acc[k]);
+        }
       }
-      remv[w] |= acc;
     }
+    if (threadIdx.x < 64) s_diag[(c + 1) & 1][threadIdx.x] = next_diag;
     __syncthreads();
   }
   if (threadIdx.x == 0) keep_cnt[img] = s_nkeep;
