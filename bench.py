@@ -368,8 +368,18 @@ def main():
         flw = sum(f for _, _, f in prof["conv_wgrad"])
         msw = sum(a.elapsed_time(b) for a, b, _ in prof["conv_wgrad"])
         ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        traffic, traffic_note = None, None
+        try:        # DRAM bytes of the dominant launch shape from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r01c_traffic.json")) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_note = (f"bytes per launch of the dominant shape {tj['shape']}: algorithmic {tj['algorithmic_bytes']} B; "
+                            f"`achieved` averages all {len(prof['conv_fwd']) // prof_steps} conv_fwd launches of a step")
+        except Exception:  # noqa: BLE001
+            pass
         roof = {"bound": "tensor", "kernel": "conv_fwd_kernel (implicit-GEMM fwd + dgrad, tcgen05)", "achieved": ach,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "traffic_note": traffic_note,
+                "peak_source": peak_src,
                 "launches_per_step": len(prof["conv_fwd"]) / prof_steps, "kernel_ms_per_step": ms / prof_steps,
                 "flops_per_launch_avg": fl / max(len(prof["conv_fwd"]), 1),
                 "wgrad": {"achieved": flw / (msw * 1e-3) / 1e12 if msw > 0 else 0.0, "kernel_ms_per_step": msw / prof_steps,
