@@ -96,3 +96,53 @@ def test_instances_and_imagelist_shims():
     il = ImageList.from_tensors([torch.ones(3, 30, 50), torch.ones(3, 33, 40)], 32)
     assert il.tensor.shape == (2, 3, 64, 64) and il.image_sizes == [(30, 50), (33, 40)]
     assert float(il.tensor[0, :, 30:, :].abs().sum()) == 0.0
+
+
+def test_c2_name_conversion_and_alignment():
+    """DetectionTSCheckpointer's Caffe2 -> Detectron2 renaming ([D2] c2_model_loading) and suffix alignment."""
+    import numpy as np
+    from ubteacher.checkpoint.detection_checkpoint import align_and_update_state_dicts, convert_c2_resnet_names
+    blobs = {"conv1_w": np.zeros((64, 3, 7, 7)), "res_conv1_bn_s": np.ones(64), "res_conv1_bn_b": np.zeros(64),
+             "res2_0_branch2a_w": np.zeros((64, 64, 1, 1)), "res2_0_branch2a_bn_s": np.ones(64), "res2_0_branch1_w": np.zeros((256, 64, 1, 1)),
+             "res2_0_branch1_bn_b": np.zeros(256), "res4_5_branch2c_w": np.zeros((1024, 256, 1, 1)), "res3_1_branch2b_bn_b": np.zeros(128),
+             "fc1000_w": np.zeros((1000, 2048)), "fc1000_b": np.zeros(1000), "conv1_w_momentum": np.zeros(1)}
+    got = convert_c2_resnet_names(blobs)
+    assert set(got) == {"stem.conv1.weight", "stem.conv1.norm.weight", "stem.conv1.norm.bias", "res2.0.conv1.weight",
+                        "res2.0.conv1.norm.weight", "res2.0.shortcut.weight", "res2.0.shortcut.norm.bias", "res4.5.conv3.weight",
+                        "res3.1.conv2.norm.bias"}
+    model_sd = {"backbone.bottom_up.stem.conv1.weight": 0, "backbone.bottom_up.res2.0.conv1.weight": 0,
+                "backbone.bottom_up.res2.0.shortcut.norm.bias": 0, "backbone.fpn_lateral3.weight": 0,
+                "proposal_generator.fcos_head.cls_tower.0.weight": 0}
+    m = align_and_update_state_dicts(model_sd, got)
+    assert set(m) == {"backbone.bottom_up.stem.conv1.weight", "backbone.bottom_up.res2.0.conv1.weight",
+                      "backbone.bottom_up.res2.0.shortcut.norm.bias"}
+
+
+def test_detector_postprocess_rescales_clips_and_filters():
+    import torch
+    from ubteacher.d2compat.structures import Boxes, Instances, detector_postprocess
+    inst = Instances((100, 200))
+    inst.pred_boxes = Boxes(torch.tensor([[10., 20., 110., 70.], [150., 90., 260., 100.], [5., 5., 5., 30.]]))
+    inst.scores = torch.tensor([0.9, 0.8, 0.7])
+    out = detector_postprocess(inst, 50, 400)          # scale_x = 2, scale_y = 0.5
+    assert out.image_size == (50, 400) and len(out) == 2          # the zero-width box is dropped
+    assert torch.equal(out.pred_boxes.tensor, torch.tensor([[20., 10., 220., 35.], [300., 45., 400., 50.]]))
+    assert torch.equal(out.scores, torch.tensor([0.9, 0.8]))
+    assert torch.equal(inst.pred_boxes.tensor[0], torch.tensor([10., 20., 110., 70.]))      # the input is not modified
+
+
+def test_warmup_multistep_lr_state_roundtrip():
+    from ubteacher.solver.lr_scheduler import WarmupMultiStepLR
+
+    class Opt:
+        def __init__(self):
+            self.param_groups = [{"lr": 0.01, "initial_lr": 0.01}]
+    a, b = Opt(), Opt()
+    sa = WarmupMultiStepLR(a, [5, 8], 0.1, 0.001, 4, "linear")
+    for _ in range(6):
+        sa.step()
+    sb = WarmupMultiStepLR(b, [5, 8], 0.1, 0.001, 4, "linear")
+    sb.load_state_dict(sa.state_dict())
+    assert sb.last_epoch == sa.last_epoch and b.param_groups[0]["lr"] == a.param_groups[0]["lr"] == 0.01 * 0.1
+    sa.step(); sb.step()
+    assert b.param_groups[0]["lr"] == a.param_groups[0]["lr"]

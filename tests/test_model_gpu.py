@@ -256,3 +256,106 @@ def test_cuda_graph_step_matches_eager():
     for i, (a, b) in enumerate(zip(eager, graph)):
         torch.testing.assert_close(a, b, rtol=[1e-5, 2e-3, 2e-3, 2e-2, 1e-1][i], atol=1e-4)
     assert rel(gs, ps) < 2e-2 and rel(gt, pt) < 1e-4
+
+
+def test_checkpointer_roundtrip_and_c2_pickle(tmp_path):
+    """DetectionTSCheckpointer (detection_checkpoint.py:10-89): save -> load restores teacher, student, momentum, LR
+    schedule and the iteration; a Caffe2-style pickle initialises the STUDENT backbone only (name matching)."""
+    import pickle
+    import numpy as np
+    from util_cfg import fcos_cfg
+    from ubteacher.d2compat.events import EventStorage
+    from ubteacher.data.synthetic import SyntheticTwoCropLoader
+    from ubteacher.engine import UBTeacherTrainer
+    cfg = fcos_cfg(**{"OUTPUT_DIR": str(tmp_path / "run")})
+    mk = lambda: UBTeacherTrainer(cfg, data_loader=SyntheticTwoCropLoader(1, 1, h=96, w=128, boxes_per_image=2, pool=2))
+    tr = mk()
+    with EventStorage(0) as tr.storage:
+        for it in range(2):
+            tr.iter = it
+            tr.run_step_full_semisup()
+            tr.scheduler.step()
+    path = tr.checkpointer.save("model_0000001", iteration=1)
+    sd = torch.load(path, map_location="cpu", weights_only=False)
+    assert any(k.startswith("modelTeacher.backbone.bottom_up.res2.0.conv1.") for k in sd["model"])
+    assert any(k.startswith("modelStudent.proposal_generator.fcos_head.cls_tower.0.") for k in sd["model"])
+    tr2 = mk()
+    assert not torch.equal(tr2.model.engine.arena.data, tr.model.engine.arena.data)
+    tr2.resume_or_load(resume=True)
+    assert tr2.start_iter == 2 and tr2.scheduler.last_epoch == tr.scheduler.last_epoch
+    for a, b in ((tr.model, tr2.model), (tr.model_teacher, tr2.model_teacher)):
+        sa, sb = a.state_dict(), b.state_dict()
+        assert sa.keys() == sb.keys() and all(torch.equal(sa[k], sb[k]) for k in sa)
+    assert torch.equal(tr2.model.engine.arena.mom, tr.model.engine.arena.mom) and tr2.optimizer.steps == tr.optimizer.steps
+    assert not tr2.checkpointer.last_incompatible.missing_keys
+    # the packed bf16 operands follow the loaded weights: both replicas produce the same teacher output
+    batch = [{"image": torch.randint(0, 256, (3, 96, 128), dtype=torch.uint8)}]
+    tr.model_teacher.eval(); tr2.model_teacher.eval()
+    o1 = tr.model_teacher(batch)[0]["instances"]
+    o2 = tr2.model_teacher(batch)[0]["instances"]
+    assert torch.equal(o1.pred_boxes.tensor, o2.pred_boxes.tensor) and torch.equal(o1.scores, o2.scores)
+    # Caffe2 pickle -> student backbone only
+    g = torch.Generator().manual_seed(1)
+    w1 = torch.randn(64, 3, 7, 7, generator=g).numpy()
+    w2 = torch.randn(64, 64, 1, 1, generator=g).numpy()
+    gam = (torch.rand(256, generator=g) + 0.5).numpy()
+    with open(tmp_path / "R-50.pkl", "wb") as f:
+        pickle.dump({"conv1_w": w1, "res2_0_branch2a_w": w2, "res2_0_branch1_bn_s": gam, "fc1000_w": np.zeros((1000, 2048), np.float32)}, f)
+    tr3 = mk()
+    t_before = tr3.model_teacher.engine.arena.data.clone()
+    tr3.checkpointer.load(str(tmp_path / "R-50.pkl"), checkpointables=[])
+    s = tr3.model.state_dict()
+    assert torch.equal(s["backbone.bottom_up.stem.conv1.weight"].cpu(), torch.from_numpy(w1))
+    assert torch.equal(s["backbone.bottom_up.res2.0.conv1.weight"].cpu(), torch.from_numpy(w2))
+    assert torch.equal(s["backbone.bottom_up.res2.0.shortcut.norm.weight"].cpu(), torch.from_numpy(gam))
+    assert torch.equal(tr3.model_teacher.engine.arena.data, t_before)
+
+
+def test_eval_mode_rescales_to_dataset_size():
+    """Eval-mode call contract (one_stage_detector.py:131-145, :225-240): [{"instances": Instances}] rescaled by [D2]
+    detector_postprocess to the dict's height / width; output_raw=True is NOT rescaled."""
+    from util_cfg import fcos_cfg
+    from ubteacher.d2compat.registry import META_ARCH_REGISTRY
+    model = META_ARCH_REGISTRY.get("OneStageDetector")(fcos_cfg())
+    diversify(model)
+    model.eval()
+    img = torch.randint(0, 256, (3, 128, 160), dtype=torch.uint8, generator=torch.Generator().manual_seed(3))
+    same = model([{"image": img}])[0]["instances"]
+    big = model([{"image": img, "height": 256, "width": 480}])[0]["instances"]
+    assert same.image_size == (128, 160) and big.image_size == (256, 480) and len(same) > 0
+    raw, _ = model([{"image": img, "height": 256, "width": 480}], output_raw=True)
+    n = int(raw["count"][0])
+    assert torch.equal(raw["pred_boxes"][0, :n].clamp(min=0).cpu()[:, 0], same.pred_boxes.tensor.cpu()[:, 0]) or n != len(same)
+    ref = same.pred_boxes.tensor.cpu() * torch.tensor([3.0, 2.0, 3.0, 2.0])
+    ref[:, 0::2].clamp_(0, 480); ref[:, 1::2].clamp_(0, 256)
+    keep = ((ref[:, 2] - ref[:, 0]) > 0) & ((ref[:, 3] - ref[:, 1]) > 0)
+    torch.testing.assert_close(big.pred_boxes.tensor.cpu(), ref[keep], rtol=0, atol=1e-3)
+
+
+def test_train_loop_burn_in_then_semisup():
+    """trainer.train(): burn-in steps (supervised only, teacher untouched), the copy at iter == BURN_UP_STEP, then the
+    semi-supervised steps, with [D2] WarmupMultiStepLR driving the learning rate (trainer.py:191-210, SURVEY §8f #4)."""
+    from util_cfg import fcos_cfg
+    from ubteacher.data.synthetic import SyntheticTwoCropLoader
+    from ubteacher.engine import UBTeacherTrainer
+    cfg = fcos_cfg(**{"SEMISUPNET.BURN_UP_STEP": 2, "SOLVER.MAX_ITER": 5, "SOLVER.WARMUP_ITERS": 3, "SOLVER.STEPS": (4,),
+                      "SOLVER.BASE_LR": 0.001})
+    tr = UBTeacherTrainer(cfg, data_loader=SyntheticTwoCropLoader(1, 1, h=96, w=128, boxes_per_image=2, pool=2))
+    t0 = tr.model_teacher.engine.arena.data.clone()
+    lrs, seen = [], []
+    step = tr.run_step_full_semisup
+
+    def spy():
+        lrs.append(tr.optimizer.param_groups[0]["lr"])
+        if tr.iter == 2:         # entering the semi-supervised phase: the teacher has not moved during burn-in
+            assert torch.equal(tr.model_teacher.engine.arena.data, t0)
+        step()
+        seen.append(set(tr.last_losses[0]))
+    tr.run_step_full_semisup = spy
+    tr.train()
+    assert tr.iter == 4 and len(lrs) == 5
+    f = cfg.SOLVER.WARMUP_FACTOR
+    want = [0.001 * (f * (1 - i / 3) + i / 3) if i < 3 else 0.001 * (0.1 if i >= 4 else 1.0) for i in range(5)]
+    assert all(abs(a - b) < 1e-12 for a, b in zip(lrs, want)), (lrs, want)
+    assert all("loss_fcos_cls_pseudo" not in s for s in seen[:2]) and all("loss_fcos_cls_pseudo" in s for s in seen[2:])
+    assert not torch.equal(tr.model_teacher.engine.arena.data, t0)

@@ -63,6 +63,11 @@ if not HAVE_D2:
             y2 = self.tensor[:, 3].clamp(min=0, max=h)
             self.tensor = torch.stack((x1, y1, x2, y2), dim=-1)
 
+        def scale(self, scale_x: float, scale_y: float):
+            self.tensor = self.tensor.clone()
+            self.tensor[:, 0::2] *= scale_x
+            self.tensor[:, 1::2] *= scale_y
+
         def nonempty(self, threshold: float = 0.0):
             box = self.tensor
             return ((box[:, 2] - box[:, 0]) > threshold) & ((box[:, 3] - box[:, 1]) > threshold)
@@ -229,3 +234,22 @@ if not HAVE_D2:
             for img, pad_img in zip(tensors, batched):
                 pad_img[..., : img.shape[-2], : img.shape[-1]].copy_(img)
             return ImageList(batched.contiguous(), image_sizes)
+
+
+def detector_postprocess(results, output_height, output_width):
+    """[D2] v0.6 ``modeling.postprocessing.detector_postprocess`` for box-only results (the part the reference's
+    wrapper ``ubteacher/modeling/one_stage_detector.py:16-43`` delegates to; UT2 has no masks / keypoints / beziers):
+    rescale ``pred_boxes`` (or ``proposal_boxes``) from the network input resolution to (output_height, output_width),
+    clip, and drop empty boxes."""
+    scale_x = float(output_width) / results.image_size[1]
+    scale_y = float(output_height) / results.image_size[0]
+    out = Instances((int(output_height), int(output_width)), **results.get_fields())
+    if out.has("pred_boxes"):
+        boxes = out.pred_boxes = out.pred_boxes.clone()       # ([D2] rescales the caller's Boxes in place; a copy here)
+    elif out.has("proposal_boxes"):
+        boxes = out.proposal_boxes = out.proposal_boxes.clone()
+    else:
+        return out
+    boxes.scale(scale_x, scale_y)
+    boxes.clip(out.image_size)
+    return out[boxes.nonempty()]

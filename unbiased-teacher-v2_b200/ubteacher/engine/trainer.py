@@ -17,6 +17,7 @@ import time
 import numpy as np
 import torch
 
+from ..checkpoint import DetectionTSCheckpointer
 from ..d2compat import comm
 from ..d2compat.events import EventStorage
 from ..d2compat.registry import META_ARCH_REGISTRY
@@ -86,6 +87,9 @@ class UBTeacherTrainer:
         self.scheduler = self.build_lr_scheduler(cfg, self.optimizer)
         self.ensem_ts_model = EnsembleTSModel(model_teacher, model)
         self.pseudo_generator = self._make_pseudo_generator(cfg)
+        # trainer.py:71-76: the checkpointer owns the teacher+student ensemble, the optimizer and the scheduler
+        self.checkpointer = DetectionTSCheckpointer(self.ensem_ts_model, cfg.OUTPUT_DIR, save_to_disk=comm.is_main_process(),
+                                                    optimizer=self.optimizer, scheduler=self.scheduler)
         self.start_iter = 0
         self.iter = 0
         self.max_iter = cfg.SOLVER.MAX_ITER
@@ -130,7 +134,19 @@ class UBTeacherTrainer:
                                       rank=comm.get_rank())
 
     def resume_or_load(self, resume=True):
-        return None   # checkpoint I/O is outside the hot path
+        """trainer.py:86-102 ([D2] DefaultTrainer.resume_or_load): last checkpoint of OUTPUT_DIR when resuming, else
+        MODEL.WEIGHTS (a Caffe2 pickle initialises the student backbone only). ``detectron2://`` URLs need the network
+        and are skipped with a warning when no local copy exists."""
+        import os
+        path = self.cfg.MODEL.WEIGHTS
+        if path and "://" in path and not os.path.exists(path):
+            logger.warning("MODEL.WEIGHTS %s is not reachable offline: keeping the seeded initialisation", path)
+            path = ""
+        ckpt = self.checkpointer.resume_or_load(path, resume=resume)
+        if resume and self.checkpointer.has_checkpoint():
+            self.start_iter = ckpt.get("iteration", -1) + 1
+            self.iter = self.start_iter
+        return ckpt
 
     # ---------------------------------------------------------------- loop
     def train(self):

@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from ...d2compat.registry import META_ARCH_REGISTRY, PROPOSAL_GENERATOR_REGISTRY, ROI_HEADS_REGISTRY
-from ...d2compat.structures import Boxes, Instances
+from ...d2compat.structures import Boxes, Instances, detector_postprocess
 from ..fcos.fcos_outputs import GT_CAP, BoxSet
 from ..rcnn_engine import RcnnEngine
 
@@ -154,9 +154,15 @@ class TwoStagePseudoLabGeneralizedRCNN(nn.Module):
         raise ValueError(f"unknown branch {branch}")
 
     def inference(self, batched_inputs):
-        """[D2] GeneralizedRCNN.inference (eval mode): [{"instances": Instances}] at the input resolution."""
-        _, dets, _ = self.forward_teacher(batched_inputs)
-        return [{"instances": r} for r in detections_to_instances(dets)]
+        """[D2] GeneralizedRCNN.inference (eval mode): RPN with the *_TEST top-k values, box head, fast_rcnn_inference,
+        then [D2] detector_postprocess to the dataset dict's height / width -> [{"instances": Instances}]."""
+        eng = self.engine
+        fwd = eng.forward_features(self._images(batched_inputs), train=False)
+        _, dets, _ = eng.forward_inference(fwd, test=True)
+        out = []
+        for d, r in zip(batched_inputs, detections_to_instances(dets)):
+            out.append({"instances": detector_postprocess(r, d.get("height", r.image_size[0]), d.get("width", r.image_size[1]))})
+        return out
 
     def forward_teacher(self, batched_inputs):
         """unsup_data_weak: (proposals_rpn, proposals_roih, ROI_predictions), all device-resident."""

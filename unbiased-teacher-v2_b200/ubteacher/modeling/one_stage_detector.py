@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from ..d2compat.registry import META_ARCH_REGISTRY
-from ..d2compat.structures import Instances
+from ..d2compat.structures import Instances, detector_postprocess
 from .fcos.fcos_outputs import BoxSet, FCOSOutputs, as_boxset, dets_to_instances
 from .fcos_engine import FcosEngine
 
@@ -99,15 +99,19 @@ class PseudoProposalNetwork(nn.Module):
     def _scales(self):
         return self.engine.scales
 
-    def _predict(self, fwd, nms_method, output_raw):
+    def _predict(self, fwd, nms_method, output_raw, batched_inputs=None):
         dets = self.fcos_outputs.predict_proposals(fwd, self._scales(), nms_method)
         if output_raw:
-            return dets, fwd
-        return [{"proposals": r} for r in dets_to_instances(dets)]
+            return dets, fwd          # "output raw will not rescale" (one_stage_detector.py:131-133)
+        out = []
+        for i, r in enumerate(dets_to_instances(dets)):      # standard output rescales to the dataset dict's height / width
+            d = batched_inputs[i] if batched_inputs is not None else {}
+            out.append({"proposals": detector_postprocess(r, d.get("height", r.image_size[0]), d.get("width", r.image_size[1]))})
+        return out
 
     def forward(self, batched_inputs, output_raw=False, nms_method="cls_n_ctr", ignore_near=False, branch="labeled"):
         fwd = self.engine.forward(self._images(batched_inputs), train=False)
-        return self._predict(fwd, nms_method, output_raw)
+        return self._predict(fwd, nms_method, output_raw, batched_inputs)
 
     def _run_backward(self, pending, gouts):
         eng = self.engine

@@ -41,6 +41,7 @@ class RcnnEngine(EngineBase):
         self.rpn_batch, self.rpn_pos_frac = r.BATCH_SIZE_PER_IMAGE, r.POSITIVE_FRACTION
         self.rpn_thr = tuple(r.IOU_THRESHOLDS)
         self.rpn_pre, self.rpn_post, self.rpn_nms = r.PRE_NMS_TOPK_TRAIN, r.POST_NMS_TOPK_TRAIN, r.NMS_THRESH
+        self.rpn_pre_test, self.rpn_post_test = r.PRE_NMS_TOPK_TEST, r.POST_NMS_TOPK_TEST
         h = m.ROI_HEADS
         self.roi_batch, self.roi_pos_frac, self.roi_iou = h.BATCH_SIZE_PER_IMAGE, h.POSITIVE_FRACTION, h.IOU_THRESHOLDS[0]
         self.append_gt = h.PROPOSAL_APPEND_GT
@@ -154,11 +155,12 @@ class RcnnEngine(EngineBase):
         return {"rpn_out": rpn_out, "levels": levels, "geom": geom, "rgeom": rgeom, "N": N, "image_sizes": sizes,
                 "image_hw": image_hw, "tape": tape, "padded": (Hp, Wp)}
 
-    def proposals(self, fwd):
+    def proposals(self, fwd, test=False):
         """[D2] find_top_rpn_proposals (rpn.py:72-74). The teacher is never put in eval mode (trainer.py:628-629,
-        SURVEY A.3 #8), so both replicas use the *_TRAIN top-k values."""
-        return R.rpn_predict_proposals(fwd["geom"], fwd["N"], fwd["rpn_out"], fwd["image_hw"], self.rpn_pre, self.rpn_post,
-                                       self.rpn_nms)
+        SURVEY A.3 #8), so inside a training step both replicas use the *_TRAIN top-k values; `test` selects the *_TEST
+        values of a model in eval mode."""
+        pre, post = (self.rpn_pre_test, self.rpn_post_test) if test else (self.rpn_pre, self.rpn_post)
+        return R.rpn_predict_proposals(fwd["geom"], fwd["N"], fwd["rpn_out"], fwd["image_hw"], pre, post, self.rpn_nms)
 
     def box_head(self, fwd, rois, roi_cnt, train):
         """ROIAlign over p2..p5 -> fc1 -> ReLU -> fc2 -> ReLU -> fused predictor. rois [N, Rcap, 4]."""
@@ -193,9 +195,9 @@ class RcnnEngine(EngineBase):
                "proposals": props}
         return rpn_losses, roi_losses, ctx
 
-    def forward_inference(self, fwd):
+    def forward_inference(self, fwd, test=False):
         """unsup_data_weak branch (rcnn.py:42-55): proposals -> box head on all of them -> fast_rcnn_inference."""
-        props = self.proposals(fwd)
+        props = self.proposals(fwd, test)
         pred = self.box_head(fwd, props["proposal_boxes"], props["count"], False)
         dets = R.fastrcnn_inference(pred, props["proposal_boxes"], props["count"], fwd["image_hw"], self.test_score,
                                     self.test_nms, self.test_topk, self.box_w)

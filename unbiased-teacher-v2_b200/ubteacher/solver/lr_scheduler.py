@@ -28,3 +28,10 @@ class WarmupMultiStepLR:
         self.last_epoch += 1
         for g, lr in zip(self.optimizer.param_groups, self.get_lr()):
             g["lr"] = lr
+
+    def state_dict(self):
+        return {"last_epoch": self.last_epoch, "base_lrs": list(self.base_lrs)}
+
+    def load_state_dict(self, sd):
+        self.last_epoch = sd["last_epoch"] - 1
+        self.step()
