@@ -28,10 +28,10 @@ constexpr int A_BYTES = BM * BK * 2;        // 16 KiB
 constexpr int SMEM_LIMIT = 232448;          // 227 KiB of dynamic shared memory per CTA on sm_100a
 constexpr int BAR_BYTES = 3072;             // 1 KiB mbarriers + TMEM slot | 1 KiB scale[256] | 1 KiB shift[256]
 constexpr int EPI_TILE_BYTES = 32 * 128;    // one 32-row x 64-col bf16 staging tile, 128B-swizzled
-constexpr int NUM_THREADS = 320;            // warp0 TMA, warp1 MMA, warps2-9 epilogue (two per TMEM lane quadrant)
+constexpr int NUM_THREADS = 576;            // warp0 TMA, warp1 MMA, warps2-17 epilogue (four per TMEM lane quadrant)
 constexpr int TMEM_COLS = 512;              // 2 accumulator buffers x 256 fp32 columns
 
-// shared memory: [stages x (16 KiB A + block_n x 128 B of B)][barriers, scale, shift][8 warps x 2 aux tiles of 4 KiB
+// shared memory: [stages x (16 KiB A + block_n x 128 B of B)][barriers, scale, shift][16 warps x 1 aux tile of 4 KiB
 // (only with aux)]. The ring is as deep as the 227 KiB allow (<= 8): narrow-N tiles move few bytes per stage, and with
 // only 4 stages in flight they are bound by TMA latency, not by bandwidth or the tensor pipe.
 __host__ __device__ constexpr int stage_bytes(int block_n) { return A_BYTES + block_n * BK * 2; }
@@ -111,11 +111,11 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
-  uint64_t* aux_bar = tempty_bar + 2;             // [16] two per epilogue warp (double-buffered aux tiles)
+  uint64_t* aux_bar = tempty_bar + 2;             // [16] one per epilogue warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 16);
   float* s_scale = reinterpret_cast<float*>(bar_base + 1024);
   float* s_shift = reinterpret_cast<float*>(bar_base + 2048);
-  uint8_t* aux_stage = bar_base + BAR_BYTES;                 // 8 warps x 2 tiles x 4 KiB (aux_kind != 0 only)
+  uint8_t* aux_stage = bar_base + BAR_BYTES;                 // 16 warps x 4 KiB (aux_kind != 0 only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -133,7 +133,7 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 256);
+      mbar_init(&tempty_bar[i], 512);
     }
     for (int i = 0; i < 16; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
@@ -210,64 +210,48 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
       }
     }
   } else {
-    // -------------------------------------------------- epilogue (8 warps: TMEM lane quadrant = warp % 4, two warps
-    // per quadrant take alternate 64-column chunks). TMEM hands each lane one output ROW. Stores go straight from
-    // registers (32-byte sectors per lane — measured faster than staging + coalesced or TMA stores: L2 merges the
-    // sectors and nothing waits on a store). What must NOT sit in the dependency chain is the residual / ReLU-mask
-    // read: those tiles are TMA-prefetched into 128B-swizzled shared-memory tiles one output tile ahead and read
-    // row-per-lane without bank conflicts; scale / shift vectors are staged in shared memory per n-tile. The "manual"
-    // path (nearest-2x upsampled FPN residual, residual + mask together, Cout < 64) uses plain loads.
+    // -------------------------------------------------- epilogue: 16 warps. TMEM lane quadrant = warp % 4 (hardware
+    // rule), 64-column chunk of the tile = (warp - 2) / 4. TMEM hands each lane one output ROW. Four warps per scheduler
+    // instead of two: the epilogue of the memory-bound 1x1 convolutions is a serial chain per warp (TMEM load -> shift /
+    // residual / ReLU -> store) and ncu showed every unit below 60 % with the warps stalled on their own loads; the
+    // TMEM loads are software-pipelined 16 columns ahead. Stores go straight from registers (256-bit per lane: L2 merges
+    // the sectors and nothing waits on a store). Residual / ReLU-mask tiles are TMA-prefetched into 128B-swizzled
+    // shared-memory tiles one output tile ahead and read row-per-lane without bank conflicts; scale / shift vectors are
+    // staged in shared memory per n-tile. The "manual" path (nearest-2x upsampled FPN residual, residual + mask
+    // together, Cout < 64) uses plain loads.
     const int quad = warp & 3;
-    const int ew = warp - 2;                     // 0..7
-    const int half = ew >> 2;                    // which alternate chunks this warp owns
-    const int et = threadIdx.x - 64;             // 0..255 among the epilogue threads
-    uint8_t* astage = aux_stage + ew * 2 * EPI_TILE_BYTES;
-    const int nchunks = (a.block_n + 63) / 64;
-    const int my_chunks = (nchunks - half + 1) / 2;           // chunks half, half+2, ...
-    const uint32_t aux_bytes = my_chunks * EPI_TILE_BYTES;
-    const bool use_aux = a.aux_kind != 0 && my_chunks > 0;
-    // One chunk per warp (block_n <= 128): the warp's two staging slots double-buffer, and the aux tile of tile i+1 is
-    // requested BEFORE tile i is processed. Memory-bound convolutions finish their MMAs long before the epilogue gets
-    // to the tile, so epilogues run back to back and a request issued only after tile i would expose the full DRAM
-    // latency on every tile (ncu: the epilogue warps sat in the aux mbarrier wait).
-    const bool dbl = use_aux && nchunks <= 2;
-    uint64_t* my_aux_bar = aux_bar + ew * 2;
-    uint32_t acc = 0, acc_phase = 0, aux_phase = 0, it = 0;
+    const int ew = warp - 2;                     // 0..15
+    const int c0 = (ew >> 2) * 64;               // this warp's 64-column chunk inside the tile
+    const int et = threadIdx.x - 64;             // 0..511 among the epilogue threads
+    const bool has_chunk = c0 < a.block_n;
+    const int cw = min(64, a.block_n - c0);
+    uint8_t* atile = aux_stage + ew * EPI_TILE_BYTES;
+    const bool use_aux = a.aux_kind != 0 && has_chunk;
+    uint32_t acc = 0, acc_phase = 0, aux_phase = 0;
     int staged_n_tile = -1;
-    if (use_aux && lane == 0 && (int)blockIdx.x < num_tiles) {   // aux tiles of this CTA's first tile
+    if (use_aux && lane == 0 && (int)blockIdx.x < num_tiles) {   // aux tile of this CTA's first tile
       const int t = blockIdx.x;
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
       const int lv = level_of(a.lt, m_tile);
-      mbar_arrive_expect_tx(&my_aux_bar[0], aux_bytes);
-      for (int c = 0; c < my_chunks; ++c)
-        tma_load_2d(astage + c * EPI_TILE_BYTES, &tmap_aux, &my_aux_bar[0], n_tile * a.block_n + (half + 2 * c) * 64,
-                    a.lt.row_off[lv] + (m_tile - a.lt.tile_off[lv]) * BM + quad * 32);
+      mbar_arrive_expect_tx(&aux_bar[ew], EPI_TILE_BYTES);
+      tma_load_2d(atile, &tmap_aux, &aux_bar[ew], n_tile * a.block_n + c0,
+                  a.lt.row_off[lv] + (m_tile - a.lt.tile_off[lv]) * BM + quad * 32);
     }
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      if (dbl) {                        // request tile t + grid's aux chunk into the other slot (read last in tile it-1)
-        __syncwarp();
-        const int tn = t + gridDim.x;
-        if (lane == 0 && tn < num_tiles) {
-          const int n_tile2 = tn % a.n_tiles, m_tile2 = tn / a.n_tiles;
-          const int lv2 = level_of(a.lt, m_tile2);
-          const uint32_t nb = (it + 1) & 1;
-          mbar_arrive_expect_tx(&my_aux_bar[nb], EPI_TILE_BYTES);
-          tma_load_2d(astage + nb * EPI_TILE_BYTES, &tmap_aux, &my_aux_bar[nb], n_tile2 * a.block_n + half * 64,
-                      a.lt.row_off[lv2] + (m_tile2 - a.lt.tile_off[lv2]) * BM + quad * 32);
-        }
-      }
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
       const int lv = level_of(a.lt, m_tile);
       const int ml = (m_tile - a.lt.tile_off[lv]) * BM + quad * 32 + lane;     // row inside the level
       const bool row_ok = ml < a.lt.M[lv];
       const int m = a.lt.row_off[lv] + ml;                                      // row in the level-major buffer
       const int nbase = n_tile * a.block_n;
-      if (n_tile != staged_n_tile) {            // (re)stage scale / shift of this n-tile: uniform across the 8 warps
-        if (staged_n_tile >= 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int n = nbase + et;
-        s_scale[et] = (a.scale && et < a.block_n && n < a.Cout) ? __ldg(a.scale + n) : 1.f;
-        s_shift[et] = (a.shift && et < a.block_n && n < a.Cout) ? __ldg(a.shift + n) : 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (n_tile != staged_n_tile) {            // (re)stage scale / shift of this n-tile: uniform across the 16 warps
+        if (staged_n_tile >= 0) asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (et < 256) {
+          const int n = nbase + et;
+          s_scale[et] = (a.scale && et < a.block_n && n < a.Cout) ? __ldg(a.scale + n) : 1.f;
+          s_shift[et] = (a.shift && et < a.block_n && n < a.Cout) ? __ldg(a.shift + n) : 0.f;
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
         staged_n_tile = n_tile;
       }
       size_t rrow = (size_t)m;                 // residual row for the manual path
@@ -279,43 +263,36 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      if (use_aux) {
-        if (dbl) mbar_wait(&my_aux_bar[it & 1], (it >> 1) & 1);
-        else mbar_wait(&my_aux_bar[0], aux_phase);
-      }
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
-      for (int c0 = half * 64, ci = 0; c0 < a.block_n; c0 += 128, ++ci) {
-        const int cw = min(64, a.block_n - c0);
-        uint32_t v[4][16];
-        tmem_ld_32x16(taddr + c0, v[0]);
-        if (cw > 16) tmem_ld_32x16(taddr + c0 + 16, v[1]);
-        if (cw > 32) tmem_ld_32x16(taddr + c0 + 32, v[2]);
-        if (cw > 48) tmem_ld_32x16(taddr + c0 + 48, v[3]);
-        tmem_ld_wait();
-        const uint8_t* atile = astage + (dbl ? (it & 1) : ci) * EPI_TILE_BYTES;
+      if (has_chunk) {
+        if (use_aux) mbar_wait(&aux_bar[ew], aux_phase);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + c0;
+        uint32_t v[2][16];
+        tmem_ld_32x16(taddr, v[0]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+          tmem_ld_wait();
+          if (j + 1 < 4 && (j + 1) * 16 < cw) tmem_ld_32x16(taddr + (j + 1) * 16, v[(j + 1) & 1]);   // in flight while j is processed
+          const uint32_t(&vj)[16] = v[j & 1];
           const int cj = c0 + j * 16;
           const int nj = nbase + cj;
           if (j * 16 < cw && nj < a.Cout && row_ok) {
             float f[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              // every broadcast LDS.128 costs four LSU wavefronts and the LSU data pipe is the busiest unit of the
-              // memory-bound 1x1 convolutions: the scale vector is only read when there is one (FrozenBN scales are
-              // folded into the packed weights, so the product path has none)
+              // the scale vector is only read when there is one (FrozenBN scales are folded into the packed weights, so
+              // the product path has none)
               const float4 hv = *reinterpret_cast<const float4*>(s_shift + cj + 4 * i);
               if (a.scale) {
                 const float4 sv = *reinterpret_cast<const float4*>(s_scale + cj + 4 * i);
-                f[4 * i] = fmaf(__uint_as_float(v[j][4 * i]), sv.x, hv.x);
-                f[4 * i + 1] = fmaf(__uint_as_float(v[j][4 * i + 1]), sv.y, hv.y);
-                f[4 * i + 2] = fmaf(__uint_as_float(v[j][4 * i + 2]), sv.z, hv.z);
-                f[4 * i + 3] = fmaf(__uint_as_float(v[j][4 * i + 3]), sv.w, hv.w);
+                f[4 * i] = fmaf(__uint_as_float(vj[4 * i]), sv.x, hv.x);
+                f[4 * i + 1] = fmaf(__uint_as_float(vj[4 * i + 1]), sv.y, hv.y);
+                f[4 * i + 2] = fmaf(__uint_as_float(vj[4 * i + 2]), sv.z, hv.z);
+                f[4 * i + 3] = fmaf(__uint_as_float(vj[4 * i + 3]), sv.w, hv.w);
               } else {
-                f[4 * i] = __uint_as_float(v[j][4 * i]) + hv.x;
-                f[4 * i + 1] = __uint_as_float(v[j][4 * i + 1]) + hv.y;
-                f[4 * i + 2] = __uint_as_float(v[j][4 * i + 2]) + hv.z;
-                f[4 * i + 3] = __uint_as_float(v[j][4 * i + 3]) + hv.w;
+                f[4 * i] = __uint_as_float(vj[4 * i]) + hv.x;
+                f[4 * i + 1] = __uint_as_float(vj[4 * i + 1]) + hv.y;
+                f[4 * i + 2] = __uint_as_float(vj[4 * i + 2]) + hv.z;
+                f[4 * i + 3] = __uint_as_float(vj[4 * i + 3]) + hv.w;
               }
             }
             uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0, y0 = x0, y1 = x0;   // x: residual, y: mask
@@ -354,30 +331,27 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 8; ++i) ow[i] = mask_bf16x2(ow[i], yw[i]);
             }
-            // one 256-bit store per lane (STG.256): half the LSU wavefronts of two 128-bit stores — the epilogue of the
-            // memory-bound 1x1 convolutions is limited by the L1/LSU pipe, not by DRAM
+            // one 256-bit store per lane (STG.256): half the LSU wavefronts of two 128-bit stores
             asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(a.out + (size_t)m * a.ldo + nj),
                          "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7])
                          : "memory");
           }
         }
       }
-      // accumulators consumed: release the TMEM buffer, then prefetch the aux tiles of this CTA's next tile
+      // accumulators consumed: release the TMEM buffer, then prefetch the aux tile of this CTA's next tile
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (use_aux && !dbl) {
+      if (use_aux) {
         aux_phase ^= 1;
-        __syncwarp();                   // every lane finished reading the aux tiles
+        __syncwarp();                   // every lane finished reading the aux tile
         const int tn = t + gridDim.x;
         if (lane == 0 && tn < num_tiles) {
           const int n_tile2 = tn % a.n_tiles, m_tile2 = tn / a.n_tiles;
           const int lv2 = level_of(a.lt, m_tile2);
-          mbar_arrive_expect_tx(&my_aux_bar[0], aux_bytes);
-          for (int c = 0; c < my_chunks; ++c)
-            tma_load_2d(astage + c * EPI_TILE_BYTES, &tmap_aux, &my_aux_bar[0],
-                        n_tile2 * a.block_n + (half + 2 * c) * 64,
-                        a.lt.row_off[lv2] + (m_tile2 - a.lt.tile_off[lv2]) * BM + quad * 32);
+          mbar_arrive_expect_tx(&aux_bar[ew], EPI_TILE_BYTES);
+          tma_load_2d(atile, &tmap_aux, &aux_bar[ew], n_tile2 * a.block_n + c0,
+                      a.lt.row_off[lv2] + (m_tile2 - a.lt.tile_off[lv2]) * BM + quad * 32);
         }
       }
     }
