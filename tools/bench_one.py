@@ -12,6 +12,7 @@ w = torch.randn(Cout, k, k, Cin, device="cuda").bfloat16()
 P, Q = ops.conv_out_hw(H, W, k, k, s, pad)
 y = torch.empty(B, P, Q, Cout, device="cuda", dtype=torch.bfloat16)
 r = torch.randn(B, P, Q, Cout, device="cuda").bfloat16()
+r2 = torch.randn(B, P, Q, Cout, device="cuda").bfloat16()
 sc = (torch.rand(Cout, device="cuda") + 0.5) if os.environ.get("SCALE") else None   # product path: FrozenBN scale folded into the weights
 sh = torch.randn(Cout, device="cuda")
 dw = torch.zeros(Cout, k, k, Cin, device="cuda")
@@ -19,7 +20,7 @@ def run():
     if kind == "wgrad":
         ops.conv2d_wgrad(x, r, Cout, k, k, s, pad, dw)
     else:
-        ops.conv2d(x, w, Cout, k, k, s, pad, sc, sh, r if aux == "res" else None, True, y, False, r if aux == "mask" else None)
+        ops.conv2d(x, w, Cout, k, k, s, pad, sc, sh, r if aux in ("res", "resmask") else None, aux != "resmask", y, False, r2 if aux in ("mask", "resmask") else None)
 for _ in range(3): run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -28,5 +29,5 @@ for _ in range(10): run()
 e1.record(); torch.cuda.synchronize()
 t = e0.elapsed_time(e1) / 10
 fl = 2.0 * B * P * Q * Cout * Cin * k * k
-byts = (x.numel() + y.numel() + (y.numel() if aux != "none" else 0)) * 2
+byts = (x.numel() + y.numel() * (1 + {"none": 0, "res": 1, "mask": 1, "resmask": 2}[aux])) * 2
 print(f"{kind} {aux}: {t*1e3:.1f} us  {fl/t/1e9:.1f} TF/s  {byts/t/1e6:.0f} GB/s")
