@@ -231,6 +231,17 @@ int ut2_fastrcnn_gather(int N, int Ccap, int K, int Rcap, const int* keep_idx, c
 int ut2_add_f32_bf16(const float* a, const void* b /* bf16, optional */, void* out, long long n, void* stream);
 int ut2_subsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream);   /* [D2] LastLevelMaxPool */
 
+/* ================================================================ two-crop strong augmentation
+ * ubteacher/data/detection_utils.py:8-46 (torchvision ColorJitter / RandomGrayscale / GaussianBlur / RandomErasing on PIL
+ * images), restated bit for bit on planar uint8 [3,h,w] device images. All random draws arrive in `table`, a DEVICE
+ * array of N 168-byte records (little endian, python struct "<6Q2i4i4f3i2Ii12iIi"):
+ *   u64 src, dst, tmp (blur scratch), noise[3] (optional float32 [3,eh,ew] per erase; 0 = hashed N(0,1));
+ *   i32 h, w; i32 order[4] (ColorJitter op per slot: 0 brightness 1 contrast 2 saturation 3 hue, -1 none);
+ *   f32 factor[4] (indexed by op); i32 hue_shift (uint8(int32(hue*255))), gray, blur_r (< 0: no blur);
+ *   u32 blur_ww, blur_fw (Pillow box-blur fixed-point weights); i32 n_erase; i32 ei[3], ej[3], eh[3], ew[3]; u32 seed; i32 pad.
+ * lsum_ws: device uint64 [N,4] scratch. max_pixels = max h*w, max_erase = max n_erase over the batch. */
+int ut2_strong_augment_u8(const void* table, int N, int max_pixels, int max_erase, unsigned long long* lsum_ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
