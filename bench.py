@@ -288,6 +288,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--arch", default="fcos", choices=["fcos", "rcnn"],
                     help="fcos = BASELINE config #2 (the headline workload); rcnn = the Faster R-CNN recipe (configs #3 / #5)")
+    ap.add_argument("--augment", action="store_true", help="produce the strong views with the device two-crop augmentation "
+                    "(SURVEY 8(f) rank 1) inside every timed step")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -344,7 +346,7 @@ def main():
 
     images_per_step = world * (args.label + args.unlabel)
     # ---- arm 1: inputs resident in HBM ---------------------------------------------------------------------
-    loader = SyntheticTwoCropLoader(args.label, args.unlabel, rank=rank, device=dev)
+    loader = SyntheticTwoCropLoader(args.label, args.unlabel, rank=rank, device=dev, strong_augment=args.augment)
     tr = Trainer(cfg, data_loader=loader)
     tr.storage = EventStorage(0)
     tr.metrics_period = 10 ** 9
@@ -391,7 +393,7 @@ def main():
     # ---- arm 2: end to end through the public API: pinned host inputs, H2D inside the step, loss read back --
     e2e = None
     if not args.no_e2e:
-        loader = SyntheticTwoCropLoader(args.label, args.unlabel, rank=rank, device=None)
+        loader = SyntheticTwoCropLoader(args.label, args.unlabel, rank=rank, device=None, strong_augment=args.augment)
         tr = Trainer(cfg, data_loader=loader)
         tr.storage = EventStorage(0)
         tr.metrics_period = 10 ** 9
@@ -400,7 +402,8 @@ def main():
             tr.enable_cuda_graph(True)
         timed(tr, max(args.warmup, 3), True)
         secs2, _, d2h, _, _ = timed(tr, args.steps, True)
-        h2d = (2 * args.label + 2 * args.unlabel) * 3 * 800 * 1333 + 2 * args.label * (128 * 4 * 4 + 128 * 8 + 4)
+        n_up = (args.label + args.unlabel) if args.augment else (2 * args.label + 2 * args.unlabel)   # augment: only the weak views cross PCIe
+        h2d = n_up * 3 * 800 * 1333 + 2 * args.label * (128 * 4 * 4 + 128 * 8 + 4)
         e2e = {"value": images_per_step * args.steps / secs2, "unit": "images/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * secs2 / args.steps}
         del tr, loader
@@ -424,7 +427,8 @@ def main():
                                        "BURN_UP_STEP=0, random init (cold pseudo-label regime)",
                            "global_batch": images_per_step, "parallelism": f"dp{world}",
                            "l2_policy": "no flush needed: each step streams >10 GB of activations (>> 126 MB L2)",
-                           "launch_mode": "eager" if args.no_graph else "whole step replayed as one CUDA graph"},
+                           "launch_mode": "eager" if args.no_graph else "whole step replayed as one CUDA graph",
+                           "two_crop_augmentation": "device (strong = aug(weak) every step, outside the graph)" if args.augment else "none (pre-made views)"},
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
                 "host_wall_s": wall}
         print(json.dumps(line), flush=True)

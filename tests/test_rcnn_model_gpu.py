@@ -289,3 +289,22 @@ def test_cuda_graph_step_matches_eager():
         assert torch.isfinite(b).all()
         torch.testing.assert_close(a, b, rtol=[1e-5, 5e-3, 5e-3, 5e-3][i], atol=1e-3)
     assert rel(gs, ps) < 2e-2
+
+
+def test_eval_mode_inference_contract():
+    """model.eval(): [D2] GeneralizedRCNN.inference -> [{"instances": Instances(pred_boxes, scores, pred_classes,
+    pred_boxes_std)}] rescaled to the dict's height / width ([D2] detector_postprocess), RPN *_TEST top-k."""
+    from util_cfg import rcnn_cfg
+    from ubteacher.d2compat.registry import META_ARCH_REGISTRY
+    m = META_ARCH_REGISTRY.get("TwoStagePseudoLabGeneralizedRCNN")(rcnn_cfg())
+    diversify(m)
+    m.eval()
+    img = torch.randint(0, 256, (3, 128, 160), dtype=torch.uint8, generator=torch.Generator().manual_seed(4))
+    a = m([{"image": img}])[0]["instances"]
+    b = m([{"image": img, "height": 256, "width": 320}])[0]["instances"]
+    assert a.image_size == (128, 160) and b.image_size == (256, 320)
+    assert a.has("pred_boxes") and a.has("scores") and a.has("pred_classes") and a.has("pred_boxes_std") and len(a) <= 100
+    ref = a.pred_boxes.tensor.cpu() * 2.0
+    keep = ((ref[:, 2] - ref[:, 0]) > 0) & ((ref[:, 3] - ref[:, 1]) > 0)
+    torch.testing.assert_close(b.pred_boxes.tensor.cpu(), ref[keep], rtol=0, atol=1e-3)
+    assert torch.equal(b.scores.cpu(), a.scores.cpu()[keep])

@@ -22,9 +22,16 @@ class SyntheticTwoCropLoader:
     """device=None: images live in pinned host memory and GT are host ``Instances`` (the end-to-end mode, the
     model does the H2D copies); device="cuda": the image pool and pre-packed GT ``BoxSet``s are resident in HBM."""
 
-    def __init__(self, n_label, n_unlabel, h=800, w=1333, rank=0, boxes_per_image=7, pool=2, pin=True, device=None):
+    def __init__(self, n_label, n_unlabel, h=800, w=1333, rank=0, boxes_per_image=7, pool=2, pin=True, device=None,
+                 strong_augment=False):
         self.nl, self.nu, self.h, self.w, self.rank, self.nbox = n_label, n_unlabel, h, w, rank, boxes_per_image
         self.device = device
+        # strong_augment: the strong ("q") views are produced from the weak ("k") views by the device two-crop
+        # augmentation (dataset_mapper.py:116-131: image_strong_aug = strong_augmentation(image_weak_aug)), every step
+        self.aug = None
+        if strong_augment:
+            from .gpu_augmentation import GpuStrongAugmentation
+            self.aug = GpuStrongAugmentation()
         g = torch.Generator().manual_seed(20260 + 1000 * rank)
         # a small pool of random images, re-used round-robin (generating 32 fresh 3.2 MB images per step on the
         # host would measure torch.randint, not the training step)
@@ -62,7 +69,7 @@ class SyntheticTwoCropLoader:
             gt = self.gt_pool[(self.step // max(len(self.pool), 1)) % len(self.gt_pool)]
             for d in lq + lk:
                 d["instances"] = gt          # batch-level device-resident ground truth (strong + weak share boxes)
-            return lq, lk, uq, uk
+            return self._strong(lq, lk, uq, uk)
 
         def lab(n):
             q, k = [], []
@@ -73,4 +80,14 @@ class SyntheticTwoCropLoader:
             return q, k
         lq, lk = lab(self.nl)
         uq, uk = lab(self.nu)
+        return self._strong(lq, lk, uq, uk)
+
+    def _strong(self, lq, lk, uq, uk):
+        if self.aug is not None:
+            dev = self.device if self.device is not None else torch.device("cuda")
+            weak = [d["image"].to(dev, non_blocking=True) for d in lk + uk]       # H2D of the weak views (end-to-end mode)
+            for d, w_ in zip(lk + uk, weak):
+                d["image"] = w_
+            for d, s_ in zip(lq + uq, self.aug(weak)):
+                d["image"] = s_
         return lq, lk, uq, uk
