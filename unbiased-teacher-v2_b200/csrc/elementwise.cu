@@ -393,7 +393,9 @@ extern "C" int ut2_zero_stuff_s2_nhwc(const void* in, void* out, int N, int P, i
 extern "C" int ut2_colsum_bf16(const void* g, float* db, int M, int C, void* stream) {
   if (C % 8 || C > 2048 || C <= 0) return ut2_fail(-2, "colsum: need C % 8 == 0 and C <= 2048");
   const int C8 = C / 8;
-  int blocks = 148 * 6;      // ~12 MB of 16-byte loads in flight (6 blocks x 256 threads x 4 loads per SM): HBM latency x bandwidth
+  // one block per SM, except for the >= 256 MB gradients of the R-CNN p2 level / level-major RPN conv, where more 16-byte
+  // loads in flight pay for the extra per-block reductions and atomics (measured: 148 is better below, 4 x 148 above)
+  int blocks = M >= 500000 ? 148 * 4 : 148;
   int rows = (M + blocks - 1) / blocks;
   const int rpp = 256 / C8;
   if (rows < 8 * rpp) rows = 8 * rpp;
