@@ -35,11 +35,14 @@ constexpr int TMEM_COLS = 512;              // 2 accumulator buffers x 256 fp32 
 // (only with aux)]. The ring is as deep as the 227 KiB allow (<= 8): narrow-N tiles move few bytes per stage, and with
 // only 4 stages in flight they are bound by TMA latency, not by bandwidth or the tensor pipe.
 __host__ __device__ constexpr int stage_bytes(int block_n) { return A_BYTES + block_n * BK * 2; }
-constexpr int smem_bytes(int stages, int block_n, bool aux) {
-  return 1024 + stages * stage_bytes(block_n) + BAR_BYTES + (aux ? 16 : 0) * EPI_TILE_BYTES;
+// aux_tiles: 0 (no residual / mask tile), 16 (one staging tile per epilogue warp) or 32 (double-buffered). pad: 1024 bytes
+// of slack for the run-time 1024-byte alignment of the buffer; the double-buffered 256-wide case fits the 227 KiB only
+// without it (2 x 48 KiB stages + 3 KiB + 128 KiB = 227 KiB exactly) and then REQUIRES an aligned base (checked).
+constexpr int smem_bytes(int stages, int block_n, int aux_tiles, int pad) {
+  return pad + stages * stage_bytes(block_n) + BAR_BYTES + aux_tiles * EPI_TILE_BYTES;
 }
-inline int pick_stages(int block_n, bool aux) {
-  int s = (SMEM_LIMIT - 1024 - BAR_BYTES - (aux ? 16 : 0) * EPI_TILE_BYTES) / stage_bytes(block_n);
+inline int pick_stages(int block_n, int aux_tiles, int pad) {
+  int s = (SMEM_LIMIT - pad - BAR_BYTES - aux_tiles * EPI_TILE_BYTES) / stage_bytes(block_n);
   return s > MAX_STAGES ? MAX_STAGES : s;
 }
 
@@ -74,6 +77,8 @@ struct ConvFwdArgs {
   int R, S, Cin;
   int relu;
   int stages;                       // operand ring depth (pick_stages)
+  int aux_dbl;                      // 1: two aux staging tiles per epilogue warp (memory-bound convs: see the epilogue)
+  int no_pad;                       // 1: the dynamic shared buffer must already be 1024-byte aligned
   int aux_kind;                     // 0 none, 1 residual tile via TMA, 2 relu-mask tile via TMA
   int manual;                       // 1: epilogue with plain loads/stores (res_up2, residual+mask, Cout < 64)
   const float* scale;
@@ -104,6 +109,7 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
                 const ConvFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer: LDS / STS, not generic LD / ST
+  if (a.no_pad && smem != smem_raw) __trap();      // the launch reserved no alignment slack (see smem_bytes)
   const int STAGES = a.stages;
   const int STAGE_BYTES = stage_bytes(a.block_n);
   uint8_t* bar_base = smem + STAGES * STAGE_BYTES;
@@ -111,8 +117,8 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
-  uint64_t* aux_bar = tempty_bar + 2;             // [16] one per epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 16);
+  uint64_t* aux_bar = tempty_bar + 2;             // [32] two per epilogue warp (the second one only with aux_dbl)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 32);
   float* s_scale = reinterpret_cast<float*>(bar_base + 1024);
   float* s_shift = reinterpret_cast<float*>(bar_base + 2048);
   uint8_t* aux_stage = bar_base + BAR_BYTES;                 // 16 warps x 4 KiB (aux_kind != 0 only)
@@ -135,7 +141,7 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 512);
     }
-    for (int i = 0; i < 16; ++i) mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < 32; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -225,19 +231,38 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
     const int et = threadIdx.x - 64;             // 0..511 among the epilogue threads
     const bool has_chunk = c0 < a.block_n;
     const int cw = min(64, a.block_n - c0);
-    uint8_t* atile = aux_stage + ew * EPI_TILE_BYTES;
     const bool use_aux = a.aux_kind != 0 && has_chunk;
-    uint32_t acc = 0, acc_phase = 0, aux_phase = 0;
+    // Memory-bound convolutions finish their MMAs long before the epilogue gets to the tile, so epilogues run back to
+    // back: an aux tile requested only after the previous tile was consumed exposes the whole DRAM latency on every tile
+    // (ncu: ~30 % of the epilogue warps' samples sat in this mbarrier wait). With aux_dbl each warp owns two staging
+    // tiles and requests tile i+1's chunk BEFORE it processes tile i.
+    const bool dbl = use_aux && a.aux_dbl;
+    uint8_t* atile0 = aux_stage + ew * (a.aux_dbl ? 2 : 1) * EPI_TILE_BYTES;
+    uint64_t* my_aux_bar = aux_bar + ew * 2;
+    uint32_t acc = 0, acc_phase = 0, aux_phase = 0, it = 0;
     int staged_n_tile = -1;
     if (use_aux && lane == 0 && (int)blockIdx.x < num_tiles) {   // aux tile of this CTA's first tile
       const int t = blockIdx.x;
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
       const int lv = level_of(a.lt, m_tile);
-      mbar_arrive_expect_tx(&aux_bar[ew], EPI_TILE_BYTES);
-      tma_load_2d(atile, &tmap_aux, &aux_bar[ew], n_tile * a.block_n + c0,
+      mbar_arrive_expect_tx(&my_aux_bar[0], EPI_TILE_BYTES);
+      tma_load_2d(atile0, &tmap_aux, &my_aux_bar[0], n_tile * a.block_n + c0,
                   a.lt.row_off[lv] + (m_tile - a.lt.tile_off[lv]) * BM + quad * 32);
     }
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      if (dbl) {                        // request the next tile's chunk into the other slot (last read in tile it-1)
+        __syncwarp();
+        const int tn = t + gridDim.x;
+        if (lane == 0 && tn < num_tiles) {
+          const int n_tile2 = tn % a.n_tiles, m_tile2 = tn / a.n_tiles;
+          const int lv2 = level_of(a.lt, m_tile2);
+          const uint32_t nb = (it + 1) & 1;
+          mbar_arrive_expect_tx(&my_aux_bar[nb], EPI_TILE_BYTES);
+          tma_load_2d(atile0 + nb * EPI_TILE_BYTES, &tmap_aux, &my_aux_bar[nb], n_tile2 * a.block_n + c0,
+                      a.lt.row_off[lv2] + (m_tile2 - a.lt.tile_off[lv2]) * BM + quad * 32);
+        }
+      }
+      const uint8_t* atile = atile0 + (dbl ? (it & 1) : 0) * EPI_TILE_BYTES;
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
       const int lv = level_of(a.lt, m_tile);
       const int ml = (m_tile - a.lt.tile_off[lv]) * BM + quad * 32 + lane;     // row inside the level
@@ -264,7 +289,10 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (has_chunk) {
-        if (use_aux) mbar_wait(&aux_bar[ew], aux_phase);
+        if (use_aux) {
+          if (dbl) mbar_wait(&my_aux_bar[it & 1], (it >> 1) & 1);
+          else mbar_wait(&my_aux_bar[0], aux_phase);
+        }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + c0;
         uint32_t v[2][16];
         tmem_ld_32x16(taddr, v[0]);
@@ -342,15 +370,15 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (use_aux) {
+      if (use_aux && !dbl) {
         aux_phase ^= 1;
         __syncwarp();                   // every lane finished reading the aux tile
         const int tn = t + gridDim.x;
         if (lane == 0 && tn < num_tiles) {
           const int n_tile2 = tn % a.n_tiles, m_tile2 = tn / a.n_tiles;
           const int lv2 = level_of(a.lt, m_tile2);
-          mbar_arrive_expect_tx(&aux_bar[ew], EPI_TILE_BYTES);
-          tma_load_2d(atile, &tmap_aux, &aux_bar[ew], n_tile2 * a.block_n + c0,
+          mbar_arrive_expect_tx(&my_aux_bar[0], EPI_TILE_BYTES);
+          tma_load_2d(atile0, &tmap_aux, &my_aux_bar[0], n_tile2 * a.block_n + c0,
                       a.lt.row_off[lv2] + (m_tile2 - a.lt.tile_off[lv2]) * BM + quad * 32);
         }
       }
@@ -621,7 +649,17 @@ static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, 
   a.out = static_cast<__nv_bfloat16*>(y);
   a.manual = (Cout < 64 && (residual || relu_mask)) || (residual && res_up2) || (residual && relu_mask);
   a.aux_kind = a.manual ? 0 : (residual ? 1 : (relu_mask ? 2 : 0));
-  a.stages = pick_stages(block_n, a.aux_kind != 0);
+  // double-buffered aux tiles for the most epilogue-bound convolutions (K <= 128: res2 / res3 conv3 + shortcut, +11 %
+  // measured); from K = 256 on the two operand stages that are left cost more than the exposed aux latency (K = 512:
+  // -25 %), and the tensor-bound ones hide it behind their main loop anyway. UT2_AUX_DBL=0 disables (A/B runs).
+  static int dbl_on = -1;
+  if (dbl_on < 0) { const char* e = getenv("UT2_AUX_DBL"); dbl_on = e ? atoi(e) : 1; }
+  a.aux_dbl = (dbl_on && a.aux_kind != 0 && R * S * Cin <= 128) ? 1 : 0;
+  const int aux_tiles = a.aux_kind ? (a.aux_dbl ? 32 : 16) : 0;
+  a.no_pad = (a.aux_dbl && pick_stages(block_n, aux_tiles, 1024) < 2) ? 1 : 0;
+  const int smem_pad = a.no_pad ? 0 : 1024;
+  a.stages = pick_stages(block_n, aux_tiles, smem_pad);
+  if (a.stages < 2) return ut2_fail(-5, "conv_fwd: shared memory budget");
   CUtensorMap tw, to, ta;
   int rc = make_tmap_2d_bf16(&tw, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64, block_n);
   if (rc) return ut2_fail(rc, "conv_fwd: weight tensor map encode failed");
@@ -641,7 +679,7 @@ static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, 
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_fwd_kernel<<<grid, NUM_THREADS, smem_bytes(a.stages, block_n, a.aux_kind != 0), static_cast<cudaStream_t>(stream)>>>(
+  conv_fwd_kernel<<<grid, NUM_THREADS, smem_bytes(a.stages, block_n, aux_tiles, smem_pad), static_cast<cudaStream_t>(stream)>>>(
       tx, tw, to, ta, a);
   return ut2_check_launch("conv_fwd");
 }
