@@ -50,7 +50,9 @@ nms_sort_kernel(int M, const float* __restrict__ boxes, const float* __restrict_
   __syncthreads();
   float mx = -3.0e38f;
   int local = 0;
-  for (int i = threadIdx.x; i < CAP; i += blockDim.x) {
+  int cap = 32;                    // the bitonic network spans the next power of two above the candidate count
+  while (cap < n_in) cap <<= 1;
+  for (int i = threadIdx.x; i < cap; i += blockDim.x) {
     unsigned long long k = ~0ull;
     if (i < n_in) {
       const float s = scores[(size_t)img * M + i];
@@ -78,9 +80,9 @@ nms_sort_kernel(int M, const float* __restrict__ boxes, const float* __restrict_
   mx = smax[0];
   for (int i = 1; i < 32; ++i) mx = fmaxf(mx, smax[i]);
   const int n = s_n;
-  for (int k = 2; k <= CAP; k <<= 1) {
+  for (int k = 2; k <= cap && n_in > 1; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < CAP / 2; t += blockDim.x) {     // one compare-exchange pair per thread and pass
+      for (int t = threadIdx.x; t < cap / 2; t += blockDim.x) {     // one compare-exchange pair per thread and pass
         const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), ixj = i | j;
         const bool up = (i & k) == 0;
         const unsigned long long a = skey[i], b = skey[ixj];

@@ -229,7 +229,11 @@ nms_sort_kernel(int M, int C, const float* __restrict__ det_box, const float* __
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
-  for (int i = threadIdx.x; i < SORT_CAP; i += blockDim.x) {
+  // the bitonic network only spans the next power of two above the candidate count (an image without candidates —
+  // every image right after initialisation — costs nothing), one compare-exchange pair per thread and pass
+  int cap = 32;
+  while (cap < n) cap <<= 1;
+  for (int i = threadIdx.x; i < cap; i += blockDim.x) {
     unsigned long long k = ~0ull;
     if (i < n) {
       const unsigned int sb = __float_as_uint(det_score[(size_t)img * M + i]);
@@ -241,17 +245,15 @@ nms_sort_kernel(int M, int C, const float* __restrict__ det_box, const float* __
   __syncthreads();
   mx = smax[0];
   for (int i = 1; i < 32; ++i) mx = fmaxf(mx, smax[i]);
-  for (int k = 2; k <= SORT_CAP; k <<= 1) {
+  for (int k = 2; k <= cap && n > 1; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < SORT_CAP; i += blockDim.x) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const bool up = (i & k) == 0;
-          const unsigned long long a = skey[i], b = skey[ixj];
-          if ((a > b) == up) {
-            skey[i] = b; skey[ixj] = a;
-            const unsigned short t = sval[i]; sval[i] = sval[ixj]; sval[ixj] = t;
-          }
+      for (int t = threadIdx.x; t < cap / 2; t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), ixj = i | j;
+        const bool up = (i & k) == 0;
+        const unsigned long long a = skey[i], b = skey[ixj];
+        if ((a > b) == up) {
+          skey[i] = b; skey[ixj] = a;
+          const unsigned short v = sval[i]; sval[i] = sval[ixj]; sval[ixj] = v;
         }
       }
       __syncthreads();
