@@ -242,6 +242,13 @@ int ut2_subsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, voi
  * lsum_ws: device uint64 [N,4] scratch. max_pixels = max h*w, max_erase = max n_erase over the batch. */
 int ut2_strong_augment_u8(const void* table, int N, int max_pixels, int max_erase, unsigned long long* lsum_ws, void* stream);
 
+/* weak augmentation (dataset_mapper.py:88-91 -> [D2] ResizeShortestEdge + RandomFlip): Pillow Image.resize(BILINEAR) bit for
+ * bit (22-bit fixed-point separable resampling, uint8 between the passes) + optional horizontal flip; src uint8 [h,w,3] HWC
+ * -> dst uint8 [3,new_h,new_w] CHW. tmp: uint8 [h,new_w,3]; ws: scratch of ut2_resize_workspace_bytes(h, w, new_h, new_w). */
+long long ut2_resize_workspace_bytes(int h, int w, int new_h, int new_w);
+int ut2_resize_flip_u8(const void* src_hwc, int h, int w, void* dst_chw, int new_h, int new_w, int flip, void* tmp_hwc, void* ws,
+                       long long ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

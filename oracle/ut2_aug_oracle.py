@@ -215,3 +215,90 @@ def strong_augment(img, p):
     if p["blur"] is not None:
         out = gaussian_blur(out, p["blur"])
     return totensor_erase_topil(out, p["erase"])
+
+
+# ------------------------------------------------------------------------------------------------ weak augmentation
+# [D2] ResizeShortestEdge + RandomFlip (dataset_mapper.py:88-91 through detectron2.data.transforms; Detectron2 is not on
+# disk: the parameter logic below restates v0.6 `ResizeShortestEdge.get_output_shape`, `ResizeTransform`, `HFlipTransform`
+# and `transform_instance_annotations` — unpinned) on top of Pillow's `Image.resize(..., BILINEAR)` (libImaging/Resample.c:
+# antialiased separable convolution with 22-bit fixed-point coefficients, uint8 between the passes — pinned against Pillow).
+PRECISION_BITS = 32 - 8 - 2
+
+
+def resample_coeffs(in_size, out_size):
+    """precompute_coeffs + normalize_coeffs_8bpc for the bilinear filter (support 1.0) over the whole input axis."""
+    scale = float(in_size) / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), dtype=np.int64)
+    kk = np.zeros((out_size, ksize), dtype=np.int64)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        x = np.arange(xmax)
+        w = np.maximum(1.0 - np.abs((x + xmin - center + 0.5) * ss), 0.0)
+        ww = 0.0
+        for v in w:                       # the C loop adds left to right (numpy's sum would go pairwise from 8 terms on)
+            ww += float(v)
+        if ww != 0.0:
+            w = w / ww
+        kk[xx, :xmax] = np.where(w < 0, (-0.5 + w * (1 << PRECISION_BITS)).astype(np.int64), (0.5 + w * (1 << PRECISION_BITS)).astype(np.int64))
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def _resample_axis1(img, out_size):
+    """One pass along axis 1 of a uint8 [A, in, C] array."""
+    bounds, kk = resample_coeffs(img.shape[1], out_size)
+    out = np.empty((img.shape[0], out_size, img.shape[2]), dtype=np.uint8)
+    src = img.astype(np.int64)
+    for xx in range(out_size):
+        xmin, xmax = bounds[xx]
+        acc = (1 << (PRECISION_BITS - 1)) + (src[:, xmin:xmin + xmax, :] * kk[xx, :xmax, None]).sum(axis=1)
+        out[:, xx, :] = np.clip(acc >> PRECISION_BITS, 0, 255)
+    return out
+
+
+def pil_resize_bilinear(img, new_w, new_h):
+    """Image.resize((new_w, new_h), BILINEAR) for uint8 [H, W, 3]: horizontal pass, then vertical pass."""
+    out = img
+    if new_w != img.shape[1]:
+        out = _resample_axis1(out, new_w)
+    if new_h != img.shape[0]:
+        out = _resample_axis1(out.transpose(1, 0, 2), new_h).transpose(1, 0, 2)
+    return np.ascontiguousarray(out)
+
+
+def shortest_edge_shape(h, w, size, max_size):
+    """[D2] ResizeShortestEdge.get_output_shape."""
+    scale = size * 1.0 / min(h, w)
+    if h < w:
+        newh, neww = size, scale * w
+    else:
+        newh, neww = scale * h, size
+    if max(newh, neww) > max_size:
+        scale = max_size * 1.0 / max(newh, neww)
+        newh, neww = newh * scale, neww * scale
+    return int(newh + 0.5), int(neww + 0.5)
+
+
+def weak_augment(img, new_h, new_w, flip):
+    out = pil_resize_bilinear(img, new_w, new_h) if (new_h, new_w) != img.shape[:2] else img
+    return np.ascontiguousarray(out[:, ::-1]) if flip else out
+
+
+def transform_boxes(boxes, h, w, new_h, new_w, flip):
+    """[D2] transform_instance_annotations for XYXY_ABS boxes: ResizeTransform.apply_coords, HFlipTransform.apply_coords on
+    the four corners, min / max, clip to the image; then filter_empty_instances (side > 1e-5). Returns (boxes, keep)."""
+    b = np.asarray(boxes, dtype=np.float64).reshape(-1, 4).copy()
+    sx, sy = new_w * 1.0 / w, new_h * 1.0 / h
+    x0, y0, x1, y1 = b[:, 0] * sx, b[:, 1] * sy, b[:, 2] * sx, b[:, 3] * sy
+    if flip:
+        x0, x1 = new_w - x1, new_w - x0
+    out = np.stack([np.minimum(x0, x1), np.minimum(y0, y1), np.maximum(x0, x1), np.maximum(y0, y1)], axis=1).clip(min=0)
+    out = np.minimum(out, np.array([new_w, new_h, new_w, new_h], dtype=np.float64))
+    keep = ((out[:, 2] - out[:, 0]) > 1e-5) & ((out[:, 3] - out[:, 1]) > 1e-5)
+    return out.astype(np.float32), keep

@@ -111,3 +111,54 @@ def test_full_size_batch_runs_and_is_deterministic():
         for (i, j, h, w, _) in p["erase"]:
             m[i:i + h, j:j + w] = False
         assert torch.equal(x[:, m], y[:, m])
+
+
+@pytest.mark.parametrize("size,new,flip", [((67, 93), (40, 56), False), ((67, 93), (67, 50), True), ((50, 80), (100, 160), True),
+                                           ((120, 75), (77, 48), False), ((200, 300), (51, 77), True), ((64, 64), (64, 64), True),
+                                           ((480, 640), (800, 1067), False), ((1200, 1600), (600, 800), True)])
+def test_resize_flip_matches_pillow_oracle(size, new, flip):
+    from oracle import ut2_aug_oracle as A
+    from ubteacher.data.dataset_mapper import resize_flip
+    img = rand_img(11, *size)
+    got = resize_flip(torch.from_numpy(img).cuda(), new[0], new[1], flip)
+    assert np.array_equal(to_host(got), A.weak_augment(img, new[0], new[1], flip))
+
+
+def test_two_crop_mapper_matches_oracle():
+    """DatasetMapperTwoCropSeparate on the device == the oracle chain (weak resize + flip, box transform, strong aug of the
+    weak view) under the same numpy / torch / random seeds; returns (strong dicts, weak dicts) with shared labels."""
+    from oracle import ut2_aug_oracle as A
+    from util_cfg import fcos_cfg
+    from ubteacher.data.dataset_mapper import DatasetMapperTwoCropSeparate
+    cfg = fcos_cfg(**{"INPUT.MIN_SIZE_TRAIN": (96, 160), "INPUT.MAX_SIZE_TRAIN": 220})
+    mapper = DatasetMapperTwoCropSeparate(cfg, True)
+    mapper.strong_augmentation.exact_noise = True
+    sizes = [(120, 90), (75, 133), (200, 150), (64, 64)]
+    dicts = []
+    for i, (h, w) in enumerate(sizes):
+        dicts.append({"image": rand_img(20 + i, h, w), "image_id": i, "file_name": f"{i}.jpg",
+                      "annotations": [{"bbox": [5.0, 7.0, w - 10.0, h - 3.0], "category_id": i, "iscrowd": 0},
+                                      {"bbox": [1.0, 1.0, 9.0, 9.0], "category_id": 7, "iscrowd": 1},
+                                      {"bbox": [w / 2.0, h / 3.0, w / 2.0 + 11, h / 3.0 + 17], "category_id": 3, "iscrowd": 0}]})
+    np.random.seed(5); torch.manual_seed(6); random.seed(7)
+    q, k = mapper(dicts)
+    np.random.seed(5); torch.manual_seed(6); random.seed(7)
+    weak_ref, meta = [], []
+    for d in dicts:
+        h, w = d["image"].shape[:2]
+        size = np.random.randint(96, 161)
+        nh, nw = A.shortest_edge_shape(h, w, size, 220)
+        flip = bool(np.random.uniform() < 0.5)
+        weak_ref.append(A.weak_augment(d["image"], nh, nw, flip))
+        meta.append((h, w, nh, nw, flip))
+    assert any(m[4] for m in meta) and not all(m[4] for m in meta)
+    for i, d in enumerate(dicts):
+        h, w, nh, nw, flip = meta[i]
+        assert np.array_equal(to_host(k[i]["image"]), weak_ref[i]), i
+        p = A.draw_params(nh, nw)
+        assert np.array_equal(to_host(q[i]["image"]), A.strong_augment(weak_ref[i], p)), i
+        boxes, keep = A.transform_boxes([a["bbox"] for a in d["annotations"] if not a["iscrowd"]], h, w, nh, nw, flip)
+        for view in (q[i], k[i]):
+            assert view["instances"].image_size == (nh, nw) and view["height"] == h and view["width"] == w and view["image_id"] == i
+            assert np.array_equal(view["instances"].gt_boxes.tensor.numpy(), boxes[keep])
+            assert view["instances"].gt_classes.tolist() == [i, 3]

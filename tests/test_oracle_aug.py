@@ -107,3 +107,20 @@ def test_end_to_end_matches_reference_pipeline(seed):
     p = A.draw_params(img.shape[0], img.shape[1])
     got = A.strong_augment(img, p)
     assert np.array_equal(got, want), (seed, p["jitter"], p["gray"], p["blur"], [e[:4] for e in p["erase"]])
+
+
+@pytest.mark.parametrize("size,new", [((67, 93), (40, 56)), ((67, 93), (67, 50)), ((50, 80), (100, 160)), ((120, 75), (77, 48)),
+                                      ((33, 41), (90, 41)), ((200, 300), (51, 77)), ((64, 64), (63, 65))])
+def test_pil_bilinear_resize_bit_exact(size, new):
+    img = rand_img(9, *size)
+    want = np.array(Image.fromarray(img, "RGB").resize((new[1], new[0]), Image.BILINEAR))
+    assert np.array_equal(A.pil_resize_bilinear(img, new[1], new[0]), want)
+
+
+def test_shortest_edge_and_box_transform():
+    assert A.shortest_edge_shape(480, 640, 800, 1333) == (800, 1067)
+    assert A.shortest_edge_shape(427, 640, 800, 1333) == (800, 1199)
+    assert A.shortest_edge_shape(300, 1000, 800, 1333) == (400, 1333)
+    assert A.shortest_edge_shape(640, 480, 600, 1333) == (800, 600)
+    b, keep = A.transform_boxes([[10, 20, 110, 220], [600, 0, 700, 50], [5, 5, 5, 9]], 480, 640, 240, 320, True)
+    assert np.allclose(b[0], [320 - 55, 10, 320 - 5, 110]) and np.allclose(b[1], [0, 0, 20, 25]) and list(keep) == [True, True, False]

@@ -14,6 +14,7 @@
 // Every kernel is a flat coalesced pass over planar uint8 (HBM-bound: <= 6 B/pixel per pass); one launch covers the
 // batch: grid = (blocks per image, N), images that do not take part in a pass exit at once.
 #include "ut2_internal.h"
+#include <math.h>
 #include <stdint.h>
 
 namespace {
@@ -190,9 +191,126 @@ __global__ void __launch_bounds__(256) aug_erase_kernel(const AugImage* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------ weak augmentation: resize + flip
+// Pillow Image.resize(..., BILINEAR) (libImaging/Resample.c): separable antialiased convolution, coefficients computed in
+// double, normalised, rounded to 22-bit fixed point; uint8 between the horizontal and the vertical pass. The double
+// arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction), so the integer coefficients equal Pillow's.
+constexpr int RS_BITS = 32 - 8 - 2;
+
+// table layout per axis: bounds[out][2] then kk[out][ksize]
+__global__ void resample_coeffs_kernel(int in_size, int out_size, int ksize, int* __restrict__ bounds, int* __restrict__ kk) {
+  const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xx >= out_size) return;
+  const double scale = __ddiv_rn((double)in_size, (double)out_size);
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = filterscale;                     // bilinear: support 1.0 * filterscale
+  const double ss = __ddiv_rn(1.0, filterscale);
+  const double center = __dmul_rn((double)xx + 0.5, scale);
+  int xmin = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+  if (xmin < 0) xmin = 0;
+  int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+  if (xmax > in_size) xmax = in_size;
+  xmax -= xmin;
+  double ww = 0.0;
+  for (int x = 0; x < xmax; ++x) {
+    const double t = fabs(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss));
+    ww = __dadd_rn(ww, t < 1.0 ? __dsub_rn(1.0, t) : 0.0);
+  }
+  int* k = kk + (size_t)xx * ksize;
+  for (int x = 0; x < ksize; ++x) {
+    int v = 0;
+    if (x < xmax) {
+      const double t = fabs(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss));
+      double w = t < 1.0 ? __dsub_rn(1.0, t) : 0.0;
+      if (ww != 0.0) w = __ddiv_rn(w, ww);
+      v = w < 0.0 ? (int)__dadd_rn(-0.5, __dmul_rn(w, (double)(1 << RS_BITS))) : (int)__dadd_rn(0.5, __dmul_rn(w, (double)(1 << RS_BITS)));
+    }
+    k[x] = v;
+  }
+  bounds[2 * xx] = xmin;
+  bounds[2 * xx + 1] = xmax;
+}
+
+// horizontal pass: src uint8 [h, w, 3] (HWC, what image decoders produce) -> tmp uint8 [h, new_w, 3]
+__global__ void __launch_bounds__(256) resample_h_kernel(const uint8_t* __restrict__ src, int h, int w, int new_w, int ksize,
+                                                         const int* __restrict__ bounds, const int* __restrict__ kk,
+                                                         uint8_t* __restrict__ tmp) {
+  const size_t n = (size_t)h * new_w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i / new_w), xx = (int)(i - (size_t)y * new_w);
+    const int xmin = bounds[2 * xx], xmax = bounds[2 * xx + 1];
+    const int* k = kk + (size_t)xx * ksize;
+    const uint8_t* line = src + ((size_t)y * w + xmin) * 3;
+    int s0 = 1 << (RS_BITS - 1), s1 = s0, s2 = s0;
+    for (int x = 0; x < xmax; ++x) {
+      const int kv = k[x];
+      s0 += line[3 * x] * kv; s1 += line[3 * x + 1] * kv; s2 += line[3 * x + 2] * kv;
+    }
+    uint8_t* o = tmp + i * 3;
+    o[0] = (uint8_t)min(max(s0 >> RS_BITS, 0), 255); o[1] = (uint8_t)min(max(s1 >> RS_BITS, 0), 255); o[2] = (uint8_t)min(max(s2 >> RS_BITS, 0), 255);
+  }
+}
+
+// vertical pass + HWC -> CHW (+ horizontal flip): tmp uint8 [h, new_w, 3] -> dst uint8 [3, new_h, new_w]
+__global__ void __launch_bounds__(256) resample_v_kernel(const uint8_t* __restrict__ tmp, int h, int new_w, int new_h, int ksize,
+                                                         const int* __restrict__ bounds, const int* __restrict__ kk, int flip,
+                                                         uint8_t* __restrict__ dst) {
+  const size_t n = (size_t)new_h * new_w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int yy = (int)(i / new_w), xx = (int)(i - (size_t)yy * new_w);
+    const int ymin = bounds[2 * yy], ymax = bounds[2 * yy + 1];
+    const int* k = kk + (size_t)yy * ksize;
+    const uint8_t* col = tmp + ((size_t)ymin * new_w + xx) * 3;
+    int s0 = 1 << (RS_BITS - 1), s1 = s0, s2 = s0;
+    for (int y = 0; y < ymax; ++y) {
+      const int kv = k[y];
+      const uint8_t* px = col + (size_t)y * new_w * 3;
+      s0 += px[0] * kv; s1 += px[1] * kv; s2 += px[2] * kv;
+    }
+    const size_t o = (size_t)yy * new_w + (flip ? new_w - 1 - xx : xx);
+    dst[o] = (uint8_t)min(max(s0 >> RS_BITS, 0), 255);
+    dst[n + o] = (uint8_t)min(max(s1 >> RS_BITS, 0), 255);
+    dst[2 * n + o] = (uint8_t)min(max(s2 >> RS_BITS, 0), 255);
+  }
+}
+
+static int resample_ksize(int in_size, int out_size) {
+  const double scale = (double)in_size / out_size;
+  const double fs = scale < 1.0 ? 1.0 : scale;
+  return (int)ceil(fs) * 2 + 1;
+}
+
 }  // namespace
 
 #define STREAM static_cast<cudaStream_t>(stream)
+
+// Weak augmentation of the two-crop pipeline (dataset_mapper.py:88-91 -> [D2] ResizeShortestEdge -> ResizeTransform ->
+// PIL Image.resize(BILINEAR), [D2] RandomFlip -> HFlipTransform): src uint8 [h, w, 3] HWC -> dst uint8 [3, new_h, new_w]
+// CHW, bit-exact with Pillow. tmp: uint8 [h, new_w, 3]; ws: int32 scratch of ut2_resize_workspace_bytes.
+extern "C" long long ut2_resize_workspace_bytes(int h, int w, int new_h, int new_w) {
+  if (h <= 0 || w <= 0 || new_h <= 0 || new_w <= 0) return 0;
+  return 4ll * ((long long)new_w * (2 + resample_ksize(w, new_w)) + (long long)new_h * (2 + resample_ksize(h, new_h))) + 256;
+}
+
+extern "C" int ut2_resize_flip_u8(const void* src_hwc, int h, int w, void* dst_chw, int new_h, int new_w, int flip, void* tmp_hwc,
+                                  void* ws, long long ws_bytes, void* stream) {
+  if (!src_hwc || !dst_chw || !tmp_hwc || !ws) return ut2_fail(-1, "resize: null pointer");
+  if (h <= 0 || w <= 0 || new_h <= 0 || new_w <= 0) return ut2_fail(-2, "resize: bad size");
+  if (ws_bytes < ut2_resize_workspace_bytes(h, w, new_h, new_w)) return ut2_fail(-3, "resize: workspace too small");
+  const int kw = resample_ksize(w, new_w), kh = resample_ksize(h, new_h);
+  int* bw = static_cast<int*>(ws);
+  int* kkw = bw + 2 * new_w;
+  int* bh = kkw + (size_t)new_w * kw;
+  int* kkh = bh + 2 * new_h;
+  resample_coeffs_kernel<<<(new_w + 127) / 128, 128, 0, STREAM>>>(w, new_w, kw, bw, kkw);
+  resample_coeffs_kernel<<<(new_h + 127) / 128, 128, 0, STREAM>>>(h, new_h, kh, bh, kkh);
+  const size_t n1 = (size_t)h * new_w, n2 = (size_t)new_h * new_w;
+  const int g1 = (int)((n1 + 255) / 256 < 148 * 8 ? (n1 + 255) / 256 : 148 * 8), g2 = (int)((n2 + 255) / 256 < 148 * 8 ? (n2 + 255) / 256 : 148 * 8);
+  resample_h_kernel<<<g1, 256, 0, STREAM>>>(static_cast<const uint8_t*>(src_hwc), h, w, new_w, kw, bw, kkw, static_cast<uint8_t*>(tmp_hwc));
+  resample_v_kernel<<<g2, 256, 0, STREAM>>>(static_cast<const uint8_t*>(tmp_hwc), h, new_w, new_h, kh, bh, kkh, flip,
+                                           static_cast<uint8_t*>(dst_chw));
+  return ut2_check_launch("resize_flip");
+}
 
 // table: DEVICE array of N 168-byte AugImage records (layout above / in include/ut2.h); lsum_ws: device uint64 [N, 4]
 // scratch. Overlapping erase regions are applied by separate launches so that "later on top" holds across blocks.
