@@ -146,3 +146,47 @@ def test_warmup_multistep_lr_state_roundtrip():
     assert sb.last_epoch == sa.last_epoch and b.param_groups[0]["lr"] == a.param_groups[0]["lr"] == 0.01 * 0.1
     sa.step(); sb.step()
     assert b.param_groups[0]["lr"] == a.param_groups[0]["lr"]
+
+
+def test_aspect_ratio_grouping_matches_reference_class():
+    """ubteacher/data/common.py:93-167 executed from the reference file (Detectron2 base class stubbed) vs the restatement,
+    on a stream with mixed orientations and different labeled / unlabeled batch sizes."""
+    import importlib.util
+    import os
+    import random
+    import sys
+    import types
+    import pytest
+    ref_path = "/root/reference/ubteacher/data/common.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("the reference tree is only mounted in the build container")
+    from ubteacher.data.common import AspectRatioGroupedSemiSupDatasetTwoCrop as Mine
+    saved = {k: sys.modules.get(k) for k in ("detectron2", "detectron2.data", "detectron2.data.common")}
+    try:
+        for k in saved:
+            sys.modules[k] = types.ModuleType(k)
+        sys.modules["detectron2.data.common"].MapDataset = object
+        sys.modules["detectron2.data.common"].AspectRatioGroupedDataset = object
+        spec = importlib.util.spec_from_file_location("_ref_common", ref_path)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    rng = random.Random(3)
+
+    def stream(n, tag):
+        out = []
+        for i in range(n):
+            w, h = (640, 480) if rng.random() < 0.6 else (480, 640)
+            out.append(({"width": w, "height": h, "id": (tag, i, "q")}, {"width": w, "height": h, "id": (tag, i, "k")}))
+        return out
+    lab, unl = stream(200, "l"), stream(200, "u")
+    a = list(ref.AspectRatioGroupedSemiSupDatasetTwoCrop((lab, unl), (3, 5)))
+    b = list(Mine((lab, unl), (3, 5)))
+    assert len(a) == len(b) > 10
+    ids = lambda batches: [[[d["id"] for d in part] for part in batch] for batch in batches]
+    assert ids(a) == ids(b)
