@@ -275,6 +275,26 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def saturate(trainer, arch):
+    """`--regime saturated`: widen the student's prediction heads (the teacher copies them at the burn-in boundary) so that
+    every level is full of candidates and pseudo labels survive the thresholds."""
+    import torch
+    g = torch.Generator().manual_seed(3)
+    V = trainer.model.engine.arena.views
+    if arch == "fcos":
+        hd = "proposal_generator.fcos_head."
+        spec = ((hd + "cls_logits.weight", 0.03), (hd + "bbox_pred.weight", 0.05), (hd + "ctrness.weight", 0.05),
+                (hd + "bbox_pred_std.weight", 0.05))
+        V[hd + "cls_logits.bias"].fill_(-3.8)
+    else:
+        spec = (("proposal_generator.rpn_head.objectness_logits.weight", 0.05), ("proposal_generator.rpn_head.anchor_deltas.weight", 0.02),
+                ("roi_heads.box_predictor.cls_score.weight", 0.3), ("roi_heads.box_predictor.bbox_pred.weight", 0.04),
+                ("roi_heads.box_predictor.bbox_pred_std.weight", 0.04))
+    for name, scale in spec:
+        V[name].copy_((torch.randn(V[name].shape, generator=g) * scale).to(V[name].device))
+    trainer.model.engine.refresh_operands()
+
+
 # ----------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -290,6 +310,10 @@ def main():
                     help="fcos = BASELINE config #2 (the headline workload); rcnn = the Faster R-CNN recipe (configs #3 / #5)")
     ap.add_argument("--augment", action="store_true", help="produce the strong views with the device two-crop augmentation "
                     "(SURVEY 8(f) rank 1) inside every timed step")
+    ap.add_argument("--regime", default="cold", choices=["cold", "saturated"],
+                    help="cold: seeded [D2]-style init (teacher scores ~0.01: no pseudo labels, the empty-GT path); saturated: the "
+                         "prediction heads are widened so that every level is full of candidates and pseudo labels survive the "
+                         "thresholds (worst-case top-k / NMS / target-assignment load, SURVEY.md 8d)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -344,6 +368,11 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / 1e3, _C.launch_count - l0, d2h, prof, wall
 
+    def pseudo_stats(trainer):
+        if trainer.last_pseudo is None:
+            return None
+        return [float(p.counts.float().mean()) for p in trainer.last_pseudo]
+
     images_per_step = world * (args.label + args.unlabel)
     # ---- arm 1: inputs resident in HBM ---------------------------------------------------------------------
     loader = SyntheticTwoCropLoader(args.label, args.unlabel, rank=rank, device=dev, strong_augment=args.augment)
@@ -351,6 +380,8 @@ def main():
     tr.storage = EventStorage(0)
     tr.metrics_period = 10 ** 9
     tr.iter = -1
+    if args.regime == "saturated":
+        saturate(tr, args.arch)
     # roofline pass: a few eager steps with every tensor-core launch bracketed by CUDA events
     timed(tr, max(args.warmup, 3), False)
     _, _, _, prof, _ = timed(tr, 2, False, profile=True)
@@ -362,6 +393,7 @@ def main():
     secs, launches, _, _, wall = timed(tr, args.steps, False)
     clk = clocks.stop() if clocks else {}
     value = images_per_step * args.steps / secs
+    pseudo_per_image = pseudo_stats(tr)
     peak_tf, peak_bw, peak_src = peaks()
     roof = None
     if prof:
@@ -398,6 +430,8 @@ def main():
         tr.storage = EventStorage(0)
         tr.metrics_period = 10 ** 9
         tr.iter = -1
+        if args.regime == "saturated":
+            saturate(tr, args.arch)
         if not args.no_graph:
             tr.enable_cuda_graph(True)
         timed(tr, max(args.warmup, 3), True)
@@ -424,7 +458,8 @@ def main():
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"{ARCH_NAME[args.arch]} UT2 run_step_full_semisup, IMG_PER_BATCH_LABEL={args.label} "
                                        f"UNLABEL={args.unlabel} per GPU, synthetic uint8 3x800x1333 (padded 800x1344), "
-                                       "BURN_UP_STEP=0, random init (cold pseudo-label regime)",
+                                       f"BURN_UP_STEP=0, random init ({args.regime} pseudo-label regime)",
+                           "regime": args.regime, "pseudo_boxes_per_image": pseudo_per_image,
                            "global_batch": images_per_step, "parallelism": f"dp{world}",
                            "l2_policy": "no flush needed: each step streams >10 GB of activations (>> 126 MB L2)",
                            "launch_mode": "eager" if args.no_graph else "whole step replayed as one CUDA graph",

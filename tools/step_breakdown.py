@@ -12,6 +12,8 @@ ARCH = os.environ.get("ARCH", "fcos")
 cfg = bench.build_cfg(B, B, arch=ARCH)
 tr = (UBTeacherTrainer if ARCH == "fcos" else UBRCNNTeacherTrainer)(cfg, data_loader=SyntheticTwoCropLoader(B, B, device=torch.device("cuda")))
 tr.storage = EventStorage(0); tr.metrics_period = 10**9; tr.iter = -1
+if os.environ.get("REGIME") == "saturated":
+    bench.saturate(tr, ARCH)
 for _ in range(3):
     tr.iter += 1; tr.run_step_full_semisup()
 torch.cuda.synchronize()

@@ -45,15 +45,33 @@ collect_kernel(Levels lv, int N, int C, const bf16* __restrict__ cls_out, const 
                int* __restrict__ cand_cnt) {
   const long long P = (long long)lv.off[lv.num] * N;
   const long long total = P * (C / 2);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / (C / 2);
+  const unsigned int lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+  // Whole warps stay in the loop: the slot reservation is warp-aggregated (one atomicAdd per warp and (image, level)
+  // counter instead of one per candidate — a saturated teacher has ~10^7 candidates on 5 N counters).
+  for (long long i0 = blockIdx.x * (long long)blockDim.x; i0 < total; i0 += (long long)gridDim.x * blockDim.x) {
+    const long long i = i0 + threadIdx.x;
+    const bool valid = i < total;
+    const long long p = valid ? i / (C / 2) : 0;
     const int c = (int)(i - p * (C / 2)) * 2;
-    const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(cls_out + p * ld + c));
-    const float pr[2] = {sigmoidf_(__uint_as_float(u << 16)), sigmoidf_(__uint_as_float(u & 0xFFFF0000u))};
-    if (!(pr[0] > thr) && !(pr[1] > thr)) continue;
-    int l, img, hw;
-    locate(lv, N, p, l, img, hw);
+    float pr[2] = {0.f, 0.f};
+    if (valid) {
+      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(cls_out + p * ld + c));
+      pr[0] = sigmoidf_(__uint_as_float(u << 16));
+      pr[1] = sigmoidf_(__uint_as_float(u & 0xFFFF0000u));
+    }
+    const bool t0 = valid && pr[0] > thr, t1 = valid && pr[1] > thr;
+    if (!__any_sync(0xffffffffu, t0 || t1)) continue;
+    int l = 0, img = 0, hw = 0;
+    if (t0 || t1) locate(lv, N, p, l, img, hw);
+    const int counter = (t0 || t1) ? img * lv.num + l : -1;
+    const unsigned int peers = __match_any_sync(0xffffffffu, counter);
+    const unsigned int b0 = __ballot_sync(0xffffffffu, t0) & peers, b1 = __ballot_sync(0xffffffffu, t1) & peers;
+    const int before = __popc(b0 & lt_mask) + __popc(b1 & lt_mask);
+    const int leader = __ffs(peers) - 1;
+    int slot0 = 0;
+    if (counter >= 0 && (int)lane == leader) slot0 = atomicAdd(cand_cnt + counter, __popc(b0) + __popc(b1));
+    slot0 = __shfl_sync(0xffffffffu, slot0, leader) + before;
+    if (counter < 0) continue;
     float q = 1.f;
     if (method == 1) {
       q = sigmoidf_(__bfloat162float(box_out[p * ld + 72]));
@@ -64,13 +82,14 @@ collect_kernel(Levels lv, int N, int C, const bf16* __restrict__ cls_out, const 
       q = s / 4.f;
     }
     const long long base = ((long long)lv.off[l] * N + (long long)img * lv.H[l] * lv.W[l]) * C;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (pr[k] > thr) {
-        const int slot = atomicAdd(cand_cnt + img * lv.num + l, 1);
-        cand_key[base + slot] = method == 0 ? pr[k] : __fmul_rn(pr[k], q);
-        cand_idx[base + slot] = hw * C + c + k;
-      }
+    if (t0) {
+      cand_key[base + slot0] = method == 0 ? pr[0] : __fmul_rn(pr[0], q);
+      cand_idx[base + slot0] = hw * C + c;
+      ++slot0;
+    }
+    if (t1) {
+      cand_key[base + slot0] = method == 0 ? pr[1] : __fmul_rn(pr[1], q);
+      cand_idx[base + slot0] = hw * C + c + 1;
     }
   }
 }
@@ -303,8 +322,8 @@ nms_mask_kernel(int M, int MW, const float* __restrict__ nms_box, const int* __r
   }
 }
 
-// serial scan + post-NMS top-k + gather of the per-detection fields the pseudo-labeler needs
-__global__ void __launch_bounds__(128)
+// chunked greedy scan + post-NMS top-k + gather of the per-detection fields the pseudo-labeler needs
+__global__ void __launch_bounds__(256)
 nms_scan_kernel(Levels lv, int N, int C, int M, int MW, int post_topk, int OUT_CAP,
                 const unsigned long long* __restrict__ mask, const int* __restrict__ order,
                 const float* __restrict__ det_box, const float* __restrict__ det_score,
@@ -315,34 +334,74 @@ nms_scan_kernel(Levels lv, int N, int C, int M, int MW, int post_topk, int OUT_C
                 int* __restrict__ out_cnt) {
   extern __shared__ unsigned long long remv[];       // MW words
   __shared__ int kept[1024];
-  __shared__ int s_nkeep;
+  __shared__ unsigned long long s_diag[64];
+  __shared__ float s_score[64];
+  __shared__ unsigned char s_rows[64];
+  __shared__ int s_nrows, s_nkeep, s_stop;
+  __shared__ float s_kth;
   const int img = blockIdx.x;
   const int n = min(det_cnt[img], SORT_CAP);
   const int nw = (n + 63) / 64;
   for (int i = threadIdx.x; i < MW; i += blockDim.x) remv[i] = 0;
-  if (threadIdx.x == 0) s_nkeep = 0;
+  if (threadIdx.x == 0) { s_nkeep = 0; s_stop = 0; s_kth = 0.f; }
   __syncthreads();
-  // Only the first `limit` survivors can matter: post-NMS keeps scores >= the post_topk-th best survivor,
-  // ties included; stop once a survivor with a strictly smaller score than the post_topk-th appears.
+  // Only the first `limit` survivors can matter: post-NMS keeps scores >= the post_topk-th best survivor, ties included;
+  // stop once a survivor with a strictly smaller score than the post_topk-th appears. Candidates are visited in 64-box
+  // chunks: one thread resolves the dependencies inside a chunk from the diagonal mask words (and applies the stop rule),
+  // then the whole CTA ORs the mask rows of that chunk's survivors into the removal bitmap — 3 barriers per 64 candidates
+  // instead of one per candidate (a saturated teacher needs thousands of candidates to find its 100 survivors).
   const float* score = det_score + (size_t)img * M;
   const int* ord = order + (size_t)img * M;
-  int nkeep = 0;
-  float kth = 0.f;
-  for (int i = 0; i < n; ++i) {
-    const bool dead = (remv[i >> 6] >> (i & 63)) & 1ull;     // uniform across the block
-    if (!dead) {
-      const float sc = score[ord[i]];
-      if (post_topk > 0 && nkeep >= post_topk) {
-        if (nkeep == post_topk) kth = score[ord[kept[post_topk - 1]]];
-        if (sc < kth || nkeep >= 1024 || nkeep >= OUT_CAP) break;
+  const unsigned long long* mimg = mask + (size_t)img * M * MW;
+  for (int c = 0; c < nw; ++c) {
+    const int cn = min(64, n - c * 64);
+    if (threadIdx.x < 64) {
+      const bool in = (int)threadIdx.x < cn;
+      s_diag[threadIdx.x] = in ? mimg[(size_t)(c * 64 + threadIdx.x) * MW + c] : 0ull;
+      s_score[threadIdx.x] = in ? score[ord[c * 64 + threadIdx.x]] : 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long dead = remv[c];
+      int nk = s_nkeep, nr = 0, stop = 0;
+      float kth = s_kth;
+      for (int b = 0; b < cn; ++b) {
+        if ((dead >> b) & 1ull) continue;
+        const float sc = s_score[b];
+        if (post_topk > 0 && nk >= post_topk) {
+          if (nk == post_topk) kth = score[ord[kept[post_topk - 1]]];
+          if (sc < kth || nk >= 1024 || nk >= OUT_CAP) { stop = 1; break; }
+        }
+        kept[nk++] = c * 64 + b;
+        s_rows[nr++] = (unsigned char)b;
+        dead |= s_diag[b];
       }
-      if (threadIdx.x == 0) kept[nkeep] = i;
-      ++nkeep;
-      const unsigned long long* mrow = mask + ((size_t)img * M + i) * MW;
-      for (int w = (i >> 6) + threadIdx.x; w < nw; w += blockDim.x) remv[w] |= mrow[w];
+      s_nkeep = nk; s_nrows = nr; s_stop = stop; s_kth = kth;
+    }
+    __syncthreads();
+    if (s_stop) break;
+    {
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5, nrows = s_nrows;
+      for (int w0 = c + 1; w0 < nw; w0 += 128) {
+        unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+        for (int r = warp; r < nrows; r += nwarps) {
+          const unsigned long long* row = mimg + (size_t)(c * 64 + s_rows[r]) * MW;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int w = w0 + lane + 32 * k;
+            if (w < nw) acc[k] |= __ldg(row + w);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int w = w0 + lane + 32 * k;
+          if (w < nw && acc[k]) atomicOr(&remv[w], acc[k]);
+        }
+      }
     }
     __syncthreads();
   }
+  int nkeep = s_nkeep;
   if (nkeep > OUT_CAP) nkeep = OUT_CAP;
   __syncthreads();
   if (threadIdx.x == 0) out_cnt[img] = nkeep;
@@ -486,7 +545,7 @@ extern "C" int ut2_fcos_predict_proposals(int num_levels, const int* hw, const i
   nms_sort_kernel<<<N, 1024, sort_smem, STREAM>>>((int)M, C, det_box, det_score, det_canon, det_cnt, 1, order, nms_box);
   const int nb = (int)((M + 63) / 64);
   nms_mask_kernel<<<dim3(nb, nb, N), 64, 0, STREAM>>>((int)M, (int)MW, nms_box, det_cnt, nms_thr, mask);
-  nms_scan_kernel<<<N, 128, (size_t)MW * 8, STREAM>>>(lv, N, C, (int)M, (int)MW, post_topk, out_cap, mask, order, det_box,
+  nms_scan_kernel<<<N, 256, (size_t)MW * 8, STREAM>>>(lv, N, C, (int)M, (int)MW, post_topk, out_cap, mask, order, det_box,
                                                       det_score, det_canon, det_cnt, static_cast<const bf16*>(cls_out),
                                                       static_cast<const bf16*>(box_out), ld, out_box, out_score, out_cls,
                                                       out_ctr, out_conf, out_std, out_loc, out_lvl, out_cnt);

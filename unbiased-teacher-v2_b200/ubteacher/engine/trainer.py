@@ -97,6 +97,7 @@ class UBTeacherTrainer:
         self.metrics_period = 20                        # PeriodicWriter period (trainer.py:551)
         self._metric_names, self._metric_buf = None, []
         self.last_losses = None
+        self.last_pseudo = None
         self.use_cuda_graph = False                     # enable_cuda_graph(): replay the whole semi-sup step
         self._graph = None
         self._static = None
@@ -274,6 +275,7 @@ class UBTeacherTrainer:
             pseudo_cls, _ = self.pseudo_generator.process_pseudo_label(pred_teacher, thr, "roih", ss.PSEUDO_BBOX_SAMPLE)
             pseudo_reg, _ = self.pseudo_generator.process_pseudo_label(pred_teacher_loc, thr_reg, "roih",
                                                                        ss.PSEUDO_BBOX_SAMPLE_REG)
+            self.last_pseudo = (pseudo_cls, pseudo_reg)          # device-resident; read by benchmarks / analysis only
             unlabel_data_q = self.remove_label(unlabel_data_q)
             unlabel_data_q = self.add_label(unlabel_data_q, pseudo_cls, "class")
             unlabel_data_q = self.add_label(unlabel_data_q, pseudo_reg, "reg")
@@ -400,6 +402,7 @@ class UBRCNNTeacherTrainer(UBTeacherTrainer):
             # teacher on the weak views; never switched to eval (trainer.py:830-837)
             _, proposals_rpn_unsup_k, proposals_roih_unsup_k, _ = self.model_teacher(unlabel_data_k, branch="unsup_data_weak")
             pseudo, _ = self.process_pseudo_label(proposals_roih_unsup_k, ss.BBOX_THRESHOLD, "roih", "thresholding")
+            self.last_pseudo = (pseudo,)
             unlabel_data_q = self.add_label(self.remove_label(unlabel_data_q), pseudo)
             unlabel_data_k = self.add_label(self.remove_label(unlabel_data_k), pseudo)
             lam, mu = ss.UNSUP_LOSS_WEIGHT, ss.UNSUP_REG_LOSS_WEIGHT
