@@ -95,6 +95,7 @@ collect_kernel(Levels lv, int N, int C, const bf16* __restrict__ cls_out, const 
 }
 
 // ---------------------------------------------------------------- 2. per-(image, level) top-k
+constexpr int TOPK_LIST = 4096;      // shared-memory capacity for the boundary bucket of the radix select
 __global__ void __launch_bounds__(1024)
 topk_kernel(Levels lv, int N, int C, int K, const float* __restrict__ cand_key, const int* __restrict__ cand_idx,
             const int* __restrict__ cand_cnt, float* __restrict__ sel_key, int* __restrict__ sel_idx,
@@ -107,19 +108,30 @@ topk_kernel(Levels lv, int N, int C, int K, const float* __restrict__ cand_key, 
   float* okey = sel_key + ((size_t)img * lv.num + l) * K;
   int* oidx = sel_idx + ((size_t)img * lv.num + l) * K;
   __shared__ unsigned int hist[256];
-  __shared__ unsigned int s_prefix, s_need, s_cnt;
+  __shared__ unsigned int s_prefix, s_need, s_cnt, s_m;
+  __shared__ unsigned int lkey[TOPK_LIST], lidx[TOPK_LIST];      // the boundary bucket, once it fits (see below)
   if (n <= K) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) { okey[i] = key[i]; oidx[i] = idx[i]; }
     if (threadIdx.x == 0) sel_cnt[img * lv.num + l] = n;
     return;
   }
-  // radix select on the (positive) float bits: find T with count(key > T) < K <= count(key >= T)
+  // Radix select on the (positive) float bits: find T with count(key > T) < K <= count(key >= T); `need` of the elements
+  // with key == T are taken, smallest idx first. A saturated level has > 10^6 candidates, so full passes are what costs:
+  // after the two passes over the top 16 key bits, one more pass writes everything above the boundary bucket straight to
+  // the output and moves the bucket itself (normally a few hundred elements) into shared memory, where the remaining five
+  // passes and the final gather run. If the bucket does not fit, the passes keep reading global memory as before.
+  const unsigned int* gkey = reinterpret_cast<const unsigned int*>(key);
+  const unsigned int* gidx = reinterpret_cast<const unsigned int*>(idx);
+  const unsigned int* skey = gkey;
+  const unsigned int* sidx = gidx;
+  int sn = n;
+  unsigned int out0 = 0;            // output slots already filled by the direct pass
   unsigned int prefix = 0, mask = 0, need = K;
   for (int pass = 3; pass >= 0; --pass) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned int k = __float_as_uint(key[i]);
+    for (int i = threadIdx.x; i < sn; i += blockDim.x) {
+      const unsigned int k = skey[i];
       if ((k & mask) == prefix) atomicAdd(&hist[(k >> (8 * pass)) & 255u], 1u);
     }
     __syncthreads();
@@ -132,21 +144,44 @@ topk_kernel(Levels lv, int N, int C, int K, const float* __restrict__ cand_key, 
       }
       s_prefix = prefix | ((unsigned int)b << (8 * pass));
       s_need = need - cum;
+      s_cnt = 0;
+      s_m = 0;
     }
     __syncthreads();
     prefix = s_prefix;
     need = s_need;
     mask |= 0xFFu << (8 * pass);
     __syncthreads();
+    if (pass == 2) {        // top 16 bits fixed: split the candidates (one pass over global memory)
+      for (int i = threadIdx.x; i < sn; i += blockDim.x) {
+        const unsigned int k = gkey[i], hi = k & mask;
+        if (hi > prefix) {
+          const unsigned int slot = atomicAdd(&s_cnt, 1u);
+          okey[slot] = __uint_as_float(k);
+          oidx[slot] = (int)gidx[i];
+        } else if (hi == prefix) {
+          const unsigned int slot = atomicAdd(&s_m, 1u);
+          if (slot < TOPK_LIST) { lkey[slot] = k; lidx[slot] = gidx[i]; }
+        }
+      }
+      __syncthreads();
+      if (s_m <= TOPK_LIST) {                 // uniform: continue on the shared-memory list
+        out0 = s_cnt;                          // == K - need
+        skey = lkey; sidx = lidx; sn = (int)s_m;
+      } else {
+        out0 = 0xFFFFFFFFu;                    // marker: the direct outputs are overwritten by the full gather below
+      }
+      __syncthreads();
+    }
   }
-  const unsigned int T = prefix;      // `need` of the elements with key == T are taken, smallest idx first
+  const unsigned int T = prefix;
   unsigned int prefix2 = 0, mask2 = 0, need2 = need;
   for (int pass = 2; pass >= 0; --pass) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      if (__float_as_uint(key[i]) != T) continue;
-      const unsigned int k = (unsigned int)idx[i];
+    for (int i = threadIdx.x; i < sn; i += blockDim.x) {
+      if (skey[i] != T) continue;
+      const unsigned int k = sidx[i];
       if ((k & mask2) == prefix2) atomicAdd(&hist[(k >> (8 * pass)) & 255u], 1u);
     }
     __syncthreads();
@@ -167,14 +202,14 @@ topk_kernel(Levels lv, int N, int C, int K, const float* __restrict__ cand_key, 
     __syncthreads();
   }
   const unsigned int idxT = prefix2;
-  if (threadIdx.x == 0) s_cnt = 0;
+  if (threadIdx.x == 0) s_cnt = (out0 == 0xFFFFFFFFu) ? 0u : out0;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const unsigned int k = __float_as_uint(key[i]);
-    const unsigned int id = (unsigned int)idx[i];
+  for (int i = threadIdx.x; i < sn; i += blockDim.x) {
+    const unsigned int k = skey[i];
+    const unsigned int id = sidx[i];
     if (k > T || (k == T && id <= idxT)) {
       const unsigned int slot = atomicAdd(&s_cnt, 1u);
-      if (slot < (unsigned int)K) { okey[slot] = key[i]; oidx[slot] = (int)id; }
+      if (slot < (unsigned int)K) { okey[slot] = __uint_as_float(k); oidx[slot] = (int)id; }
     }
   }
   if (threadIdx.x == 0) sel_cnt[img * lv.num + l] = K;
