@@ -98,6 +98,8 @@ class UBTeacherTrainer:
         self._metric_names, self._metric_buf = None, []
         self.last_losses = None
         self.last_pseudo = None
+        self._prefetched = None                         # next batch, when its H2D copy was started early (graph mode)
+        self._staged = None
         self.use_cuda_graph = False                     # enable_cuda_graph(): replay the whole semi-sup step
         self._graph = None
         self._static = None
@@ -180,7 +182,10 @@ class UBTeacherTrainer:
         assert self.model.training, "[UBTeacherTrainer] model was changed to eval mode!"
         ss = self.cfg.SEMISUPNET
         start = time.perf_counter()
-        data = next(self._data_loader_iter)
+        if self._prefetched is not None:             # fetched (and already on its way to the device) during the last step
+            data, self._prefetched = self._prefetched, None
+        else:
+            data = next(self._data_loader_iter)
         data_time = time.perf_counter() - start
         if self.use_cuda_graph and self.iter > ss.BURN_UP_STEP and self.optimizer.steps > 0 and \
                 (self.iter - ss.BURN_UP_STEP) % ss.TEACHER_UPDATE_ITER == 0:
@@ -222,8 +227,55 @@ class UBTeacherTrainer:
         st["gt"].counts.copy_(gt.counts, non_blocking=True)
         return st["data"]
 
+    def _prefetch_next(self):
+        """Called right after the graph launch of step i: fetch batch i+1 and, when it lives in (pinned) host memory, start
+        its host->device copies on a side stream into staging buffers so that they overlap step i's kernels; step i+1 then
+        only does device-to-device copies into the graph's static inputs. Device-resident batches are just fetched."""
+        from ..modeling.fcos.fcos_outputs import BoxSet, as_boxset
+        try:
+            data = next(self._data_loader_iter)
+        except StopIteration:
+            return
+        self._prefetched = data
+        lq, lk, uq, uk = data
+        imgs = [d["image"] for d in lq + lk + uq + uk]
+        if self._static is None or any(i.is_cuda for i in imgs) or \
+                [tuple(i.shape) for i in imgs] != self._static["shapes"][:-1]:
+            return
+        dev = self.model.device
+        if self._staged is None:
+            self._staged = {"imgs": [torch.empty_like(t) for t in self._static["imgs"]], "stream": torch.cuda.Stream(device=dev),
+                            "copied": torch.cuda.Event(), "consumed": torch.cuda.Event()}
+            self._staged["consumed"].record()
+        sg = self._staged
+        with torch.cuda.stream(sg["stream"]):
+            sg["stream"].wait_event(sg["consumed"])          # the previous staging contents were copied out
+            for dst, src in zip(sg["imgs"], imgs):
+                dst.copy_(src, non_blocking=True)
+            lab = lq + lk
+            gt = lab[0]["instances"] if isinstance(lab[0]["instances"], BoxSet) else as_boxset([d["instances"] for d in lab], dev)
+            sg["gt"] = gt
+            sg["copied"].record()
+        sg["for"] = data
+
+    def _stage_prefetched(self, data):
+        """Static inputs <- staging buffers (device to device) for a batch whose H2D copies were started by _prefetch_next."""
+        sg, st = self._staged, self._static
+        if sg is None or sg.get("for") is not data or tuple(sg["gt"].boxes.shape) != st["shapes"][-1]:
+            return None
+        sg["for"] = None
+        cur = torch.cuda.current_stream()
+        cur.wait_event(sg["copied"])
+        for dst, src in zip(st["imgs"], sg["imgs"]):
+            dst.copy_(src, non_blocking=True)
+        st["gt"].boxes.copy_(sg["gt"].boxes, non_blocking=True)
+        st["gt"].classes.copy_(sg["gt"].classes, non_blocking=True)
+        st["gt"].counts.copy_(sg["gt"].counts, non_blocking=True)
+        sg["consumed"].record()
+        return st["data"]
+
     def _graph_step(self, data, data_time):
-        static = self._stage_inputs(data)
+        static = self._stage_prefetched(data) or self._stage_inputs(data)
         if static is None:                      # a differently shaped batch: run it eagerly
             return self._step_body(data, data_time)
         self.optimizer.push_lr()
@@ -241,6 +293,7 @@ class UBTeacherTrainer:
             self._graph_names = self.last_losses[0]
             self._graph_vec = self.last_losses[1]
         self._graph.replay()
+        self._prefetch_next()
         from .. import _C
         _C.launch_count += self._graph_launches      # kernels inside the replayed graph
         self.optimizer.steps += 1
