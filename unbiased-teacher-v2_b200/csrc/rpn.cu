@@ -152,13 +152,16 @@ __device__ __forceinline__ unsigned long long sel_key(const uint32_t* keys, uint
   return ((unsigned long long)k << 32) | (uint32_t)a;
 }
 
+constexpr int SUB_LIST = 8192;      // shared-memory capacity for the boundary bucket of the sampling select
+
 __global__ void __launch_bounds__(1024)
 rpn_subsample_kernel(int A, int batch, int max_pos, const uint32_t* __restrict__ keys, uint32_t seed,
                      const uint32_t* __restrict__ seed_dev, const int* __restrict__ counts, signed char* __restrict__ labels) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned long long s_prefix;
   __shared__ unsigned int s_need;
-  __shared__ int s_done;
+  __shared__ int s_done, s_ln;
+  __shared__ unsigned int slist[SUB_LIST];
   const int img = blockIdx.x;
   if (seed_dev) seed += seed_dev[0] * 0x9E3779B1u;     // device-resident draw counter (CUDA-graph replay)
   signed char* lab = labels + (size_t)img * A;
@@ -177,13 +180,22 @@ rpn_subsample_kernel(int A, int batch, int max_pos, const uint32_t* __restrict__
     unsigned long long prefix = 0, mask = 0;
     unsigned int need = want;
     bool all_in_bucket = false;
+    bool listed = false;            // the boundary bucket lives in shared memory (anchor indices)
+    int ln = 0;
     for (int pass = 7; pass >= 0 && !all_in_bucket; --pass) {
       for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
       __syncthreads();
-      for (int a = threadIdx.x; a < A; a += blockDim.x) {
-        if (lab[a] != c) continue;
-        const unsigned long long k = sel_key(keys, seed, img, A, a);
-        if ((k & mask) == prefix) atomicAdd(&hist[(unsigned int)(k >> (8 * pass)) & 255u], 1u);
+      if (listed) {
+        for (int j = threadIdx.x; j < ln; j += blockDim.x) {
+          const unsigned long long k = sel_key(keys, seed, img, A, (int)slist[j]);
+          if ((k & mask) == prefix) atomicAdd(&hist[(unsigned int)(k >> (8 * pass)) & 255u], 1u);
+        }
+      } else {
+        for (int a = threadIdx.x; a < A; a += blockDim.x) {
+          if (lab[a] != c) continue;
+          const unsigned long long k = sel_key(keys, seed, img, A, a);
+          if ((k & mask) == prefix) atomicAdd(&hist[(unsigned int)(k >> (8 * pass)) & 255u], 1u);
+        }
       }
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -196,6 +208,7 @@ rpn_subsample_kernel(int A, int batch, int max_pos, const uint32_t* __restrict__
         s_prefix = prefix | ((unsigned long long)b << (8 * pass));
         s_need = need - cum;
         s_done = (need - cum) == hist[b];
+        s_ln = 0;
       }
       __syncthreads();
       prefix = s_prefix;
@@ -203,6 +216,35 @@ rpn_subsample_kernel(int A, int batch, int max_pos, const uint32_t* __restrict__
       mask |= 0xFFull << (8 * pass);
       all_in_bucket = s_done != 0;
       __syncthreads();
+      if (pass == 7 && !all_in_bucket) {
+        // One scan settles everything outside the boundary bucket (keys are uniform hashes: the bucket holds ~1/256 of
+        // the class) and moves the bucket into shared memory; the remaining passes then run on ~10^3 instead of
+        // 268 569 anchors. If the bucket does not fit, the passes keep scanning the labels.
+        for (int a = threadIdx.x; a < A; a += blockDim.x) {
+          if (lab[a] != c) continue;
+          const unsigned long long k = sel_key(keys, seed, img, A, a) & mask;
+          if (k > prefix) {
+            lab[a] = -1;                                  // above the bucket: never selected
+          } else if (k == prefix) {
+            const int t = atomicAdd(&s_ln, 1);
+            if (t < SUB_LIST) slist[t] = (unsigned int)a;
+          }
+        }
+        __syncthreads();
+        if (s_ln <= SUB_LIST) {
+          listed = true;
+          ln = s_ln;
+        }
+        __syncthreads();
+      }
+    }
+    if (listed) {         // inside the bucket: drop the keys above the final prefix
+      for (int j = threadIdx.x; j < ln; j += blockDim.x) {
+        const int a = (int)slist[j];
+        if ((sel_key(keys, seed, img, A, a) & mask) > prefix) lab[a] = -1;
+      }
+      __syncthreads();
+      continue;
     }
     // selected: (k & mask) < prefix, or (k & mask) == prefix (the whole remaining bucket is taken)
     for (int a = threadIdx.x; a < A; a += blockDim.x) {
@@ -332,6 +374,36 @@ __device__ __forceinline__ unsigned int bf2ord(unsigned short u) {
   return (u & 0x8000u) ? (unsigned int)((~u) & 0xFFFFu) : (unsigned int)(u | 0x8000u);
 }
 
+constexpr unsigned int TIE_CAP = 8192;      // shared-memory list of the anchors whose logit equals the top-k threshold
+
+// [D2] Box2BoxTransform.apply_deltas (weights 1, dw / dh clamped) + clip to the image; invalid boxes get score -inf
+__device__ __forceinline__ void emit_candidate(const RpnLevels& lv, int l, int N, int img, int HW, int hw, int k, unsigned short raw,
+                                               const bf16* __restrict__ rpn_out, float ih, float iw, float scale_clamp, size_t o,
+                                               float* __restrict__ cand_box, float* __restrict__ cand_score,
+                                               int* __restrict__ cand_canon, int* __restrict__ cand_lvl) {
+  const bf16* row = rpn_out + ((size_t)lv.off[l] * N + (size_t)img * HW + hw) * LD;
+  const int h = hw / lv.W[l], w = hw - h * lv.W[l];
+  const float sx = (float)(w * lv.stride[l]), sy = (float)(h * lv.stride[l]);
+  const float ax1 = sx + lv.cell[l][k][0], ay1 = sy + lv.cell[l][k][1];
+  const float ax2 = sx + lv.cell[l][k][2], ay2 = sy + lv.cell[l][k][3];
+  const float aw = ax2 - ax1, ah = ay2 - ay1;
+  const float cx = ax1 + 0.5f * aw, cy = ay1 + 0.5f * ah;
+  const float dx = bf(row + 3 + 4 * k), dy = bf(row + 4 + 4 * k);
+  const float dw = fminf(bf(row + 5 + 4 * k), scale_clamp), dh = fminf(bf(row + 6 + 4 * k), scale_clamp);
+  const float pcx = dx * aw + cx, pcy = dy * ah + cy;
+  const float pw = expf(dw) * aw, ph = expf(dh) * ah;
+  float x1 = pcx - 0.5f * pw, y1 = pcy - 0.5f * ph, x2 = pcx + 0.5f * pw, y2 = pcy + 0.5f * ph;
+  const float score = __uint_as_float((unsigned int)raw << 16);
+  bool valid = isfinite(x1) && isfinite(y1) && isfinite(x2) && isfinite(y2) && isfinite(score);
+  x1 = fminf(fmaxf(x1, 0.f), iw); x2 = fminf(fmaxf(x2, 0.f), iw);
+  y1 = fminf(fmaxf(y1, 0.f), ih); y2 = fminf(fmaxf(y2, 0.f), ih);
+  valid = valid && (x2 - x1 > 0.f) && (y2 - y1 > 0.f);
+  reinterpret_cast<float4*>(cand_box)[o] = make_float4(x1, y1, x2, y2);
+  cand_score[o] = valid ? score : -INFINITY;
+  cand_canon[o] = (lv.off[l] + hw) * NA + k;
+  cand_lvl[o] = l;
+}
+
 __global__ void __launch_bounds__(1024)
 rpn_select_decode_kernel(RpnLevels lv, int N, int K, int Mcap, const bf16* __restrict__ rpn_out,
                          const float* __restrict__ image_hw, float scale_clamp, float* __restrict__ cand_box,
@@ -341,7 +413,8 @@ rpn_select_decode_kernel(RpnLevels lv, int N, int K, int Mcap, const bf16* __res
   const int n = HW * NA;
   const unsigned short* base = reinterpret_cast<const unsigned short*>(rpn_out) + ((size_t)lv.off[l] * N + (size_t)img * HW) * LD;
   __shared__ unsigned int hist[256];
-  __shared__ unsigned int s_prefix, s_need, s_cnt;
+  __shared__ unsigned int s_prefix, s_need, s_cnt, s_ties;
+  __shared__ unsigned int ties[TIE_CAP];
   int slot0 = 0;                                  // first output slot of this level: sum of min(HW_i * NA, K)
   for (int i = 0; i < l; ++i) slot0 += min(lv.H[i] * lv.W[i] * NA, K);
   const int take = min(n, K);
@@ -373,13 +446,41 @@ rpn_select_decode_kernel(RpnLevels lv, int N, int K, int Mcap, const bf16* __res
       __syncthreads();
     }
     T = prefix;
-    unsigned int prefix2 = 0, mask2 = 0, need2 = need;      // `need` of the elements with key == T: smallest index first
+    // `need` of the elements with key == T are taken, smallest index first. One scan emits everything above T and moves
+    // the indices of the ties into shared memory; when they fit (bf16 logits tie by the hundreds, not by the tens of
+    // thousands), the three index passes and the emission of the chosen ties run on that list instead of on the whole
+    // level (3 instead of 6 full scans of up to 201 600 anchors by one CTA).
+    if (threadIdx.x == 0) { s_cnt = 0; s_ties = 0; }
+    __syncthreads();
+    const float ih0 = image_hw[img * 2], iw0 = image_hw[img * 2 + 1];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int hw = i / NA, k = i - hw * NA;
+      const unsigned short raw = base[(size_t)hw * LD + k];
+      const unsigned int key = bf2ord(raw);
+      if (key > T) {
+        const unsigned int slot = atomicAdd(&s_cnt, 1u);
+        emit_candidate(lv, l, N, img, HW, hw, k, raw, rpn_out, ih0, iw0, scale_clamp, (size_t)img * Mcap + slot0 + slot, cand_box,
+                       cand_score, cand_canon, cand_lvl);
+      } else if (key == T) {
+        const unsigned int t = atomicAdd(&s_ties, 1u);
+        if (t < TIE_CAP) ties[t] = (unsigned int)i;
+      }
+    }
+    __syncthreads();
+    const bool listed = s_ties <= TIE_CAP;
+    const int nt = listed ? (int)s_ties : n;
+    unsigned int prefix2 = 0, mask2 = 0, need2 = need;
     for (int pass = 2; pass >= 0; --pass) {
       for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
       __syncthreads();
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        if (bf2ord(base[(size_t)(i / NA) * LD + (i % NA)]) != T) continue;
-        const unsigned int k = (unsigned int)i;
+      for (int j = threadIdx.x; j < nt; j += blockDim.x) {
+        unsigned int k;
+        if (listed) {
+          k = ties[j];
+        } else {
+          if (bf2ord(base[(size_t)(j / NA) * LD + (j % NA)]) != T) continue;
+          k = (unsigned int)j;
+        }
         if ((k & mask2) == prefix2) atomicAdd(&hist[(k >> (8 * pass)) & 255u], 1u);
       }
       __syncthreads();
@@ -400,41 +501,30 @@ rpn_select_decode_kernel(RpnLevels lv, int N, int K, int Mcap, const bf16* __res
       __syncthreads();
     }
     idxT = prefix2;
+    // the chosen ties (index <= idxT)
+    for (int j = threadIdx.x; j < nt; j += blockDim.x) {
+      int i;
+      if (listed) {
+        i = (int)ties[j];
+      } else {
+        if (bf2ord(base[(size_t)(j / NA) * LD + (j % NA)]) != T) continue;
+        i = j;
+      }
+      if ((unsigned int)i > idxT) continue;
+      const int hw = i / NA, k = i - hw * NA;
+      const unsigned int slot = atomicAdd(&s_cnt, 1u);
+      if (slot >= (unsigned int)take) continue;
+      emit_candidate(lv, l, N, img, HW, hw, k, base[(size_t)hw * LD + k], rpn_out, ih0, iw0, scale_clamp,
+                     (size_t)img * Mcap + slot0 + slot, cand_box, cand_score, cand_canon, cand_lvl);
+    }
+    return;
   }
-  if (threadIdx.x == 0) s_cnt = 0;
-  __syncthreads();
+  // n <= K: every anchor of the level is a candidate
   const float ih = image_hw[img * 2], iw = image_hw[img * 2 + 1];
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int hw = i / NA, k = i - hw * NA;
-    const unsigned short raw = base[(size_t)hw * LD + k];
-    if (n > K) {
-      const unsigned int key = bf2ord(raw);
-      if (!(key > T || (key == T && (unsigned int)i <= idxT))) continue;
-    }
-    const unsigned int slot = atomicAdd(&s_cnt, 1u);
-    if (slot >= (unsigned int)take) continue;
-    const bf16* row = rpn_out + ((size_t)lv.off[l] * N + (size_t)img * HW + hw) * LD;
-    const int h = hw / lv.W[l], w = hw - h * lv.W[l];
-    const float sx = (float)(w * lv.stride[l]), sy = (float)(h * lv.stride[l]);
-    const float ax1 = sx + lv.cell[l][k][0], ay1 = sy + lv.cell[l][k][1];
-    const float ax2 = sx + lv.cell[l][k][2], ay2 = sy + lv.cell[l][k][3];
-    const float aw = ax2 - ax1, ah = ay2 - ay1;
-    const float cx = ax1 + 0.5f * aw, cy = ay1 + 0.5f * ah;
-    const float dx = bf(row + 3 + 4 * k), dy = bf(row + 4 + 4 * k);
-    const float dw = fminf(bf(row + 5 + 4 * k), scale_clamp), dh = fminf(bf(row + 6 + 4 * k), scale_clamp);
-    const float pcx = dx * aw + cx, pcy = dy * ah + cy;
-    const float pw = expf(dw) * aw, ph = expf(dh) * ah;
-    float x1 = pcx - 0.5f * pw, y1 = pcy - 0.5f * ph, x2 = pcx + 0.5f * pw, y2 = pcy + 0.5f * ph;
-    const float score = __uint_as_float((unsigned int)raw << 16);
-    bool valid = isfinite(x1) && isfinite(y1) && isfinite(x2) && isfinite(y2) && isfinite(score);
-    x1 = fminf(fmaxf(x1, 0.f), iw); x2 = fminf(fmaxf(x2, 0.f), iw);
-    y1 = fminf(fmaxf(y1, 0.f), ih); y2 = fminf(fmaxf(y2, 0.f), ih);
-    valid = valid && (x2 - x1 > 0.f) && (y2 - y1 > 0.f);
-    const size_t o = (size_t)img * Mcap + slot0 + slot;
-    reinterpret_cast<float4*>(cand_box)[o] = make_float4(x1, y1, x2, y2);
-    cand_score[o] = valid ? score : -INFINITY;
-    cand_canon[o] = (lv.off[l] + hw) * NA + k;
-    cand_lvl[o] = l;
+    emit_candidate(lv, l, N, img, HW, hw, k, base[(size_t)hw * LD + k], rpn_out, ih, iw, scale_clamp, (size_t)img * Mcap + slot0 + i,
+                   cand_box, cand_score, cand_canon, cand_lvl);
   }
 }
 
