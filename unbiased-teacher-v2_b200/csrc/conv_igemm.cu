@@ -608,7 +608,7 @@ static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, 
                            int res_up2, const void* relu_mask, int relu, void* y, void* stream) {
   if (!x || !w || !y) return ut2_fail(-1, "conv_fwd: null pointer");
   if (Cin % 8 || Cin <= 0) return ut2_fail(-2, "conv_fwd: Cin must be a multiple of 8");
-  const int block_n = pick_block_n(Cout);
+  int block_n = pick_block_n(Cout);
   if (block_n < 0) return ut2_fail(-3, "conv_fwd: unsupported Cout (need %16==0; >256 needs %128==0)");
   if (stride < 1 || stride > 8 || pad < 0 || R < 1 || S < 1) return ut2_fail(-4, "conv_fwd: bad geometry");
   if (num_levels < 1 || num_levels > MAX_LV) return ut2_fail(-4, "conv_fwd: 1..5 levels");
@@ -637,6 +637,16 @@ static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, 
       if (l + 1 <= MAX_LV) a.lt.tile_off[l + 1] = a.lt.tile_off[l];
       tx.m[l] = tx.m[ll];
     }
+  }
+  // Under-filled grids (small batches, the deep trunk / top pyramid levels: fewer tiles than half the SMs): narrower tiles
+  // put more SMs to work; the A tiles they re-read come from L2. UT2_NARROW=0 disables (A/B runs).
+  {
+    static int narrow_on = -1;
+    if (narrow_on < 0) { const char* e = getenv("UT2_NARROW"); narrow_on = e ? atoi(e) : 1; }
+    const int m_tiles = a.lt.tile_off[num_levels];
+    while (narrow_on && block_n >= 128 && block_n % 32 == 0 && Cout % (block_n / 2) == 0 &&
+           m_tiles * ((Cout + block_n - 1) / block_n) * 2 <= num_sms())
+      block_n /= 2;
   }
   const int P = a.lt.P[0], Q = a.lt.Q[0];
   a.M = (int)out_rows; a.Cout = Cout; a.ldo = Cout;
