@@ -8,6 +8,7 @@
 #include "ut2_internal.h"
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace {
 typedef __nv_bfloat16 bf16;
@@ -284,20 +285,27 @@ gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, con
   }
 }
 
+static int gn_min_px() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("UT2_GN_MINPX"); v = e ? atoi(e) : 256; if (v < 8) v = 8; }
+  return v;
+}
+
 inline int fill_gn_levels(GnLevels& lv, int num_levels, const int* hws, int N) {
   if (num_levels < 1 || num_levels > GN_MAXL) return -1;
   lv.num = num_levels;
   lv.N = N;
   long long total = 0;
   for (int l = 0; l < num_levels; ++l) total += hws[l];
-  // aim for ~148*4 blocks in total, spread over the levels by size, at least 64 pixels each
+  // aim for ~148*4 blocks in total, spread over the levels by size, at least 256 pixels each (UT2_GN_MINPX): every block ends
+  // in ~500 fp32 / fp64 atomics on the same few addresses, which dominates small batches when the blocks are short
   const long long target = (total * N + 148 * 4 - 1) / (148 * 4);
   int row = 0;
   lv.blk_off[0] = 0;
   for (int l = 0; l < GN_MAXL; ++l) {
     if (l < num_levels) {
       const int HW = hws[l];
-      int ppb = (int)(target < 64 ? 64 : target);
+      int ppb = (int)(target < gn_min_px() ? gn_min_px() : target);
       ppb = (ppb + GN_ROWS - 1) / GN_ROWS * GN_ROWS;
       lv.HW[l] = HW; lv.row_off[l] = row; lv.ppb[l] = ppb; lv.bpi[l] = (HW + ppb - 1) / ppb;
       lv.blk_off[l + 1] = lv.blk_off[l] + lv.bpi[l] * N;
