@@ -165,6 +165,14 @@ long long ut2_nms_workspace_bytes(int N, int M);
 int ut2_nms_batched(int N, int M, const float* boxes, const float* scores, const int* tie, const int* cls, const int* cnt,
                     float thr, int trick_limit, int max_keep, void* workspace, long long workspace_bytes, int* keep_idx,
                     int* keep_cnt, void* stream);
+/* the same for candidate lists laid out class by class — the RPN's level-by-level list ([D2] find_top_rpn_proposals, idxs =
+ * FPN level): seg_off = HOST array of S + 1 slot offsets inside every image's M slots (S <= 8, segments <= 2048 slots, all
+ * slots candidates; non-finite scores dropped). Each (image, segment) is sorted / masked / scanned on its own and the
+ * survivors merged by (score desc, tie asc): identical keep list to ut2_nms_batched with cls = segment index. */
+long long ut2_nms_segmented_workspace_bytes(int N, int S, int Mseg, int max_keep);
+int ut2_nms_segmented(int N, int M, int S, const int* seg_off, const float* boxes, const float* scores, const int* tie, float thr,
+                      int trick_limit, int max_keep, void* workspace, long long workspace_bytes, int* keep_idx, int* keep_cnt,
+                      void* stream);
 /* dst[img,k,:] = src[img, idx[img,k], :] for k < cnt[img], else 0; rows of W elements of elem_bytes (4 | 8) */
 int ut2_gather_rows(int N, int M, int K, int W, int elem_bytes, const void* src, const int* idx, const int* cnt, void* dst,
                     void* stream);

@@ -441,3 +441,35 @@ def test_helpers():
     x = rb(torch.randn(2, 25, 42, 32, generator=g))
     y = R.subsample2x(x.bfloat16().cuda())
     assert torch.equal(y.float().cpu(), x[:, ::2, ::2])
+
+
+@pytest.mark.parametrize("trick_limit", [20000, 100])
+def test_nms_segmented_equals_joint_nms(trick_limit):
+    """Per-(image, level) NMS + merge == the joint batched NMS with idxs = level (both torchvision strategies: coordinate
+    trick for small calls, per class otherwise), including -inf scores, an empty segment and a max_keep that cuts."""
+    from ubteacher import ops_rcnn as R
+    g = torch.Generator().manual_seed(31)
+    N, seg_sizes = 3, [700, 300, 0, 90, 17]
+    seg_off = [0]
+    for n in seg_sizes:
+        seg_off.append(seg_off[-1] + n)
+    M = seg_off[-1] + 5                       # a few unused slots after the last segment
+    ctr = torch.rand(N, M, 2, generator=g) * 300
+    wh = torch.rand(N, M, 2, generator=g) * 120 + 4
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], dim=-1)
+    scores = torch.randn(N, M, generator=g)
+    scores[:, ::7] = scores[:, 3:4]           # ties across and inside segments
+    scores[0, 5:40] = float("-inf")
+    lvl = torch.zeros(N, M, dtype=torch.int32)
+    for s in range(len(seg_sizes)):
+        lvl[:, seg_off[s]:seg_off[s + 1]] = s
+    tie = torch.stack([torch.randperm(M, generator=g) for _ in range(N)]).to(torch.int32)
+    cnt = torch.full((N,), seg_off[-1], dtype=torch.int32)
+    for max_keep in (1000, 60):
+        k_ref, c_ref = R.nms_batched(boxes.cuda(), scores.cuda(), lvl.cuda(), cnt.cuda(), 0.7, max_keep, tie=tie.cuda(), trick_limit=trick_limit)
+        k_seg, c_seg = R.nms_segmented(boxes.cuda(), scores.cuda(), tie.cuda(), seg_off, 0.7, max_keep, trick_limit=trick_limit)
+        torch.cuda.synchronize()
+        assert torch.equal(c_ref, c_seg), (c_ref, c_seg)
+        for i in range(N):
+            n = int(c_ref[i])
+            assert torch.equal(k_ref[i, :n], k_seg[i, :n]), (i, max_keep)

@@ -329,9 +329,15 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr
   const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
   const float width = fmaxf(right - left, 0.f), height = fmaxf(bottom - top, 0.f);
   const float inter = __fmul_rn(width, height);
+  if (!(inter > 0.f)) return false;
   const float sa = __fmul_rn(a.z - a.x, a.w - a.y);
   const float sb = __fmul_rn(b.z - b.x, b.w - b.y);
-  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter)) > thr;
+  const float uni = __fsub_rn(__fadd_rn(sa, sb), inter);
+  // The exact fp32 division only decides pairs within 1e-4 of the threshold; disjoint boxes (IoU 0) and clear cases are
+  // settled by the multiplication test, which cannot disagree with RN(inter / union) > thr outside that band.
+  const float d = inter - thr * uni;
+  if (fabsf(d) > 1e-4f * fabsf(uni)) return d > 0.f && uni > 0.f;
+  return __fdiv_rn(inter, uni) > thr;
 }
 
 // mask[img][i][cb] bit j: sorted box i suppresses sorted box cb*64+j (only j > i matters)

@@ -63,6 +63,24 @@ def nms_batched(boxes, scores, cls, cnt, thr, max_keep, tie=None, trick_limit=20
     return keep, kcnt
 
 
+def nms_segmented(boxes, scores, tie, seg_off, thr, max_keep, trick_limit=20000):
+    """Per-segment NMS + merge (csrc/nms.cu, ut2_nms_segmented): boxes [N,M,4], scores [N,M], tie [N,M] i32 | None, seg_off:
+    list of S+1 slot offsets -> keep_idx [N,max_keep] i32 (slots in the image's list), keep_cnt [N]."""
+    N, M = scores.shape
+    dev = scores.device
+    S = len(seg_off) - 1
+    mseg = max(max(seg_off[i + 1] - seg_off[i] for i in range(S)), 1)
+    fn = _lib_ll("ut2_nms_segmented_workspace_bytes")
+    wsb = fn(N, S, mseg, max_keep)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    keep = torch.empty((N, max_keep), dtype=torch.int32, device=dev)
+    kcnt = torch.empty(N, dtype=torch.int32, device=dev)
+    c_off = (ctypes.c_int * (S + 1))(*seg_off)
+    _C.counted_call("ut2_nms_segmented", N, M, S, c_off, boxes, scores, tie, f32(thr), trick_limit, max_keep, ws, i64(wsb), keep, kcnt)
+    _C.launch_count += 4
+    return keep, kcnt
+
+
 def gather_rows(src, idx, cnt, width):
     """src [N,M,width] (4- or 8-byte elements) -> [N,K,width] gathered by idx [N,K] (zero beyond cnt)."""
     N, K = idx.shape
@@ -116,10 +134,16 @@ def rpn_select_decode(geom, N, rpn_out, image_hw, pre_topk):
     return out
 
 
-def rpn_predict_proposals(geom, N, rpn_out, image_hw, pre_topk=2000, post_topk=1000, nms_thr=0.7):
+def rpn_predict_proposals(geom, N, rpn_out, image_hw, pre_topk=2000, post_topk=1000, nms_thr=0.7, segmented=True):
     """[D2] find_top_rpn_proposals: -> proposal_boxes [N,post_topk,4], objectness_logits [N,post_topk], count [N]."""
     c = rpn_select_decode(geom, N, rpn_out, image_hw, pre_topk)
-    keep, kcnt = nms_batched(c["boxes"], c["scores"], c["levels"], c["count"], nms_thr, post_topk, tie=c["canon"])
+    seg_off = [0]
+    for h, w in geom.hw:                    # the candidate list is laid out level by level (rpn_select_decode)
+        seg_off.append(seg_off[-1] + min(3 * h * w, pre_topk))
+    if segmented and pre_topk <= 2048 and len(geom.hw) <= 8:
+        keep, kcnt = nms_segmented(c["boxes"], c["scores"], c["canon"], seg_off, nms_thr, post_topk)
+    else:
+        keep, kcnt = nms_batched(c["boxes"], c["scores"], c["levels"], c["count"], nms_thr, post_topk, tie=c["canon"])
     return {"proposal_boxes": gather_rows(c["boxes"], keep, kcnt, 4),
             "objectness_logits": gather_rows(c["scores"].unsqueeze(-1), keep, kcnt, 1).squeeze(-1), "count": kcnt}
 
