@@ -35,6 +35,27 @@ for _ in range(iters):
     aug(imgs, params=params)
 e1.record(); torch.cuda.synchronize()
 print(f"device, fixed parameters: {B * iters / (e0.elapsed_time(e1) / 1e3):9.1f} images/s")
+# two-crop mapper: decoded 480x640 uint8 HWC images on the host -> (strong, weak) views on the device
+try:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util_cfg import fcos_cfg
+    from ubteacher.data.dataset_mapper import DatasetMapperTwoCropSeparate
+    cfg = fcos_cfg(**{"MODEL.DEVICE": "cuda"})
+    mapper = DatasetMapperTwoCropSeparate(cfg, True)
+    gh = np.random.default_rng(0)
+    dicts = [{"image": torch.from_numpy(gh.integers(0, 256, (480, 640, 3), dtype=np.uint8)).pin_memory(),
+              "annotations": [{"bbox": [10.0, 20.0, 300.0, 400.0], "category_id": 1, "iscrowd": 0}]} for _ in range(B)]
+    for _ in range(2):
+        mapper(dicts)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        mapper(dicts)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(f"two-crop mapper (480x640 -> shortest edge in [400, 1200], H2D + resize/flip + strong aug): {B * 10 / dt:9.1f} images/s (host wall)")
+except Exception as e:  # noqa: BLE001
+    print("mapper bench failed:", repr(e))
 try:
     from PIL import Image
     import torchvision.transforms as T

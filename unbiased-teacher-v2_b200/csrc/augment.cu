@@ -89,6 +89,12 @@ __device__ __forceinline__ void hue_px(unsigned int& r, unsigned int& g, unsigne
 __global__ void __launch_bounds__(256) aug_copy_kernel(const AugImage* __restrict__ tab) {
   const AugImage& im = tab[blockIdx.y];
   const size_t n = (size_t)3 * im.h * im.w;
+  if ((n & 15) == 0 && ((reinterpret_cast<uintptr_t>(im.dst) | reinterpret_cast<uintptr_t>(im.src)) & 15) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(im.src);
+    uint4* d4 = reinterpret_cast<uint4*>(im.dst);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (n >> 4); i += (size_t)gridDim.x * blockDim.x) d4[i] = s4[i];
+    return;
+  }
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) im.dst[i] = im.src[i];
 }
 
@@ -115,14 +121,33 @@ __global__ void __launch_bounds__(256) aug_color_kernel(const AugImage* __restri
   int mean = 0;
   if (op == 1) mean = (int)((double)lsum[blockIdx.y * 4 + slot] / (double)hw + 0.5);      // ImageStat mean, int(m + 0.5)
   uint8_t* c0 = im.dst; uint8_t* c1 = im.dst + hw; uint8_t* c2 = im.dst + 2 * hw;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
-    unsigned int r = c0[i], g = c1[i], b = c2[i];
+  auto px = [&](unsigned int& r, unsigned int& g, unsigned int& b) {
     if (op == 3) {
       hue_px(r, g, b, (unsigned int)im.hue_shift);
     } else {
       const int d = op == 0 ? 0 : (op == 1 ? mean : (int)luma(r, g, b));
       r = blend1(d, (int)r, f, interp); g = blend1(d, (int)g, f, interp); b = blend1(d, (int)b, f, interp);
     }
+  };
+  if ((hw & 3) == 0 && (reinterpret_cast<uintptr_t>(im.dst) & 3) == 0) {      // 4 pixels per thread: 32-bit plane accesses
+    const size_t n4 = hw >> 2;
+    uint32_t* p0 = reinterpret_cast<uint32_t*>(c0); uint32_t* p1 = reinterpret_cast<uint32_t*>(c1); uint32_t* p2 = reinterpret_cast<uint32_t*>(c2);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+      const uint32_t wr = p0[i], wg = p1[i], wb = p2[i];
+      uint32_t orr = 0, og = 0, ob = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        unsigned int r = (wr >> (8 * k)) & 255u, g = (wg >> (8 * k)) & 255u, b = (wb >> (8 * k)) & 255u;
+        px(r, g, b);
+        orr |= r << (8 * k); og |= g << (8 * k); ob |= b << (8 * k);
+      }
+      p0[i] = orr; p1[i] = og; p2[i] = ob;
+    }
+    return;
+  }
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned int r = c0[i], g = c1[i], b = c2[i];
+    px(r, g, b);
     c0[i] = (uint8_t)r; c1[i] = (uint8_t)g; c2[i] = (uint8_t)b;
   }
 }
