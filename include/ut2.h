@@ -247,7 +247,8 @@ int ut2_subsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, voi
  *   i32 h, w; i32 order[4] (ColorJitter op per slot: 0 brightness 1 contrast 2 saturation 3 hue, -1 none);
  *   f32 factor[4] (indexed by op); i32 hue_shift (uint8(int32(hue*255))), gray, blur_r (< 0: no blur);
  *   u32 blur_ww, blur_fw (Pillow box-blur fixed-point weights); i32 n_erase; i32 ei[3], ej[3], eh[3], ew[3]; u32 seed; i32 pad.
- * lsum_ws: device uint64 [N,4] scratch. max_pixels = max h*w, max_erase = max n_erase over the batch. */
+ * lsum_ws: device uint64 [N,4] scratch. max_pixels = max h*w, max_erase = max n_erase over the batch (+ 256 when some
+ * image has blur_r > 2: the three box passes per direction then run unfused for it). */
 int ut2_strong_augment_u8(const void* table, int N, int max_pixels, int max_erase, unsigned long long* lsum_ws, void* stream);
 
 /* weak augmentation (dataset_mapper.py:88-91 -> [D2] ResizeShortestEdge + RandomFlip): Pillow Image.resize(BILINEAR) bit for

@@ -162,3 +162,18 @@ def test_two_crop_mapper_matches_oracle():
             assert view["instances"].image_size == (nh, nw) and view["height"] == h and view["width"] == w and view["image_id"] == i
             assert np.array_equal(view["instances"].gt_boxes.tensor.numpy(), boxes[keep])
             assert view["instances"].gt_classes.tolist() == [i, 3]
+
+
+@pytest.mark.parametrize("size", [(70, 90), (33, 500), (300, 40), (5, 7)])
+def test_gaussian_blur_fused_and_general_paths(size):
+    """Box radius 0 / 1 / 2 take the fused three-pass kernels (row segments of 224 and column strips of 32 x 64 with halos
+    and edge replication per pass), larger radii the pass-by-pass kernels; all equal Pillow's GaussianBlur (oracle)."""
+    from oracle import ut2_aug_oracle as A
+    from ubteacher.data.gpu_augmentation import GpuStrongAugmentation, box_blur_params
+    img = rand_img(31, *size)
+    radii = [0.1, 0.9, 2.0, 3.0, 3.4, 6.0, 9.5]
+    assert sorted({box_blur_params(r)[0] for r in radii}) == [0, 1, 2, 5, 9]
+    params = [{"jitter": None, "gray": False, "blur": r, "erase": []} for r in radii]
+    outs = GpuStrongAugmentation()([to_dev(img) for _ in radii], params=params)
+    for r, o in zip(radii, outs):
+        assert np.array_equal(to_host(o), A.gaussian_blur(img, r)), (size, r)

@@ -162,11 +162,13 @@ __global__ void __launch_bounds__(256) aug_gray_kernel(const AugImage* __restric
   }
 }
 
+constexpr int BOX_FUSED_R_FWD = 2;      // == BOX_FUSED_R (defined with the fused kernels below)
+
 // One extended-box-blur pass (libImaging/BoxBlur.c): out = (ww * sum_{|k|<=r} in[x+k] + fw * (in[x-r-1] + in[x+r+1]) +
 // 2^23) >> 24 with replicated edges, along x (vertical = 0) or y (vertical = 1). pass parity picks the ping-pong side.
 __global__ void __launch_bounds__(256) aug_box_kernel(const AugImage* __restrict__ tab, int pass, int vertical) {
   const AugImage& im = tab[blockIdx.y];
-  if (im.blur_r < 0) return;
+  if (im.blur_r <= BOX_FUSED_R_FWD) return;    // radii <= 2 (every radius the reference draws) take the fused kernels below
   const uint8_t* in = (pass & 1) ? im.tmp : im.dst;
   uint8_t* out = (pass & 1) ? im.dst : im.tmp;
   const int h = im.h, w = im.w, r = im.blur_r;
@@ -182,6 +184,92 @@ __global__ void __launch_bounds__(256) aug_box_kernel(const AugImage* __restrict
     for (int k = -r; k <= r; ++k) acc += line[(size_t)min(max(pos + k, 0), len - 1) * stride];
     const unsigned long long far = (unsigned long long)line[(size_t)max(pos - r - 1, 0) * stride] + line[(size_t)min(pos + r + 1, len - 1) * stride];
     out[i] = (uint8_t)((acc * ww + far * fw + (1ull << 23)) >> 24);
+  }
+}
+
+// The three passes of one direction in ONE kernel (box radius <= 2, i.e. every Gaussian radius up to ~3.5): a row segment /
+// column strip plus a halo of 3 * (r + 1) pixels is staged in shared memory, blurred three times there (uint8 between the
+// passes, like Pillow) and written once: 2 instead of 6 bytes moved per pixel, channel and direction. Pillow replicates
+// the edge pixel of the CURRENT pass, so after every pass the out-of-image part of the halo is refilled from the freshly
+// blurred border pixel.
+constexpr int BOX_FUSED_R = 2;
+constexpr int BXH_SEG = 224;                    // output pixels per row segment (224 + 2 * 9 <= 256 threads)
+constexpr int BXV_TH = 32, BXV_TW = 64;         // rows x columns per strip tile
+
+__device__ __forceinline__ uint8_t box_tap(const uint8_t* b, int t, int stride, int r, unsigned long long ww, unsigned long long fw) {
+  unsigned long long acc = 0;
+  for (int k = -r; k <= r; ++k) acc += b[(t + k) * stride];
+  const unsigned long long far = (unsigned long long)b[(t - r - 1) * stride] + b[(t + r + 1) * stride];
+  return (uint8_t)((acc * ww + far * fw + (1ull << 23)) >> 24);
+}
+
+// horizontal: dst -> tmp
+__global__ void __launch_bounds__(256) aug_box3_h_kernel(const AugImage* __restrict__ tab) {
+  const AugImage& im = tab[blockIdx.y];
+  if (im.blur_r < 0 || im.blur_r > BOX_FUSED_R) return;
+  __shared__ uint8_t buf[2][256];
+  const int r = im.blur_r, halo = 3 * (r + 1), L = BXH_SEG + 2 * halo, w = im.w;
+  const unsigned long long ww = im.blur_ww, fw = im.blur_fw;
+  const int nseg = (w + BXH_SEG - 1) / BXH_SEG;
+  const long long items = 3ll * im.h * nseg;
+  const int t = threadIdx.x;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const long long row = item / nseg;
+    const int x0 = (int)(item - row * nseg) * BXH_SEG;
+    const uint8_t* line = im.dst + row * w;
+    const int gx = x0 - halo + t;
+    if (t < L) buf[0][t] = line[min(max(gx, 0), w - 1)];
+    __syncthreads();
+    int cur = 0;
+    for (int p = 1; p <= 3; ++p) {
+      const int lo = (r + 1) * p, hi = L - (r + 1) * p;
+      if (t >= lo && t < hi) buf[cur ^ 1][t] = box_tap(buf[cur], t, 1, r, ww, fw);
+      __syncthreads();
+      if (t < L && (gx < 0 || gx >= w)) buf[cur ^ 1][t] = buf[cur ^ 1][min(max(gx, 0), w - 1) - (x0 - halo)];
+      __syncthreads();
+      cur ^= 1;
+    }
+    if (t >= halo && t < halo + BXH_SEG && gx < w) im.tmp[row * w + gx] = buf[cur][t];
+    __syncthreads();
+  }
+}
+
+// vertical: tmp -> dst
+__global__ void __launch_bounds__(256) aug_box3_v_kernel(const AugImage* __restrict__ tab) {
+  const AugImage& im = tab[blockIdx.y];
+  if (im.blur_r < 0 || im.blur_r > BOX_FUSED_R) return;
+  __shared__ uint8_t buf[2][(BXV_TH + 6 * (BOX_FUSED_R + 1)) * BXV_TW];
+  const int r = im.blur_r, halo = 3 * (r + 1), LH = BXV_TH + 2 * halo, h = im.h, w = im.w;
+  const unsigned long long ww = im.blur_ww, fw = im.blur_fw;
+  const int ty = (h + BXV_TH - 1) / BXV_TH, tx = (w + BXV_TW - 1) / BXV_TW;
+  const long long items = 3ll * ty * tx;
+  const int col = threadIdx.x & (BXV_TW - 1), rg = threadIdx.x >> 6;      // 4 row groups
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int c = (int)(item / ((long long)ty * tx));
+    const int rem = (int)(item - (long long)c * ty * tx);
+    const int y0 = (rem / tx) * BXV_TH, x = (rem % tx) * BXV_TW + col;
+    const bool in_x = x < w;
+    const uint8_t* plane = im.tmp + (size_t)c * h * w;
+    for (int j = rg; j < LH; j += 4)
+      buf[0][j * BXV_TW + col] = in_x ? plane[(size_t)min(max(y0 - halo + j, 0), h - 1) * w + x] : 0;
+    __syncthreads();
+    int cur = 0;
+    for (int p = 1; p <= 3; ++p) {
+      const int lo = (r + 1) * p, hi = LH - (r + 1) * p;
+      for (int j = lo + rg; j < hi; j += 4) buf[cur ^ 1][j * BXV_TW + col] = box_tap(buf[cur] + col, j, BXV_TW, r, ww, fw);
+      __syncthreads();
+      for (int j = rg; j < LH; j += 4) {
+        const int gy = y0 - halo + j;
+        if (gy < 0 || gy >= h) buf[cur ^ 1][j * BXV_TW + col] = buf[cur ^ 1][(min(max(gy, 0), h - 1) - (y0 - halo)) * BXV_TW + col];
+      }
+      __syncthreads();
+      cur ^= 1;
+    }
+    for (int j = halo + rg; j < halo + BXV_TH; j += 4) {
+      const int gy = y0 - halo + j;
+      if (in_x && gy < h) im.dst[(size_t)c * h * w + (size_t)gy * w + x] = buf[cur][j * BXV_TW + col];
+    }
+    __syncthreads();
   }
 }
 
@@ -341,6 +429,8 @@ extern "C" int ut2_resize_flip_u8(const void* src_hwc, int h, int w, void* dst_c
 // scratch. Overlapping erase regions are applied by separate launches so that "later on top" holds across blocks.
 extern "C" int ut2_strong_augment_u8(const void* table, int N, int max_pixels, int max_erase, unsigned long long* lsum_ws,
                                      void* stream) {
+  const int general_blur = max_erase >> 8;      // bit 8 of max_erase: some image has a box radius > 2 (host knows the draws)
+  max_erase &= 255;
   if (N <= 0) return 0;
   if (!table || !lsum_ws) return ut2_fail(-1, "strong_augment: null pointer");
   if (max_erase < 0 || max_erase > 3) return ut2_fail(-2, "strong_augment: at most 3 erase regions");
@@ -357,7 +447,10 @@ extern "C" int ut2_strong_augment_u8(const void* table, int N, int max_pixels, i
     aug_color_kernel<<<grid, 256, 0, STREAM>>>(tab, slot, lsum_ws);
   }
   aug_gray_kernel<<<grid, 256, 0, STREAM>>>(tab);
-  for (int pass = 0; pass < 6; ++pass) aug_box_kernel<<<grid3, 256, 0, STREAM>>>(tab, pass, pass >= 3);
+  aug_box3_h_kernel<<<grid3, 256, 0, STREAM>>>(tab);              // box radius <= 2: three passes per direction in one kernel
+  aug_box3_v_kernel<<<grid3, 256, 0, STREAM>>>(tab);
+  if (general_blur)                                             // larger radii (never drawn by the reference's [0.1, 2.0])
+    for (int pass = 0; pass < 6; ++pass) aug_box_kernel<<<grid3, 256, 0, STREAM>>>(tab, pass, pass >= 3);
   for (int k = 0; k < max_erase; ++k) aug_erase_kernel<<<grid, 256, 0, STREAM>>>(tab, k);   // one launch per region: later ones on top
   return ut2_check_launch("strong_augment");
 }

@@ -99,6 +99,7 @@ class GpuStrongAugmentation:
         outs, keep = [], []
         raw = bytearray()
         max_px = max_er = 0
+        big_blur = False
         for im, p in zip(images, params):
             assert im.dtype == torch.uint8 and im.dim() == 3 and im.shape[0] == 3 and im.is_contiguous()
             h, w = int(im.shape[1]), int(im.shape[2])
@@ -124,13 +125,14 @@ class GpuStrongAugmentation:
                     noise[k] = vd.data_ptr()
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if not self.exact_noise else 0
             br, bww, bfw = blur if blur is not None else (-1, 0, 0)
+            big_blur = big_blur or br > 2
             raw += REC.pack(im.data_ptr(), out.data_ptr(), tmp, noise[0], noise[1], noise[2], h, w, *order, *factor, hue_shift,
                             int(p["gray"]), br, bww, bfw, len(p["erase"]), *ei, *ej, *eh, *ew, seed, 0)
             max_px = max(max_px, h * w)
             max_er = max(max_er, len(p["erase"]))
         table = torch.frombuffer(raw, dtype=torch.uint8).clone().pin_memory().to(dev, non_blocking=True)
         ws = torch.empty((n, 4), dtype=torch.int64, device=dev)
-        _C.counted_call("ut2_strong_augment_u8", table, n, max_px, max_er, ws)
-        _C.launch_count += 16 + max_er
+        _C.counted_call("ut2_strong_augment_u8", table, n, max_px, max_er + (256 if big_blur else 0), ws)
+        _C.launch_count += 12 + max_er + (6 if big_blur else 0)
         self._keep = (keep, table, ws)      # alive until the next call (stream-ordered use)
         return outs
