@@ -190,3 +190,33 @@ def test_aspect_ratio_grouping_matches_reference_class():
     assert len(a) == len(b) > 10
     ids = lambda batches: [[[d["id"] for d in part] for part in batch] for batch in batches]
     assert ids(a) == ids(b)
+
+
+def test_two_crop_host_logic_matches_oracle():
+    """Host-side pieces of the device two-crop pipeline vs the oracle: Pillow box-blur parameters, [D2] shortest-edge shape,
+    box transform, and the order of the random draws (same seeds -> same parameters as the reference pipeline draws)."""
+    import random
+    import numpy as np
+    import torch
+    from oracle import ut2_aug_oracle as A
+    from ubteacher.data.dataset_mapper import shortest_edge_shape, transform_boxes
+    from ubteacher.data.gpu_augmentation import GpuStrongAugmentation, box_blur_params
+    for radius in (0.1, 0.35, 0.77, 1.0, 1.61, 2.0, 3.3, 7.0):
+        fr = A.gaussian_box_radius(radius)
+        assert box_blur_params(radius) == A.box_weights(fr)
+    for h, w, size in ((480, 640, 800), (427, 640, 800), (300, 1000, 800), (640, 480, 600), (1200, 1600, 400)):
+        assert shortest_edge_shape(h, w, size, 1333) == A.shortest_edge_shape(h, w, size, 1333)
+    boxes = [[10, 20, 110, 220], [600, 0, 700, 50], [5, 5, 5, 9], [0, 0, 640, 480]]
+    for flip in (False, True):
+        b0, k0 = transform_boxes(boxes, 480, 640, 333, 444, flip)
+        b1, k1 = A.transform_boxes(boxes, 480, 640, 333, 444, flip)
+        assert np.array_equal(b0, b1) and np.array_equal(k0, k1)
+    aug = GpuStrongAugmentation(exact_noise=True)
+    for seed in range(6):
+        torch.manual_seed(seed); random.seed(seed)
+        p = aug.draw(200, 300)
+        torch.manual_seed(seed); random.seed(seed)
+        q = A.draw_params(200, 300)
+        assert p["jitter"] == q["jitter"] and p["gray"] == q["gray"] and p["blur"] == q["blur"]
+        assert [e[:4] for e in p["erase"]] == [e[:4] for e in q["erase"]]
+        assert all(np.array_equal(np.asarray(a[4]), b[4]) for a, b in zip(p["erase"], q["erase"]))
