@@ -220,3 +220,22 @@ def test_two_crop_host_logic_matches_oracle():
         assert p["jitter"] == q["jitter"] and p["gray"] == q["gray"] and p["blur"] == q["blur"]
         assert [e[:4] for e in p["erase"]] == [e[:4] for e in q["erase"]]
         assert all(np.array_equal(np.asarray(a[4]), b[4]) for a, b in zip(p["erase"], q["erase"]))
+
+
+def test_coco_box_ap_known_cases():
+    """COCO-style AP restatement on cases with a known answer."""
+    import numpy as np
+    from ubteacher.evaluation import coco_box_ap
+    gt = {0: (np.array([[0, 0, 10, 10], [20, 20, 40, 40.0]]), np.array([1, 2])), 1: (np.array([[5, 5, 25, 25.0]]), np.array([1]))}
+    perfect = {0: (gt[0][0], gt[0][1], np.array([0.9, 0.8])), 1: (gt[1][0], gt[1][1], np.array([0.7]))}
+    r = coco_box_ap(perfect, gt)
+    assert abs(r["AP"] - 100) < 1e-9 and abs(r["AP50"] - 100) < 1e-9
+    # category 1: one of two boxes found, plus a higher-scored false positive -> precision 0.5 up to recall 0.5: AP = 51/101 * 0.5
+    dets = {0: (np.array([[100, 100, 110, 110], [0, 0, 10, 10.0]]), np.array([1, 1]), np.array([0.9, 0.8])),
+            1: (np.zeros((0, 4)), np.zeros(0, dtype=np.int64), np.zeros(0))}
+    r = coco_box_ap(dets, {k: (v[0][v[1] == 1], v[1][v[1] == 1]) for k, v in gt.items()})
+    assert abs(r["AP50"] - 100 * 51 / 101 * 0.5) < 1e-9 and abs(r["AP"] - r["AP50"]) < 1e-9
+    # IoU 0.6 box: counted at thresholds 0.50 and 0.55 (and 0.60 itself), not above
+    shifted = {0: (np.array([[0, 0, 10, 6.0]]), np.array([1]), np.array([0.9]))}
+    r = coco_box_ap(shifted, {0: (np.array([[0, 0, 10, 10.0]]), np.array([1]))})
+    assert abs(r["AP50"] - 100) < 1e-9 and abs(r["AP75"]) < 1e-9 and abs(r["AP"] - 30) < 1e-9

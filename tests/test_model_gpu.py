@@ -315,6 +315,7 @@ def test_eval_mode_rescales_to_dataset_size():
     """Eval-mode call contract (one_stage_detector.py:131-145, :225-240): [{"instances": Instances}] rescaled by [D2]
     detector_postprocess to the dict's height / width; output_raw=True is NOT rescaled."""
     from util_cfg import fcos_cfg
+    import ubteacher.modeling  # noqa: F401  (registers the meta-architectures)
     from ubteacher.d2compat.registry import META_ARCH_REGISTRY
     model = META_ARCH_REGISTRY.get("OneStageDetector")(fcos_cfg())
     diversify(model)
@@ -359,3 +360,38 @@ def test_train_loop_burn_in_then_semisup():
     assert all(abs(a - b) < 1e-12 for a, b in zip(lrs, want)), (lrs, want)
     assert all("loss_fcos_cls_pseudo" not in s for s in seen[:2]) and all("loss_fcos_cls_pseudo" in s for s in seen[2:])
     assert not torch.equal(tr.model_teacher.engine.arena.data, t0)
+
+
+def test_inference_on_dataset_and_box_ap():
+    """Eval path end to end (evaluation/evaluator.py:14-104): inference_on_dataset puts the model in eval mode (and back),
+    calls it with nms_method = NMS_CRITERIA_TEST, and the evaluator scores the detections; using the model's own detections
+    as ground truth gives AP 100, shifted ground truth gives less."""
+    from util_cfg import fcos_cfg
+    import ubteacher.modeling  # noqa: F401  (registers the meta-architectures)
+    from ubteacher.d2compat.registry import META_ARCH_REGISTRY
+    from ubteacher.d2compat.structures import Boxes, Instances
+    from ubteacher.evaluation import BoxAPEvaluator, inference_on_dataset
+    cfg = fcos_cfg()
+    model = META_ARCH_REGISTRY.get("OneStageDetector")(cfg)
+    diversify(model)
+    model.train()
+    g = torch.Generator().manual_seed(8)
+    batches = [[{"image": torch.randint(0, 256, (3, 128, 160), generator=g, dtype=torch.uint8), "image_id": 2 * b + i,
+                 "height": 128, "width": 160} for i in range(2)] for b in range(3)]
+    model.eval()
+    for batch in batches:                     # ground truth := the detections themselves
+        for d, o in zip(batch, model(batch, nms_method=cfg.MODEL.FCOS.NMS_CRITERIA_TEST)):
+            inst = Instances((128, 160))
+            inst.gt_boxes = Boxes(o["instances"].pred_boxes.tensor.clone())
+            inst.gt_classes = o["instances"].pred_classes.clone()
+            d["instances"] = inst
+    model.train()
+    res = inference_on_dataset(model, batches, BoxAPEvaluator(), cfg)
+    assert model.training                                     # inference_context restored the mode
+    assert sum(len(d["instances"]) for b in batches for d in b) > 0
+    assert abs(res["bbox"]["AP"] - 100.0) < 1e-6 and abs(res["bbox"]["AP50"] - 100.0) < 1e-6
+    for b in batches:
+        for d in b:
+            d["instances"].gt_boxes.tensor[:, 0::2] += 3.0    # shift the ground truth: strictly worse
+    res2 = inference_on_dataset(model, batches, BoxAPEvaluator(), cfg)
+    assert res2["bbox"]["AP"] < 99.0

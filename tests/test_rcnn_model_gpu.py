@@ -295,6 +295,7 @@ def test_eval_mode_inference_contract():
     """model.eval(): [D2] GeneralizedRCNN.inference -> [{"instances": Instances(pred_boxes, scores, pred_classes,
     pred_boxes_std)}] rescaled to the dict's height / width ([D2] detector_postprocess), RPN *_TEST top-k."""
     from util_cfg import rcnn_cfg
+    import ubteacher.modeling  # noqa: F401  (registers the meta-architectures)
     from ubteacher.d2compat.registry import META_ARCH_REGISTRY
     m = META_ARCH_REGISTRY.get("TwoStagePseudoLabGeneralizedRCNN")(rcnn_cfg())
     diversify(m)

@@ -136,6 +136,34 @@ class UBTeacherTrainer:
         return SyntheticTwoCropLoader(cfg.SOLVER.IMG_PER_BATCH_LABEL // w, cfg.SOLVER.IMG_PER_BATCH_UNLABEL // w,
                                       rank=comm.get_rank())
 
+    @classmethod
+    def build_evaluator(cls, cfg, dataset_name=None, output_folder=None):
+        """trainer.py:104-127 builds [D2]'s COCOEvaluator; pycocotools is not available here, so the host-side COCO-style box
+        AP (ubteacher/evaluation/box_ap.py) stands in: same DatasetEvaluator protocol, ground truth taken from the inputs."""
+        from ..evaluation import BoxAPEvaluator
+        return BoxAPEvaluator()
+
+    @classmethod
+    def build_test_loader(cls, cfg, dataset_name=None, num_batches=4, batch_size=2):
+        """A fixed-length list of synthetic labeled batches (no dataset on this box)."""
+        from ..data.synthetic import SyntheticTwoCropLoader
+        ld = SyntheticTwoCropLoader(batch_size, 1, rank=0, pin=False)
+        out = []
+        for i in range(num_batches):
+            _, lk, _, _ = next(ld)
+            for j, d in enumerate(lk):
+                d["image_id"] = i * batch_size + j
+            out.append(lk)
+        return out
+
+    @classmethod
+    def test(cls, cfg, model, evaluators=None):
+        """[D2] DefaultTrainer.test through the reference's inference_on_dataset (trainer.py:129-159, evaluation/evaluator.py)."""
+        from ..evaluation import inference_on_dataset
+        loader = cls.build_test_loader(cfg)
+        evaluator = evaluators if evaluators is not None else cls.build_evaluator(cfg)
+        return inference_on_dataset(model, loader, evaluator, cfg)
+
     def resume_or_load(self, resume=True):
         """trainer.py:86-102 ([D2] DefaultTrainer.resume_or_load): last checkpoint of OUTPUT_DIR when resuming, else
         MODEL.WEIGHTS (a Caffe2 pickle initialises the student backbone only). ``detectron2://`` URLs need the network
