@@ -239,3 +239,25 @@ def test_coco_box_ap_known_cases():
     shifted = {0: (np.array([[0, 0, 10, 6.0]]), np.array([1]), np.array([0.9]))}
     r = coco_box_ap(shifted, {0: (np.array([[0, 0, 10, 10.0]]), np.array([1]))})
     assert abs(r["AP50"] - 100) < 1e-9 and abs(r["AP75"]) < 1e-9 and abs(r["AP"] - 30) < 1e-9
+
+
+def test_train_net_entry_point_setup_and_trainer_choice():
+    """train_net.py (reference lines 15-35): config assembly from file + KEY VALUE overrides, trainer picked by
+    SEMISUPNET.Trainer, ValueError for anything else."""
+    import importlib.util
+    import os
+    import pytest
+    PKG = os.path.join(ROOT, "unbiased-teacher-v2_b200")
+    spec = importlib.util.spec_from_file_location("ut2_train_net", os.path.join(PKG, "train_net.py"))
+    tn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tn)
+    args = tn.argument_parser().parse_args(["--config-file", os.path.join(PKG, "configs/Faster-RCNN/coco-standard/faster_rcnn_R_50_FPN_ut2_sup1_run0.yaml"),
+                                            "SOLVER.MAX_ITER", "7", "SEMISUPNET.BURN_UP_STEP", "3"])
+    cfg = tn.setup(args)
+    assert cfg.SOLVER.MAX_ITER == 7 and cfg.SEMISUPNET.BURN_UP_STEP == 3 and cfg.MODEL.META_ARCHITECTURE == "TwoStagePseudoLabGeneralizedRCNN"
+    assert tn.pick_trainer(cfg).__name__ == "UBRCNNTeacherTrainer"
+    args = tn.argument_parser().parse_args(["--config-file", os.path.join(PKG, "configs/FCOS/coco-standard/fcos_R_50_ut2_sup1_run0.yaml")])
+    assert tn.pick_trainer(tn.setup(args)).__name__ == "UBTeacherTrainer"
+    args = tn.argument_parser().parse_args(["SEMISUPNET.Trainer", "something_else"])
+    with pytest.raises(ValueError, match="Trainer Name is not found"):
+        tn.pick_trainer(tn.setup(args))
