@@ -261,3 +261,71 @@ def test_train_net_entry_point_setup_and_trainer_choice():
     args = tn.argument_parser().parse_args(["SEMISUPNET.Trainer", "something_else"])
     with pytest.raises(ValueError, match="Trainer Name is not found"):
         tn.pick_trainer(tn.setup(args))
+
+
+def test_semisup_two_crop_loader_host_logic():
+    """data/build.py: the label / unlabel split against the reference function on the reference's own seed file, the
+    rank-sharded sampler, and the batch stream (orientation-pure batches, per-rank batch sizes, decode + mapper per batch)."""
+    import importlib.util
+    import itertools
+    import os
+    import sys
+    import types
+    import numpy as np
+    import pytest
+    from ubteacher.data.build import TrainingSampler, TwoCropBatchLoader, divide_label_unlabel
+    seed_file = "/root/reference/dataseed/COCO_supervision.txt"
+    if os.path.exists(seed_file):
+        names = ["detectron2", "detectron2.data", "detectron2.data.build", "detectron2.data.common", "detectron2.data.dataset_mapper",
+                 "detectron2.data.samplers", "detectron2.utils", "detectron2.utils.comm", "detectron2.utils.file_io", "ubteacher.data.common"]
+        saved = {k: sys.modules.get(k) for k in names}
+        try:
+            for k in names:
+                sys.modules[k] = types.ModuleType(k)
+            for k, attrs in (("detectron2.data.build", ["build_batch_data_loader", "get_detection_dataset_dicts", "trivial_batch_collator",
+                                                        "worker_init_reset_seed"]),
+                             ("detectron2.data.common", ["DatasetFromList", "MapDataset"]), ("detectron2.data.dataset_mapper", ["DatasetMapper"]),
+                             ("detectron2.data.samplers", ["InferenceSampler", "RepeatFactorTrainingSampler", "TrainingSampler"]),
+                             ("detectron2.utils.comm", ["get_world_size"]), ("ubteacher.data.common", ["AspectRatioGroupedSemiSupDatasetTwoCrop"])):
+                for a in attrs:
+                    setattr(sys.modules[k], a, object)
+            sys.modules["detectron2.utils.file_io"].PathManager = types.SimpleNamespace(open=open)
+            spec = importlib.util.spec_from_file_location("_ref_build", "/root/reference/ubteacher/data/build.py")
+            ref = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(ref)
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    sys.modules.pop(k, None)
+                else:
+                    sys.modules[k] = v
+        dicts = [{"image_id": i} for i in range(117266)]          # len(COCO train2017) after [D2]'s filtering: what the seed file indexes
+        for pct, seed in ((1.0, 0), (5.0, 3)):
+            a = ref.divide_label_unlabel(dicts, pct, seed, seed_file)
+            b = divide_label_unlabel(dicts, pct, seed, seed_file)
+            assert a[0] == b[0] and a[1] == b[1] and len(b[0]) == int(pct / 100 * len(dicts))
+        with pytest.raises(AssertionError):
+            divide_label_unlabel(dicts[:1000], 1.0, 0, seed_file)
+    # sampler: ranks partition one shared permutation stream
+    s0 = list(itertools.islice(iter(TrainingSampler(10, seed=4, rank=0, world_size=2)), 10))
+    s1 = list(itertools.islice(iter(TrainingSampler(10, seed=4, rank=1, world_size=2)), 10))
+    full = list(itertools.islice(iter(TrainingSampler(10, seed=4, rank=0, world_size=1)), 20))
+    assert s0 == full[0::2] and s1 == full[1::2] and sorted(full[:10]) == list(range(10))
+    # batch stream with a recording mapper / reader
+    rng = np.random.default_rng(0)
+    mk = lambda n, tag: [{"file_name": f"{tag}{i}.jpg", "width": 640 if rng.random() < 0.5 else 480, "height": 500, "id": (tag, i)} for i in range(n)]
+    reads = []
+
+    def reader(d):
+        reads.append(d["file_name"])
+        return np.zeros((d["height"], d["width"], 3), dtype=np.uint8)
+
+    def mapper(batch):
+        assert all("image" in d for d in batch)
+        return [dict(d, view="strong") for d in batch], [dict(d, view="weak") for d in batch]
+    loader = TwoCropBatchLoader(mk(40, "l"), mk(60, "u"), mapper, 2, 3, seed=1, reader=reader, rank=0, world_size=1)
+    for lq, lk, uq, uk in itertools.islice(iter(loader), 12):
+        assert len(lq) == len(lk) == 2 and len(uq) == len(uk) == 3
+        assert [d["id"] for d in lq] == [d["id"] for d in lk] and all(d["view"] == "strong" for d in lq + uq)
+        assert len({d["width"] > d["height"] for d in lq}) == 1 and len({d["width"] > d["height"] for d in uq}) == 1
+    assert len(reads) == 12 * 5          # only the images of emitted batches were decoded
