@@ -177,3 +177,35 @@ def test_gaussian_blur_fused_and_general_paths(size):
     outs = GpuStrongAugmentation()([to_dev(img) for _ in radii], params=params)
     for r, o in zip(radii, outs):
         assert np.array_equal(to_host(o), A.gaussian_blur(img, r)), (size, r)
+
+
+def test_two_crop_loader_end_to_end():
+    """build_detection_semisup_train_loader_two_crops with the device mapper: batches of (strong, weak) views, uint8 CHW on
+    the device, strong and weak of an image share size and labels, orientation-pure batches."""
+    import itertools
+    from util_cfg import fcos_cfg
+    from ubteacher.data.build import build_detection_semisup_train_loader_two_crops
+    cfg = fcos_cfg(**{"INPUT.MIN_SIZE_TRAIN": (64, 96), "INPUT.MAX_SIZE_TRAIN": 160, "SOLVER.IMG_PER_BATCH_LABEL": 2,
+                      "SOLVER.IMG_PER_BATCH_UNLABEL": 3})
+    g = np.random.default_rng(4)
+
+    def mk(n, tag, labeled):
+        out = []
+        for i in range(n):
+            h, w = (60, 90) if g.random() < 0.5 else (90, 60)
+            d = {"file_name": f"{tag}{i}", "height": h, "width": w, "image_id": i}
+            if labeled:
+                d["annotations"] = [{"bbox": [5.0, 6.0, w - 7.0, h - 8.0], "category_id": i % 80, "iscrowd": 0}]
+            out.append(d)
+        return out
+    reader = lambda d: g.integers(0, 256, (d["height"], d["width"], 3), dtype=np.uint8)
+    loader = build_detection_semisup_train_loader_two_crops(cfg, label_dicts=mk(12, "l", True), unlabel_dicts=mk(20, "u", False), reader=reader)
+    for lq, lk, uq, uk in itertools.islice(iter(loader), 4):
+        assert len(lq) == len(lk) == 2 and len(uq) == len(uk) == 3
+        for q, k in zip(lq + uq, lk + uk):
+            assert q["image"].is_cuda and q["image"].dtype == torch.uint8 and q["image"].shape == k["image"].shape and q["image"].shape[0] == 3
+            assert q["image_id"] == k["image_id"]
+        for q, k in zip(lq, lk):
+            assert torch.equal(q["instances"].gt_boxes.tensor, k["instances"].gt_boxes.tensor) and len(q["instances"]) == 1
+        assert len({d["width"] > d["height"] for d in lq}) == 1 and len({d["width"] > d["height"] for d in uq}) == 1
+    torch.cuda.synchronize()
