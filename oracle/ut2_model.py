@@ -14,6 +14,58 @@ from . import ut2_oracle as O
 STAGES = [("res2", 3, 1), ("res3", 4, 2), ("res4", 6, 2), ("res5", 3, 2)]
 BN_EPS = 1e-5
 
+# ---------------------------------------------------------------------------------------------------------------------
+# bf16 rounding points. The CUDA path keeps every activation AND every back-propagated activation gradient as a bf16
+# tensor in HBM (fp32 accumulation inside a kernel, one round-to-nearest-even when the tensor is written) and multiplies
+# bf16 copies of the fp32 master weights (FrozenBN scale folded in before the rounding). Inside ``with bf16_points():``
+# this restatement rounds at exactly those places — q() where a tensor is produced and where it is consumed (forward
+# value and incoming gradient), qw() on the tensor-core weight operand (forward only: weight gradients stay fp32) — so
+# that a comparison with the device separates accumulated ROUNDING from LOGIC errors (tests/test_model_gpu.py,
+# tests/test_rcnn_model_gpu.py). Outside the context the functions are the plain fp32 reference arithmetic.
+_BF16 = [False]
+
+
+class _RoundBoth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+class _RoundFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class bf16_points:
+    def __enter__(self):
+        self.prev = _BF16[0]
+        _BF16[0] = True
+
+    def __exit__(self, *a):
+        _BF16[0] = self.prev
+
+
+def q(x):
+    return _RoundBoth.apply(x) if _BF16[0] else x
+
+
+def qw(w):
+    return _RoundFwd.apply(w) if _BF16[0] else w
+
+
+def conv(x, w, b=None, stride=1, pad=0):
+    """conv2d through the rounding points: bf16 input / weight operands, fp32 accumulation + bias."""
+    return F.conv2d(q(x), qw(w), b, stride, pad)
+
 
 def frozen_bn(x, sd, p):
     """[D2] FrozenBatchNorm2d: y = x * (w * rsqrt(var + eps)) + (b - mean * scale)."""
@@ -23,37 +75,48 @@ def frozen_bn(x, sd, p):
 
 
 def conv_bn(x, sd, p, stride=1, pad=0):
+    if _BF16[0]:   # the device folds the FrozenBN scale into the packed bf16 weights; the epilogue adds the shift
+        n = p + ".norm"
+        scale = sd[n + ".weight"] * (sd[n + ".running_var"] + BN_EPS).rsqrt()
+        shift = sd[n + ".bias"] - sd[n + ".running_mean"] * scale
+        return F.conv2d(q(x), qw(sd[p + ".weight"] * scale.view(-1, 1, 1, 1)), None, stride, pad) + shift.view(1, -1, 1, 1)
     return frozen_bn(F.conv2d(x, sd[p + ".weight"], None, stride, pad), sd, p + ".norm")
+
+
+def stem(x, sd, p):
+    if _BF16[0]:   # csrc/stem_tc.cu: bf16 pixels x bf16 (unscaled) filter, FrozenBN scale + shift in the fp32 epilogue
+        return frozen_bn(F.conv2d(q(x), qw(sd[p + ".weight"]), None, 2, 3), sd, p + ".norm")
+    return conv_bn(x, sd, p, 2, 3)
 
 
 def trunk(sd, x):
     """[D2] BasicStem + 4 bottleneck stages (STRIDE_IN_1X1) -> {"res2".."res5"}."""
     bu = "backbone.bottom_up."
-    x = F.relu(conv_bn(x, sd, bu + "stem.conv1", 2, 3))
+    x = q(F.relu(stem(x, sd, bu + "stem.conv1")))
     x = F.max_pool2d(x, 3, 2, 1)
     feats = {}
     for stage, n, stride in STAGES:
         for i in range(n):
             p = f"{bu}{stage}.{i}."
             s = stride if i == 0 else 1
-            sc = conv_bn(x, sd, p + "shortcut", s) if (p + "shortcut.weight") in sd else x
-            out = F.relu(conv_bn(x, sd, p + "conv1", s))
-            out = F.relu(conv_bn(out, sd, p + "conv2", 1, 1))
+            sc = q(conv_bn(x, sd, p + "shortcut", s)) if (p + "shortcut.weight") in sd else x
+            out = q(F.relu(conv_bn(x, sd, p + "conv1", s)))
+            out = q(F.relu(conv_bn(out, sd, p + "conv2", 1, 1)))
             out = conv_bn(out, sd, p + "conv3")
-            x = F.relu(out + sc)
+            x = q(F.relu(out + sc))
         feats[stage] = x
     return feats
 
 
 def fpn_topdown(sd, feats, levels):
     """[D2] FPN (fuse "sum", nearest 2x top-down): returns {level: output} for the given level numbers (descending)."""
-    lat = lambda l, c: F.conv2d(c, sd[f"backbone.fpn_lateral{l}.weight"], sd[f"backbone.fpn_lateral{l}.bias"])
-    outc = lambda l, t: F.conv2d(t, sd[f"backbone.fpn_output{l}.weight"], sd[f"backbone.fpn_output{l}.bias"], 1, 1)
+    lat = lambda l, c: conv(c, sd[f"backbone.fpn_lateral{l}.weight"], sd[f"backbone.fpn_lateral{l}.bias"])
+    outc = lambda l, t: conv(t, sd[f"backbone.fpn_output{l}.weight"], sd[f"backbone.fpn_output{l}.bias"], 1, 1)
     prev, outs = None, {}
     for l in levels:
         cur = lat(l, feats[f"res{l}"])
-        prev = cur if prev is None else cur + F.interpolate(prev, scale_factor=2.0, mode="nearest")
-        outs[l] = outc(l, prev)
+        prev = q(cur if prev is None else cur + F.interpolate(prev, scale_factor=2.0, mode="nearest"))
+        outs[l] = q(outc(l, prev))
     return outs
 
 
@@ -61,8 +124,8 @@ def backbone(sd, x):
     """FCOS backbone: trunk -> FPN p3..p5 + LastLevelP6P7(p5) (backbone/fpn.py:11-78)."""
     o = fpn_topdown(sd, trunk(sd, x), (5, 4, 3))
     p5, p4, p3 = o[5], o[4], o[3]
-    p6 = F.conv2d(p5, sd["backbone.top_block.p6.weight"], sd["backbone.top_block.p6.bias"], 2, 1)
-    p7 = F.conv2d(F.relu(p6), sd["backbone.top_block.p7.weight"], sd["backbone.top_block.p7.bias"], 2, 1)
+    p6 = q(conv(p5, sd["backbone.top_block.p6.weight"], sd["backbone.top_block.p6.bias"], 2, 1))
+    p7 = q(conv(F.relu(p6), sd["backbone.top_block.p7.weight"], sd["backbone.top_block.p7.bias"], 2, 1))
     return [p3, p4, p5, p6, p7]
 
 
@@ -75,10 +138,11 @@ def fcos_head(sd, feats):
         for t in ("cls_tower", "bbox_tower"):
             x = f
             for i in range(4):
-                x = F.conv2d(x, sd[f"{hd}{t}.{3 * i}.weight"], sd[f"{hd}{t}.{3 * i}.bias"], 1, 1)
-                x = F.relu(F.group_norm(x, 32, sd[f"{hd}{t}.{3 * i + 1}.weight"], sd[f"{hd}{t}.{3 * i + 1}.bias"], 1e-5))
+                x = q(conv(x, sd[f"{hd}{t}.{3 * i}.weight"], sd[f"{hd}{t}.{3 * i}.bias"], 1, 1))
+                x = q(F.relu(F.group_norm(x, 32, sd[f"{hd}{t}.{3 * i + 1}.weight"], sd[f"{hd}{t}.{3 * i + 1}.bias"], 1e-5)))
             towers[t] = x
-        c = lambda n, x: F.conv2d(x, sd[hd + n + ".weight"], sd[hd + n + ".bias"], 1, 1)
+        # the predictors' outputs are bf16 tensors; Scale_l is applied to the rounded value inside the loss / decode kernels
+        c = lambda n, x: q(conv(x, sd[hd + n + ".weight"], sd[hd + n + ".bias"], 1, 1))
         logits.append(c("cls_logits", towers["cls_tower"]))
         ctr.append(c("ctrness", towers["bbox_tower"]))
         reg.append(c("bbox_pred", towers["bbox_tower"]) * sd[f"{hd}scales.{l}.scale"])

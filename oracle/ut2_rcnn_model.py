@@ -27,9 +27,9 @@ def rpn_head(sd, feats):
     p = "proposal_generator.rpn_head."
     logits, deltas = [], []
     for f in feats:
-        t = F.relu(F.conv2d(f, sd[p + "conv.weight"], sd[p + "conv.bias"], 1, 1))
-        lg = F.conv2d(t, sd[p + "objectness_logits.weight"], sd[p + "objectness_logits.bias"])
-        dl = F.conv2d(t, sd[p + "anchor_deltas.weight"], sd[p + "anchor_deltas.bias"])
+        t = M.q(F.relu(M.conv(f, sd[p + "conv.weight"], sd[p + "conv.bias"], 1, 1)))
+        lg = M.q(M.conv(t, sd[p + "objectness_logits.weight"], sd[p + "objectness_logits.bias"]))
+        dl = M.q(M.conv(t, sd[p + "anchor_deltas.weight"], sd[p + "anchor_deltas.bias"]))
         N, _, H, W = lg.shape
         logits.append(lg.permute(0, 2, 3, 1).flatten(1))
         deltas.append(dl.view(N, -1, 4, H, W).permute(0, 3, 4, 1, 2).flatten(1, -2))
@@ -38,13 +38,14 @@ def rpn_head(sd, feats):
 
 def box_head(sd, pooled):
     """[D2] FastRCNNConvFCHead (2 x FC 1024 + ReLU) + the three predictors (fast_rcnn.py:760-766, :818-832)."""
-    x = pooled.flatten(1)
-    x = F.relu(F.linear(x, sd["roi_heads.box_head.fc1.weight"], sd["roi_heads.box_head.fc1.bias"]))
-    x = F.relu(F.linear(x, sd["roi_heads.box_head.fc2.weight"], sd["roi_heads.box_head.fc2.bias"]))
+    q, qw = M.q, M.qw                  # bf16 rounding points (identity outside ``with M.bf16_points()``)
+    x = q(pooled.flatten(1))           # ROIAlign writes bf16
+    x = q(F.relu(F.linear(x, qw(sd["roi_heads.box_head.fc1.weight"]), sd["roi_heads.box_head.fc1.bias"])))
+    x = q(F.relu(F.linear(x, qw(sd["roi_heads.box_head.fc2.weight"]), sd["roi_heads.box_head.fc2.bias"])))
     bp = "roi_heads.box_predictor."
-    return (F.linear(x, sd[bp + "cls_score.weight"], sd[bp + "cls_score.bias"]),
-            F.linear(x, sd[bp + "bbox_pred.weight"], sd[bp + "bbox_pred.bias"]),
-            F.linear(x, sd[bp + "bbox_pred_std.weight"], sd[bp + "bbox_pred_std.bias"]))
+    return (q(F.linear(x, qw(sd[bp + "cls_score.weight"]), sd[bp + "cls_score.bias"])),
+            q(F.linear(x, qw(sd[bp + "bbox_pred.weight"]), sd[bp + "bbox_pred.bias"])),
+            q(F.linear(x, qw(sd[bp + "bbox_pred_std.weight"]), sd[bp + "bbox_pred_std.bias"])))
 
 
 def preprocess(sd, images):

@@ -227,3 +227,155 @@ def test_groupnorm_levels_equals_per_level():
         assert torch.allclose(dxl.float(), dr.float(), rtol=1 / 64, atol=2e-3), l
     assert torch.allclose(dgam, rg, rtol=1e-3, atol=1e-2) and torch.allclose(dbet, rb, rtol=1e-3, atol=1e-2)
     assert torch.allclose(dbias, rbias, rtol=1e-3, atol=1e-2)
+
+
+# --------------------------------------------------------------------------------------- benchmark-scale launches
+# The kernels are persistent (grid <= 148 CTAs): the cases above never give a CTA a second tile. These launches have 4-7x
+# as many tiles as SMs, i.e. every CTA walks the operand ring across tile boundaries, alternates the two TMEM accumulator
+# buffers, flips the aux-tile phases ((it >> 1) & 1 with aux_dbl) and restages scale / shift between n-tiles — the regime
+# bench.py runs (16 x 100 x 168 -> 2100 tiles). Reference: fp32 F.conv2d on the CPU, same tolerances as above.
+BIG_FWD = [
+    # id, (N, H, W, Cin, Cout, R, stride, pad), aux, relu
+    ("head3x3_256", (5, 100, 168, 256, 256, 3, 1, 1), None, True),                 # 657 tiles, tensor-bound head / FPN output shape
+    ("res2_conv3_aux_dbl", (2, 200, 336, 64, 256, 1, 1, 0), "res", True),          # 1050 tiles, K = 64: double-buffered aux tiles
+    ("res4_conv3_res", (5, 50, 84, 256, 1024, 1, 1, 0), "res", True),              # 165 x 4 = 660 tiles, single aux tile, 4 n-tiles
+    ("res5_conv3_res_8ntiles", (8, 25, 42, 512, 2048, 1, 1, 0), "res", True),      # 66 x 8 = 528 tiles, scale / shift restaging
+    ("dgrad_mask_128", (4, 100, 168, 128, 128, 3, 1, 1), "mask", False),           # 525 tiles, ReLU-mask aux tile (dgrad epilogue)
+    ("dgrad_mask_64_aux_dbl", (2, 200, 336, 64, 64, 1, 1, 0), "mask", False),      # 1050 tiles, mask + aux_dbl, N = 64 tile
+    ("fpn_lateral_res_up2", (4, 100, 168, 512, 256, 1, 1, 0), "res_up2", False),   # 525 tiles, manual epilogue (nearest-2x residual)
+    ("res_and_mask_manual", (4, 100, 168, 64, 128, 1, 1, 0), "res+mask", False),   # 525 tiles, manual epilogue (both)
+    ("cls_logits_80", (4, 100, 168, 256, 80, 3, 1, 1), None, False),               # 525 tiles, Cout = 80
+    ("res3_conv1_s2", (4, 200, 336, 256, 128, 1, 2, 0), None, True),               # 525 tiles, strided 1x1 (STRIDE_IN_1X1)
+    ("p6_3x3_s2", (8, 100, 168, 256, 256, 3, 2, 1), None, False),                  # 263 tiles, strided 3x3
+    ("dgrad_ragged_cin", (4, 100, 168, 80, 256, 3, 1, 1), None, False),            # 525 tiles, Cin = 80 (zero-filled ragged chunk)
+]
+
+
+@pytest.mark.parametrize("name,case,aux,relu", BIG_FWD, ids=[c[0] for c in BIG_FWD])
+def test_conv_fwd_many_tiles_per_cta(name, case, aux, relu):
+    from ubteacher import _C
+
+    N, H, W, Cin, Cout, R, stride, pad = case
+    x, w = _mk(N, H, W, Cin, Cout, R, seed=len(name))
+    P = (H + 2 * pad - R) // stride + 1
+    Q = (W + 2 * pad - R) // stride + 1
+    tiles = ((N * P * Q + 127) // 128) * ((Cout + 255) // 256 if Cout > 256 else 1)
+    assert tiles > 148, "the point of this test is more tiles than SMs"
+    g = torch.Generator().manual_seed(13)
+    shift = torch.randn(Cout, generator=g)
+    res = mask = None
+    if aux in ("res", "res+mask"):
+        res = torch.randn(N, P, Q, Cout, generator=g).bfloat16()
+    if aux == "res_up2":
+        res = torch.randn(N, P // 2, Q // 2, Cout, generator=g).bfloat16()
+    if aux in ("mask", "res+mask"):
+        mask = torch.randn(N, P, Q, Cout, generator=g).relu().bfloat16()      # half of it exactly zero, like a ReLU output
+    y = torch.full((N, P, Q, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    cu = lambda t: t.cuda() if t is not None else None
+    _C.call("ut2_conv2d_nhwc_bf16_fwd", x.cuda(), N, H, W, Cin, w.cuda(), Cout, R, R, stride, pad,
+            None, shift.cuda(), cu(res), int(aux == "res_up2"), cu(mask), int(relu), y)
+    torch.cuda.synchronize()
+    r = res
+    if aux == "res_up2":
+        r = res.float().repeat_interleave(2, 1).repeat_interleave(2, 2)
+    ref = _ref_fwd(x, w, stride, pad, None, shift, r, relu)
+    if mask is not None:
+        ref = ref * (mask.float() > 0)
+    got = y.float().cpu()
+    assert torch.isfinite(got).all(), "unwritten output rows"
+    torch.testing.assert_close(got, ref, rtol=RTOL, atol=ATOL)
+
+
+BIG_WGRAD = [
+    # id, (N, H, W, Cin, Cout, R, stride, pad)          stage width chosen by the launcher
+    ("head3x3_256_pix96", (4, 100, 168, 256, 256, 3, 1, 1)),          # block_n 256 -> 96-pixel stages, split-K 8 x 88 blocks
+    ("res2_1x1_64_pix128", (2, 200, 336, 64, 256, 1, 1, 0)),          # block_n 64 -> 128-pixel stages, 65-way split-K
+    ("res3_3x3_128_pix128", (4, 100, 168, 128, 128, 3, 1, 1)),        # block_n 128
+    ("res4_1x1_1024_256_pix96", (5, 50, 84, 1024, 256, 1, 1, 0)),     # 4 input-channel tiles x 2 output tiles
+    ("cls_logits_80", (4, 100, 168, 256, 80, 3, 1, 1)),               # ragged Cout
+    ("res3_conv1_s2", (4, 200, 336, 256, 128, 1, 2, 0)),              # strided
+]
+
+
+@pytest.mark.parametrize("name,case", BIG_WGRAD, ids=[c[0] for c in BIG_WGRAD])
+def test_conv_wgrad_long_reductions(name, case):
+    """Weight gradients at reduction lengths (tens of thousands of pixels per output tile, split-K over the whole grid)
+    where each CTA wraps its operand ring many times."""
+    from ubteacher import _C
+
+    N, H, W, Cin, Cout, R, stride, pad = case
+    x, w = _mk(N, H, W, Cin, Cout, R, seed=len(name))
+    P = (H + 2 * pad - R) // stride + 1
+    Q = (W + 2 * pad - R) // stride + 1
+    g = torch.Generator().manual_seed(5)
+    dy = torch.randn(N, P, Q, Cout, generator=g).bfloat16()
+    dw = torch.zeros(Cout, R, R, Cin, dtype=torch.float32, device="cuda")
+    _C.call("ut2_conv2d_nhwc_bf16_wgrad", x.cuda(), N, H, W, Cin, dy.cuda(), Cout, R, R, stride, pad, None, dw, 0)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Cout, Cin, R, R), dy.float().permute(0, 3, 1, 2),
+                                      stride=stride, padding=pad).permute(0, 2, 3, 1)
+    scale = ref.abs().max().item()
+    torch.testing.assert_close(dw.cpu(), ref, rtol=2e-3, atol=2e-3 * scale)
+
+
+@pytest.mark.parametrize("pix", [64, 96, 128])
+def test_conv_wgrad_every_stage_width(pix, monkeypatch):
+    """All three instantiations of conv_wgrad_kernel<PIX> on one long reduction (UT2_WG_PIX is read once per process, so the
+    override runs in a child interpreter)."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path[:0] = [%r, %r]
+from ubteacher import _C
+N, H, W, Cin, Cout, R = 3, 100, 168, 256, 256, 3
+g = torch.Generator().manual_seed(1)
+x = torch.randn(N, H, W, Cin, generator=g).bfloat16()
+dy = torch.randn(N, H, W, Cout, generator=g).bfloat16()
+dw = torch.zeros(Cout, R, R, Cin, device="cuda")
+_C.call("ut2_conv2d_nhwc_bf16_wgrad", x.cuda(), N, H, W, Cin, dy.cuda(), Cout, R, R, 1, 1, None, dw, 0)
+torch.cuda.synchronize()
+ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Cout, Cin, R, R), dy.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
+torch.testing.assert_close(dw.cpu(), ref, rtol=2e-3, atol=2e-3 * ref.abs().max().item())
+print("OK")
+''' % (os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "unbiased-teacher-v2_b200"),
+       os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, UT2_WG_PIX=str(pix))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
+
+
+FULL_HW = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]       # the FCOS pyramid of an 800 x 1344 batch
+
+
+def _split_hw(t, N, C, hws):
+    out, off = [], 0
+    for h, w in hws:
+        out.append(t[off:off + N * h * w].view(N, h, w, C))
+        off += N * h * w
+    return out
+
+
+@pytest.mark.parametrize("cout,relu", [(256, False), (80, False)])
+def test_conv_levels_full_size_pyramid(cout, relu):
+    """ut2_conv2d_levels_bf16_fwd / _wgrad over the level-major pyramid of FOUR full-size images (89 600 rows, 702 tiles: tiles
+    of all five levels interleave inside every CTA) against fp32 F.conv2d per level."""
+    from ubteacher import ops
+    geom, N = ops.LevelGeom(FULL_HW, [8, 16, 32, 64, 128]), 4
+    g = torch.Generator().manual_seed(cout)
+    x = torch.randn(geom.L * N, 256, generator=g).bfloat16()
+    w = (torch.randn(cout, 3, 3, 256, generator=g) / (9 * 256) ** 0.5).bfloat16()
+    shift = torch.randn(cout, generator=g)
+    dy = torch.randn(geom.L * N, cout, generator=g).bfloat16()
+    y = ops.conv2d_levels(x.cuda(), geom, N, w.cuda(), cout, 3, 3, 1, None, shift.cuda(), None, relu)
+    dw = torch.zeros(cout, 3, 3, 256, device="cuda")
+    ops.conv2d_wgrad_levels(x.cuda(), dy.cuda(), geom, N, cout, 3, 3, 1, dw)
+    torch.cuda.synchronize()
+    ref_dw = torch.zeros(cout, 3, 3, 256)
+    for xl, yl, dl in zip(_split_hw(x, N, 256, FULL_HW), _split_hw(y.cpu(), N, cout, FULL_HW), _split_hw(dy, N, cout, FULL_HW)):
+        ref = _ref_fwd(xl, w, 1, 1, None, shift, None, relu)
+        torch.testing.assert_close(yl.float(), ref, rtol=RTOL, atol=ATOL)
+        ref_dw += torch.nn.grad.conv2d_weight(xl.float().permute(0, 3, 1, 2), (cout, 256, 3, 3), dl.float().permute(0, 3, 1, 2),
+                                              padding=1).permute(0, 2, 3, 1)
+    torch.testing.assert_close(dw.cpu(), ref_dw, rtol=2e-3, atol=2e-3 * ref_dw.abs().max().item())

@@ -104,8 +104,21 @@ def test_labeled_loss_and_gradients_match_oracle(model):
     for k in ref:   # fp32 loss arithmetic on bf16 activations: 3 %
         torch.testing.assert_close(losses[k].cpu(), ref[k].detach(), rtol=3e-2, atol=1e-3)
     (ref["loss_fcos_cls"] * w[0] + ref["loss_fcos_loc"] * w[1] + ref["loss_fcos_ctr"] * w[2]).backward()
+    # second oracle run with the device's bf16 rounding points (oracle/ut2_model.py: bf16_points): same arithmetic, tensors
+    # rounded where the engine stores them. Separates accumulated rounding (fp32 run, loose bounds below) from logic.
+    params_q = {k: sd[k].clone().requires_grad_(True) for k in tk}
+    sdq = dict(sd)
+    sdq.update(params_q)
+    with M.bf16_points():
+        sq = M.forward_dense(sdq, [b["image"] for b in batch])
+        refq, _ = O.fcos_losses_labeled(sq["logits"], sq["reg"], sq["std"], sq["ctr"], sq["locations"], [b["boxes"] for b in batch],
+                                        [b["classes"] for b in batch])
+        (refq["loss_fcos_cls"] * w[0] + refq["loss_fcos_loc"] * w[1] + refq["loss_fcos_ctr"] * w[2]).backward()
+    for k in refq:
+        torch.testing.assert_close(losses[k].cpu(), refq[k].detach(), rtol=3e-2, atol=1e-3)
     G = model.engine.arena.gviews
     checked = 0
+    report = []
     for k in ["proposal_generator.fcos_head.cls_logits.weight", "proposal_generator.fcos_head.cls_logits.bias",
               "proposal_generator.fcos_head.bbox_pred.weight", "proposal_generator.fcos_head.bbox_pred_std.bias",
               "proposal_generator.fcos_head.ctrness.weight", "proposal_generator.fcos_head.cls_tower.0.weight",
@@ -118,15 +131,141 @@ def test_labeled_loss_and_gradients_match_oracle(model):
         a, b = G[k].float().cpu().double().flatten(), params[k].grad.double().flatten()
         cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
         ratio = float(a.norm() / (b.norm() + 1e-30))
-        # bf16 activations AND bf16 back-propagated gradients against an fp32 run: the disagreement grows with
-        # depth below the loss (measured: head 0.9999, FPN 0.997, res5 0.99, res4 0.96, res3 0.92 — ReLU masks and
-        # the steep 1/sigma^2 NLL gradient amplify the 2^-9 rounding). The loss-kernel gradients themselves agree
-        # to 3e-4 (test_kernels_gpu.py), so the thresholds below bound accumulated rounding, not logic.
-        need = 0.88 if ".res3." in k else 0.93 if ".res4." in k else 0.97 if ".res5." in k else 0.99
-        assert cos > need and 0.8 < ratio < 1.2, (k, cos, ratio)
+        # bf16 activations AND bf16 back-propagated gradients against an fp32 run; the per-block / per-head isolated
+        # tests above bound logic errors much tighter (0.9995), these bound the accumulated rounding of the whole chain.
+        # measured on B200 (profiles/r02_gradient_parity.txt): >= 0.9986 at every depth except P6 / P7 (0.994: two tiny
+        # levels, a handful of positives); the bounds keep a margin for the fp32-atomic accumulation order
+        need = 0.99 if "top_block" in k else 0.997
+        bq = params_q[k].grad.double().flatten()
+        cosq = float((a * bq).sum() / (a.norm() * bq.norm() + 1e-30))
+        ratioq = float(a.norm() / (bq.norm() + 1e-30))
+        report.append((k, cos, ratio, cosq, ratioq))
+        assert cos > need and 0.93 < ratio < 1.07, (k, cos, ratio)
+        assert cosq > need and 0.9 < ratioq < 1.1, (k, cosq, ratioq)
         checked += 1
+    print("\n".join(f"{k:58s} fp32: cos {c:.4f} ratio {r:.3f} | bf16 points: cos {cq:.5f} ratio {rq:.4f}" for k, c, r, cq, rq in report))
     assert checked == 20
     model.engine.arena.grad.zero_()
+
+
+def _cosr(a, b):
+    a, b = a.float().cpu().double().flatten(), b.double().flatten()
+    return float((a * b).sum() / (a.norm() * b.norm() + 1e-30)), float(a.norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("stage,idx,hw", [("res3", 0, (40, 56)), ("res3", 1, (20, 28)), ("res4", 0, (20, 28)), ("res4", 3, (10, 14)),
+                                          ("res5", 0, (10, 14)), ("res5", 2, (6, 8))])
+def test_bottleneck_forward_backward_isolated(model, stage, idx, hw):
+    """ONE bottleneck block on the device (forward, then the explicit backward schedule: relu_bwd, three wgrad / dgrad pairs
+    with fused ReLU masks, shortcut-gradient add, strided-1x1 compact dgrad + zero-stuff) against autograd through the
+    bf16-rounding-point oracle of the same block on IDENTICAL bf16 inputs. End to end the two runs decorrelate (a one-ulp
+    flip after the stem grows to 0.3 % by res3 and 0.7 % by res5 in this randomly initialised trunk — measured in
+    tools/debug_bf16_trunk.py — so device-vs-bf16-oracle is no tighter than device-vs-fp32 there); per block nothing
+    amplifies, so any logic error (a wrong shortcut add, a misplaced zero-stuff) shows: direction 0.9995, norm 0.5 %."""
+    import torch.nn.functional as F
+    from oracle import ut2_model as M
+    eng = model.engine
+    blks = dict(eng.blocks)[stage]
+    b = blks[idx]
+    p = f"backbone.bottom_up.{stage}.{idx}."
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items() if k.startswith(p)}
+    N, (H, W) = 2, hw
+    g = torch.Generator().manual_seed(17 + idx)
+    x = torch.randn(N, H, W, b["conv1"].cin, generator=g).relu().bfloat16()
+    y, ctx = eng._block_fwd(b, x.cuda(), True)
+    dy = (torch.randn(y.shape, generator=g) * 0.1).bfloat16()
+    dy2 = (torch.randn(y.shape, generator=g) * 0.1).bfloat16() if idx == 0 else None   # a stage's last block also gets the FPN lateral's gradient
+    eng.arena.grad.zero_()
+    dx = eng._block_bwd(b, ctx, dy.cuda(), dy2.cuda() if dy2 is not None else None)
+    torch.cuda.synchronize()
+    names = [n for n in ("shortcut", "conv1", "conv2", "conv3") if n in b]
+    params = {p + n + ".weight": sd[p + n + ".weight"].clone().requires_grad_(True) for n in names}
+    sdp = dict(sd)
+    sdp.update(params)
+    xin = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    s = b["stride"]
+    with M.bf16_points():
+        sc = M.q(M.conv_bn(xin, sdp, p + "shortcut", s)) if "shortcut" in b else xin
+        o = M.q(F.relu(M.conv_bn(xin, sdp, p + "conv1", s)))
+        o = M.q(F.relu(M.conv_bn(o, sdp, p + "conv2", 1, 1)))
+        yo = M.q(F.relu(M.conv_bn(o, sdp, p + "conv3") + sc))
+        gy = dy.float() + (dy2.float() if dy2 is not None else 0)
+        yo.backward(gy.permute(0, 3, 1, 2))
+    assert rel(y.permute(0, 3, 1, 2), yo.detach()) < 2e-3
+    G = eng.arena.gviews
+    for k, v in params.items():
+        cos, ratio = _cosr(G[k], v.grad)
+        assert cos > 0.9995 and abs(ratio - 1) < 5e-3, (k, cos, ratio)
+    if b["need_dx"]:
+        cos, ratio = _cosr(dx.permute(0, 3, 1, 2), xin.grad)
+        assert cos > 0.9995 and abs(ratio - 1) < 5e-3, ("dx", cos, ratio)
+    else:
+        assert dx is None           # res3.0 sits on the frozen res2: no data gradient below it
+    eng.arena.grad.zero_()
+
+
+def test_fpn_and_head_backward_isolated(model):
+    """FPN (laterals, nearest-2x top-down, outputs, P6/P7) + FCOS head (towers with GroupNorm, predictors) forward and the
+    explicit backward schedule on the device against autograd through the bf16-rounding-point oracle, both starting from the
+    SAME res3 / res4 / res5 tensors and the SAME output gradients: weight / bias / GroupNorm / lateral-input gradients."""
+    from oracle import ut2_model as M
+    eng = model.engine
+    N, Hp, Wp = 2, 160, 224
+    g = torch.Generator().manual_seed(23)
+    feats = {f"res{l}": (torch.randn(N, Hp // s, Wp // s, c, generator=g).relu() * 0.5).bfloat16()
+             for l, s, c in ((3, 8, 512), (4, 16, 1024), (5, 32, 2048))}
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    captured = {}
+    orig_f, orig_b = eng.trunk_forward, eng.trunk_backward
+    try:
+        eng.trunk_forward = lambda images, train, tape: ({k: v.cuda() for k, v in feats.items()}, [(Hp, Wp)] * N, (Hp, Wp))
+        eng.trunk_backward = lambda tape, extra: captured.update(extra)
+        fwd = eng.forward([None] * N, train=True)
+        geom = fwd["geom"]
+        dcls = (torch.randn(geom.L * N, 80, generator=g) * 0.05).bfloat16()
+        dbox = (torch.randn(geom.L * N, 80, generator=g) * 0.05).bfloat16()
+        dbox[:, 73:] = 0                              # rows 73..79 of the fused box predictor are padding
+        eng.arena.grad.zero_()
+        eng.backward(fwd, dcls.cuda(), dbox.cuda())
+        torch.cuda.synchronize()
+    finally:
+        eng.trunk_forward, eng.trunk_backward = orig_f, orig_b
+    tk = [k for k in M.trainable_keys(sd) if not k.startswith("backbone.bottom_up.") and "scales" not in k]
+    params = {k: sd[k].clone().requires_grad_(True) for k in tk}
+    sdp = dict(sd)
+    sdp.update(params)
+    fin = {k: v.float().permute(0, 3, 1, 2).clone().requires_grad_(True) for k, v in feats.items()}
+    with M.bf16_points():
+        o = M.fpn_topdown(sdp, fin, (5, 4, 3))
+        p6 = M.q(M.conv(o[5], sdp["backbone.top_block.p6.weight"], sdp["backbone.top_block.p6.bias"], 2, 1))
+        p7 = M.q(M.conv(torch.relu(p6), sdp["backbone.top_block.p7.weight"], sdp["backbone.top_block.p7.bias"], 2, 1))
+        hd = "proposal_generator.fcos_head."
+        sdu = dict(sdp)
+        for l in range(5):
+            sdu[f"{hd}scales.{l}.scale"] = torch.ones(1)          # box_out holds the UNSCALED bbox_pred (Scale_l lives in the loss kernels)
+        logits, reg, std, ctr = M.fcos_head(sdu, [o[3], o[4], o[5], p6, p7])
+        tot = 0
+        for l in range(5):
+            h, w = geom.hw[l]
+            lo, hi = geom.off[l] * N, geom.off[l + 1] * N
+            gc = dcls[lo:hi].view(N, h, w, 80).permute(0, 3, 1, 2).float()
+            gb = dbox[lo:hi].view(N, h, w, 80).permute(0, 3, 1, 2).float()
+            tot = tot + (logits[l] * gc).sum() + (reg[l] * gb[:, :68]).sum() + (std[l] * gb[:, 68:72]).sum() + (ctr[l] * gb[:, 72:73]).sum()
+            got = fwd["cls_out"][lo:hi].view(N, h, w, 80).permute(0, 3, 1, 2)
+            assert rel(got, logits[l].detach()) < 0.02, l       # ten chained bf16 layers: decorrelated rounding, not logic
+        tot.backward()
+    G = eng.arena.gviews
+    worst = (1.0, None)
+    for k in tk:
+        cos, ratio = _cosr(G[k], params[k].grad)
+        worst = min(worst, (cos, k))
+        # ten chained bf16 layers, twelve for P6 / P7 (measured worst: 0.9978 / 0.9948 on their 12- and 4-pixel maps)
+        assert cos > (0.99 if "top_block" in k else 0.995) and abs(ratio - 1) < 0.02, (k, cos, ratio)
+    for st in ("res3", "res4", "res5"):
+        cos, ratio = _cosr(captured[st].permute(0, 3, 1, 2), fin[st].grad)
+        assert cos > 0.995 and abs(ratio - 1) < 0.02, (st, cos, ratio)
+    print("worst cosine", worst)
+    eng.arena.grad.zero_()
 
 
 def test_autograd_bridge_equals_explicit_backward(model):
@@ -145,9 +284,7 @@ def test_autograd_bridge_equals_explicit_backward(model):
     assert rel(g2, g1) < 2e-3     # same kernels; only the fp32 atomic accumulation order differs
 
 
-def test_teacher_proposals_and_full_step_vs_oracle():
-    """Two trainer steps at small resolution; the oracle step is driven with the device's pseudo-label sets
-    (threshold borderlines differ between bf16 and fp32 scores), everything else is independent."""
+def _steps_vs_oracle(sizes, n_steps, n_label, n_unlabel, nbox):
     from oracle import ut2_model as M
     from util_cfg import fcos_cfg, oracle_step_cfg
     from ubteacher.engine import UBTeacherTrainer
@@ -161,8 +298,8 @@ def test_teacher_proposals_and_full_step_vs_oracle():
 
         def __next__(self):
             self.i += 1
-            mk = lambda n, seed: make_batch(n, [(128, 160), (160, 192)], seed, nbox=4)
-            lq, uq = mk(1, 100 + self.i), mk(2, 200 + self.i)
+            mk = lambda n, seed: make_batch(n, sizes, seed, nbox=nbox)
+            lq, uq = mk(n_label, 100 + self.i), mk(n_unlabel, 200 + self.i)
             lk = [dict(d, image=torch.flip(d["image"], [0])) for d in lq]
             uk = [dict(d) for d in uq]
             return lq, lk, uq, uk
@@ -180,7 +317,7 @@ def test_teacher_proposals_and_full_step_vs_oracle():
     ref_loader = Loader()
     from ubteacher.d2compat.events import EventStorage
     with EventStorage(0) as tr.storage:
-        for it in range(2):
+        for it in range(n_steps):
             tr.iter = it
             lr = tr.optimizer.param_groups[0]["lr"]
             # capture the device pseudo sets by wrapping process_pseudo_label
@@ -213,7 +350,7 @@ def test_teacher_proposals_and_full_step_vs_oracle():
                     assert abs(got[k] - float(v)) <= 4e-2 * abs(float(v)) + 2e-3, (it, k, got[k], float(v))
             tr.scheduler.step()
             tr.storage.step()
-    # after two SGD steps the parameter UPDATES point the same way (fp32 master weights, bf16 gradients) ...
+    # after the SGD steps the parameter UPDATES point the same way (fp32 master weights, bf16 gradients) ...
     sd = tr.model.state_dict()
     for k in ["proposal_generator.fcos_head.cls_logits.bias", "backbone.fpn_output4.weight",
               "backbone.bottom_up.res5.1.conv2.weight"]:
@@ -226,6 +363,19 @@ def test_teacher_proposals_and_full_step_vs_oracle():
     td = tr.model_teacher.state_dict()
     for k in ["proposal_generator.fcos_head.cls_logits.weight", "backbone.bottom_up.stem.conv1.weight"]:
         assert rel(td[k], teacher[k]) < 1e-4, k
+
+
+def test_teacher_proposals_and_full_step_vs_oracle():
+    """Two trainer steps at small resolution; the oracle step is driven with the device's pseudo-label sets
+    (threshold borderlines differ between bf16 and fp32 scores), everything else is independent."""
+    _steps_vs_oracle([(128, 160), (160, 192)], 2, 1, 2, 4)
+
+
+def test_full_size_step_vs_oracle():
+    """BASELINE config #1 on the device: ONE full-size step (1 labeled + 1 unlabeled 3 x 800 x 1333 image -> 800 x 1344,
+    22 400 locations per image, every conv launch with more tiles than SMs) against the oracle step: losses within 4 %,
+    update direction, EMA teacher."""
+    _steps_vs_oracle([(800, 1333)], 1, 1, 1, 7)
 
 
 def test_cuda_graph_step_matches_eager():

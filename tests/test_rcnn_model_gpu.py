@@ -146,8 +146,19 @@ def test_losses_and_gradients_match_oracle(model, branch):
     for k in ("loss_rpn_cls", "loss_rpn_loc", "loss_cls", "loss_box_reg"):   # fp32 loss arithmetic on bf16 activations: 4 %
         torch.testing.assert_close(losses[k].cpu(), ref[k].detach(), rtol=4e-2, atol=2e-3)
     (ref["loss_rpn_cls"] * w[0] + ref["loss_rpn_loc"] * w[1] + ref["loss_cls"] * w[2] + ref["loss_box_reg"] * w[3]).backward()
+    # second oracle run with the device's bf16 rounding points (oracle/ut2_model.py: bf16_points): rounding vs logic
+    from oracle import ut2_model as M
+    params_q = {k: sd[k].clone().requires_grad_(True) for k in tk}
+    sdq = dict(sd)
+    sdq.update(params_q)
+    with M.bf16_points():
+        refq, _ = RM.forward_train(sdq, [b["image"] for b in batch], gt, branch, [kr[i] for i in range(N)], keys_roi, dev_props)
+        (refq["loss_rpn_cls"] * w[0] + refq["loss_rpn_loc"] * w[1] + refq["loss_cls"] * w[2] + refq["loss_box_reg"] * w[3]).backward()
+    for k in ("loss_rpn_cls", "loss_rpn_loc", "loss_cls", "loss_box_reg"):
+        torch.testing.assert_close(losses[k].cpu(), refq[k].detach(), rtol=4e-2, atol=2e-3)
     G = {k: v for k, v in model.named_parameters()}
     sdg = eng.arena.gviews
+    report = []
     for k in GRAD_KEYS:
         gv = sdg[k]
         if k == "roi_heads.box_head.fc1.weight":
@@ -160,8 +171,15 @@ def test_losses_and_gradients_match_oracle(model, branch):
         cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
         ratio = float(a.norm() / (b.norm() + 1e-30))
         # same depth-aware bounds as the FCOS model test (bf16 activations and bf16 back-propagated gradients vs fp32)
-        need = 0.88 if ".res3." in k else 0.93 if ".res4." in k else 0.97 if ".res5." in k else 0.985
-        assert cos > need and 0.8 < ratio < 1.25, (k, cos, ratio)
+        # measured on B200 (profiles/r02_gradient_parity.txt): >= 0.9997 everywhere except fpn_output4 (0.998: a ROI on a
+        # pooler-level borderline) — bf16 rounding of the whole chain; logic is bounded per block in test_model_gpu.py
+        need = 0.995
+        assert cos > need and 0.95 < ratio < 1.05, (k, cos, ratio)
+        bq = params_q[k].grad.double().flatten()
+        report.append((k, cos, ratio, float((a * bq).sum() / (a.norm() * bq.norm() + 1e-30)), float(a.norm() / (bq.norm() + 1e-30))))
+        # bf16-point oracle: the non-differentiable 'tsbetter' mask (c_t > c_s + 0.1) flips on borderline elements
+        assert report[-1][3] > 0.99 and 0.95 < report[-1][4] < 1.05, report[-1]
+    print("\n".join(f"{k:58s} fp32: cos {c:.4f} ratio {r:.3f} | bf16 points: cos {cq:.5f} ratio {rq:.4f}" for k, c, r, cq, rq in report))
     eng.arena.grad.zero_()
 
 
@@ -252,6 +270,141 @@ def test_trainer_steps():
     ref = O.ema_update(s1.cpu(), t1.cpu(), tr.cfg.SEMISUPNET.EMA_KEEP_RATE)
     assert torch.equal(t2.cpu(), ref)
     assert torch.isfinite(tr.last_losses[1]).all()
+
+
+def _rcnn_steps_vs_oracle(sizes, n_steps, n_label, n_unlabel, nbox):
+    """UBRCNNTeacherTrainer.run_step_full_semisup against oracle ut2_rcnn_step (trainer.py:786-912) on the same weights,
+    images and injected sampling keys. The oracle is driven with the device's pseudo-label set and proposal boxes (score /
+    NMS borderlines differ between bf16 and fp32), everything else — anchor labelling + sampling, RPN losses, ROI sampling,
+    ROIAlign, box head, focal / L1 + NLL / tsbetter losses, the loss weights (lambda, 0, lambda, mu), SGD, EMA — is independent."""
+    from oracle import ut2_rcnn_model as RM
+    from util_cfg import rcnn_cfg
+    from ubteacher.arena import _view
+    from ubteacher.d2compat.events import EventStorage
+    from ubteacher.engine import UBRCNNTeacherTrainer
+
+    class Loader:
+        def __init__(self):
+            self.i = 0
+
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            self.i += 1
+            mk = lambda n, seed: make_batch(n, sizes, seed, nbox=nbox)
+            lq, uq = mk(n_label, 100 + self.i), mk(n_unlabel, 200 + self.i)
+            lk = [dict(d, image=torch.flip(d["image"], [0])) for d in lq]
+            uk = [dict(d) for d in uq]
+            return lq, lk, uq, uk
+
+    # a fifth of the recipe's learning rate: with randomly initialised, widened predictors one step at 0.01 can push the
+    # box deltas far enough that the NLL * IoU term of the NEXT step is NaN (in the oracle too, fed the same weights)
+    cfg = rcnn_cfg(**{"SOLVER.BASE_LR": 0.002})
+    tr = UBRCNNTeacherTrainer(cfg, data_loader=Loader())
+    diversify(tr.model)
+    tr.scheduler.warmup_iters = 0
+    tr.scheduler.last_epoch = -1
+    tr.scheduler.step()
+    eng = tr.model.engine
+    Hp, Wp = eng.padded_size(sizes)
+    geom, _ = eng.level_geom(Hp, Wp)
+    nmax = max(2 * n_label, n_unlabel)
+    kr, ko = _inject_keys(tr.model, nmax, geom.A, 21)
+    # a pseudo-label threshold that the randomly initialised teacher actually clears: the median detection score
+    probe = next(Loader())[3]
+    tr.model.train()
+    _, _, dets, _ = tr.model(probe, branch="unsup_data_weak")
+    sc = torch.cat([dets["scores"][i, :int(n)] for i, n in enumerate(dets["count"].cpu().tolist())])
+    assert sc.numel() > 4
+    cfg.defrost()
+    cfg.SEMISUPNET.BBOX_THRESHOLD = float(sc.median())
+    student = cpu_sd(tr.model)
+    init = {k: v.clone() for k, v in student.items()}
+    before = {k: v.clone() for k, v in student.items()}
+    teacher = {k: v.clone() for k, v in student.items()}      # iter == BURN_UP_STEP copies the student first (trainer.py:815-817)
+    mom = {}
+    ref_loader = Loader()
+    ss = cfg.SEMISUPNET
+    with EventStorage(0) as tr.storage:
+        for it in range(n_steps):
+            tr.iter = it
+            lr = tr.optimizer.param_groups[0]["lr"]
+            pend, pseudo_dev = [], []
+            f_orig, p_orig = tr.model.forward_train, tr.process_pseudo_label
+
+            def f_spy(*a, **k):
+                out = f_orig(*a, **k)
+                pend.append(out[1])
+                return out
+
+            def p_spy(*a, **k):
+                out = p_orig(*a, **k)
+                pseudo_dev.append(out[0])
+                return out
+
+            tr.model.forward_train, tr.process_pseudo_label = f_spy, p_spy
+            tr.run_step_full_semisup()
+            tr.model.forward_train, tr.process_pseudo_label = f_orig, p_orig
+            names, vec = tr.last_losses
+            got = dict(zip(names, vec.cpu().tolist()))
+            bs = pseudo_dev[0]
+            cnt = bs.counts.cpu().tolist()
+            assert sum(cnt) > 0, "test needs a non-empty pseudo-label set"
+            pseudo = {"boxes": [bs.boxes[i, :n].cpu() for i, n in enumerate(cnt)], "classes": [bs.classes[i, :n].cpu() for i, n in enumerate(cnt)],
+                      "scores": [bs.scores[i, :n].cpu() for i, n in enumerate(cnt)], "std": [bs.reg_pred_std[i, :n].cpu() for i, n in enumerate(cnt)]}
+            batch = next(ref_loader)
+            props, keys = {}, {}
+            ngt = {"sup": [len(d["boxes"]) for d in batch[0] + batch[1]], "unsup": cnt}
+            for tag, pd in zip(("sup", "unsup"), pend):
+                pc = pd["ctx"]["proposals"]["count"].cpu().tolist()
+                props[tag] = [pd["ctx"]["proposals"]["proposal_boxes"][i, :n].cpu() for i, n in enumerate(pc)]
+                keys["rpn_" + tag] = [kr[i] for i in range(len(pc))]
+                keys["roi_" + tag] = [ko[i, :pc[i] + ngt[tag][i]] for i in range(len(pc))]
+            ocfg = {"UNSUP_LOSS_WEIGHT": ss.UNSUP_LOSS_WEIGHT, "UNSUP_REG_LOSS_WEIGHT": ss.UNSUP_REG_LOSS_WEIGHT,
+                    "EMA_KEEP_RATE": ss.EMA_KEEP_RATE, "BBOX_THRESHOLD": ss.BBOX_THRESHOLD, "WEIGHT_DECAY": cfg.SOLVER.WEIGHT_DECAY,
+                    "MOMENTUM": cfg.SOLVER.MOMENTUM, "LR": lr}
+            rec, grads, _ = RM.ut2_rcnn_step(student, teacher, mom, batch, ocfg, it == 0, keys, pseudo_override=pseudo,
+                                             proposals_override=props)
+            assert set(got) >= {k for k in rec if k.startswith("loss")}
+            for k, v in rec.items():
+                if k.startswith("loss"):       # fp32 loss arithmetic on bf16 activations: 4 %
+                    assert abs(got[k] - float(v)) <= 4e-2 * abs(float(v)) + 2e-3, (it, k, got[k], float(v))
+            # this step's parameter UPDATE (loss weights lambda, 0, lambda, mu; SGD with momentum and weight decay) points the
+            # same way ...
+            sd = cpu_sd(tr.model)
+            for k in ["roi_heads.box_predictor.cls_score.weight", "roi_heads.box_head.fc2.weight", "proposal_generator.rpn_head.conv.weight",
+                      "proposal_generator.rpn_head.anchor_deltas.weight", "backbone.fpn_output3.weight",
+                      "backbone.bottom_up.res5.1.conv2.weight", "backbone.bottom_up.res3.2.conv1.weight"]:
+                a = (sd[k] - before[k]).double().flatten()
+                b = (student[k] - before[k]).double().flatten()
+                assert float((a * b).sum() / (a.norm() * b.norm())) > 0.97, (it, k)
+                assert 0.9 < float(a.norm() / b.norm()) < 1.1, (it, k)
+            # ... frozen parameters did not move and the EMA teacher tracks the oracle's
+            assert torch.equal(sd["backbone.bottom_up.res2.0.conv1.weight"], init["backbone.bottom_up.res2.0.conv1.weight"])
+            td = cpu_sd(tr.model_teacher)
+            for k in ["roi_heads.box_predictor.cls_score.weight", "backbone.bottom_up.stem.conv1.weight", "backbone.fpn_lateral4.weight"]:
+                assert rel(td[k], teacher[k]) < 1e-5, (it, k)
+            # every step is checked from the SAME starting state: re-seed the oracle with the device's student, teacher and
+            # momentum (otherwise step 2 compares two trajectories that have already drifted apart by one bf16 update)
+            A = eng.arena
+            student, teacher = sd, td
+            mom = {k: _view(A.mom, A.offset[k], A.specs[k].shape).detach().cpu().clone().reshape(student[k].shape)
+                   for k in RM.trainable_keys(student)}
+            before = {k: v.clone() for k, v in student.items()}
+            tr.scheduler.step()
+            tr.storage.step()
+    eng.debug_keys = None
+
+
+def test_trainer_step_vs_oracle_step():
+    _rcnn_steps_vs_oracle([(128, 160), (160, 192)], 2, 1, 2, 4)
+
+
+def test_full_size_step_vs_oracle():
+    """BASELINE configs #3 / #5 geometry: ONE full-size step (1 labeled + 1 unlabeled 3 x 800 x 1333 image, 268 569 anchors
+    per image) against the oracle step."""
+    _rcnn_steps_vs_oracle([(800, 1333)], 1, 1, 1, 7)
 
 
 def test_cuda_graph_step_matches_eager():
