@@ -230,9 +230,10 @@ def cpu_step_runner_rcnn(cfg, h, w, n_label=1, n_unlabel=1):
 
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the step cannot run (Detectron2 absent, hard-coded
-    .cuda(): BASELINE.md §2), so this arm times the oracle port of it on the host cores. Each step is a bounded sample:
-    1 labeled + 1 unlabeled image, at a resolution chosen so that K + W steps fit a ~4 minute budget; throughput is
-    reported in full-size-image equivalents (pixels / (800*1344)) per second."""
+    .cuda(): BASELINE.md §2), so this arm times the oracle port of it on the host cores. Each step is a bounded sample of
+    the workload: ONE labeled + ONE unlabeled FULL-SIZE image (3 x 800 x 1333 -> 800 x 1344, BASELINE config #1) at every
+    N, so that the per-N series is comparable. Only if the first (warm-up) step says that K + W such steps would not fit
+    REF_BUDGET_S on this host is the resolution lowered, and then throughput is reported in full-size-image equivalents."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -241,21 +242,22 @@ def run_reference(args):
     cfg = build_cfg(1, 1, device="cpu", arch=args.arch)
     runner = cpu_step_runner if args.arch == "fcos" else cpu_step_runner_rcnn
     port = "oracle/ut2_model.py:ut2_step" if args.arch == "fcos" else "oracle/ut2_rcnn_model.py:ut2_rcnn_step"
-    budget = 240.0
-    # calibrate on a 256x320 step, cost ~ linear in pixels
-    step, cores = runner(cfg, 256, 320)
-    t0 = time.perf_counter()
-    step()
-    t_small = time.perf_counter() - t0
-    per_pixel = t_small / (256 * 320)
-    total = args.steps + args.warmup
-    scale = 1.0
-    for scale in (1.0, 0.75, 0.5, 0.375, 0.25, 0.1875, 0.125):
-        h, w = (800, 1333) if scale == 1.0 else (int(800 * scale) // 32 * 32, int(1333 * scale) // 32 * 32)
-        if per_pixel * h * w * total <= budget:
-            break
+    budget = float(os.environ.get("REF_BUDGET_S", "600"))
+    total = args.steps + max(args.warmup, 1)
+    h, w = 800, 1333
     step, cores = runner(cfg, h, w)
-    for _ in range(args.warmup):
+    t0 = time.perf_counter()
+    step()                                              # warm-up step 1 doubles as the calibration
+    t_full = time.perf_counter() - t0
+    done_warm = 1
+    if t_full * total > budget:                         # a very slow host: shrink the sample (cost ~ linear in pixels)
+        for scale in (0.75, 0.5, 0.375, 0.25, 0.1875, 0.125):
+            h, w = int(800 * scale) // 32 * 32, int(1333 * scale) // 32 * 32
+            if t_full * scale * scale * total <= budget:
+                break
+        step, cores = runner(cfg, h, w)
+        done_warm = 0
+    for _ in range(max(args.warmup - done_warm, 0)):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -264,12 +266,13 @@ def run_reference(args):
     eq_images = 2.0 * (((h + 31) // 32 * 32) * ((w + 31) // 32 * 32)) / FULL_PIXELS
     v = eq_images * args.steps / dt
     sample = (f"oracle port ({port}, fp32 torch CPU), 1 labeled + 1 unlabeled image of {h}x{w} per step "
-              f"({eq_images:.3f} full-size-image equivalents), {args.steps} timed steps")
+              f"({eq_images:.3f} full-size-image equivalents), {args.steps} timed steps after {max(args.warmup, 1)} warm-up")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{ARCH_NAME[args.arch]} UT2 run_step_full_semisup, label {args.label} + unlabel {args.unlabel} per GPU, "
-                                   "synthetic 3x800x1333 (reference arm: bounded CPU sample, see cpu_baseline.sample)"},
+                                   "synthetic 3x800x1333 (reference arm: bounded CPU sample, see cpu_baseline.sample)",
+                       "sample_hw": [h, w], "full_size_sample": (h, w) == (800, 1333)},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -315,6 +318,8 @@ def main():
                          "prediction heads are widened so that every level is full of candidates and pseudo labels survive the "
                          "thresholds (worst-case top-k / NMS / target-assignment load, SURVEY.md 8d)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `extra` arms of the JSON line (saturated regime, the other "
+                    "detector, the recipes' 2 + 2 images per GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -407,7 +412,8 @@ def main():
             with open(os.path.join(ROOT, "profiles", "r01c_traffic.json")) as f:
                 tj = json.load(f)
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-            traffic_note = (f"bytes per launch of the dominant shape {tj['shape']}: algorithmic {tj['algorithmic_bytes']} B; "
+            traffic_note = (f"NOT measured live: read from the committed ncu --set full capture profiles/r01c_traffic.json; "
+                            f"bytes per launch of the dominant shape {tj['shape']}: algorithmic {tj['algorithmic_bytes']} B; "
                             f"`achieved` averages all {len(prof['conv_fwd']) // prof_steps} conv_fwd launches of a step")
         except Exception:  # noqa: BLE001
             pass
@@ -422,6 +428,41 @@ def main():
                 if args.label == args.unlabel else None}
     del tr, loader
     torch.cuda.empty_cache()
+
+    def extra_arm(arch, label, unlabel, regime):
+        """What the driver cannot see otherwise: the same device-timed measurement (inputs resident in HBM,
+        graph replay, max over ranks) for another regime / detector / per-GPU batch, reduced to ms, images/s, step_flops_frac."""
+        T = UBTeacherTrainer if arch == "fcos" else UBRCNNTeacherTrainer
+        c = build_cfg(label * world, unlabel * world, arch=arch)
+        ld = SyntheticTwoCropLoader(label, unlabel, rank=rank, device=dev)
+        t = T(c, data_loader=ld)
+        t.storage = EventStorage(0)
+        t.metrics_period = 10 ** 9
+        t.iter = -1
+        if regime == "saturated":
+            saturate(t, arch)
+        timed(t, 3, False)                       # eager steps before the capture
+        if not args.no_graph:
+            t.enable_cuda_graph(True)
+        timed(t, max(args.warmup, 3), False)
+        sec, nl, _, _, _ = timed(t, args.steps, False)
+        ms = 1e3 * sec / args.steps
+        out = {"workload": f"{ARCH_NAME[arch]} UT2 step, label {label} + unlabel {unlabel} per GPU, {regime} regime, n_gpus {world}",
+               "ms_per_step": ms, "value": world * (label + unlabel) / (ms * 1e-3), "unit": "images/s",
+               "step_flops_frac": FLOP_PER_11[arch] * (label + unlabel) / 2.0 / (ms * 1e-3) / (peak_tf * 1e12) if label == unlabel else None,
+               "pseudo_boxes_per_image": pseudo_stats(t), "gpu_launches": nl}
+        del t, ld
+        torch.cuda.empty_cache()
+        return out
+
+    extra = None
+    if not args.no_extras:
+        other = "rcnn" if args.arch == "fcos" else "fcos"
+        extra = {"saturated" if args.regime == "cold" else "cold":
+                 extra_arm(args.arch, args.label, args.unlabel, "saturated" if args.regime == "cold" else "cold"),
+                 other: extra_arm(other, args.label, args.unlabel, args.regime),
+                 "per_gpu_2": extra_arm(args.arch, 2, 2, args.regime),
+                 other + "_per_gpu_2": extra_arm(other, 2, 2, args.regime)}
     # ---- arm 2: end to end through the public API: pinned host inputs, H2D inside the step, loss read back --
     e2e = None
     if not args.no_e2e:
@@ -445,13 +486,17 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         runner = cpu_step_runner if args.arch == "fcos" else cpu_step_runner_rcnn
         port = "oracle/ut2_model.py:ut2_step" if args.arch == "fcos" else "oracle/ut2_rcnn_model.py:ut2_rcnn_step"
+        torch.set_num_threads(os.cpu_count() or 1)
         step, cores = runner(build_cfg(1, 1, device="cpu", arch=args.arch), 800, 1333)
+        step()                                   # warm-up
+        n_cpu = 3
         t0 = time.perf_counter()
-        step()
-        dt = time.perf_counter() - t0
+        for _ in range(n_cpu):
+            step()
+        dt = (time.perf_counter() - t0) / n_cpu
         cpu = {"value": 2.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"oracle port ({port}, fp32 torch CPU): one full step with 1 labeled + 1 "
-                         f"unlabeled 3x800x1333 image, {dt:.1f} s, no warm-up"}
+               "sample": f"oracle port ({port}, fp32 torch CPU): full steps with 1 labeled + 1 unlabeled 3x800x1333 image "
+                         f"(BASELINE config #1), 1 warm-up + {n_cpu} timed, {dt:.2f} s per step"}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -464,7 +509,7 @@ def main():
                            "l2_policy": "no flush needed: each step streams >10 GB of activations (>> 126 MB L2)",
                            "launch_mode": "eager" if args.no_graph else "whole step replayed as one CUDA graph",
                            "two_crop_augmentation": "device (strong = aug(weak) every step, outside the graph)" if args.augment else "none (pre-made views)"},
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "extra": extra, "gpu_launches": launches, "clocks": clk,
                 "host_wall_s": wall}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -236,6 +236,13 @@ int ut2_fastrcnn_candidates(int N, int Rcap, const void* pred, const float* rois
 int ut2_fastrcnn_gather(int N, int Ccap, int K, int Rcap, const int* keep_idx, const int* keep_cnt, const float* cand_box,
                         const float* cand_score, const int* cand_canon, const void* pred, float* out_box, float* out_score,
                         long long* out_cls, float* out_std, int* out_roi, int* out_cnt, void* stream);
+/* Box2BoxXYXYTransform as a stand-alone operator (ubteacher/modeling/box_regression.py:36-75 get_deltas, :77-129
+ * apply_deltas; the loss / inference kernels above apply the same arithmetic in registers). Boxes [n,4] xyxy f32;
+ * deltas (dl, dr, dd, du) [n, 4*k]; get_deltas divides by size + 1, apply_deltas multiplies by size (reference quirk). */
+int ut2_box2box_xyxy_get_deltas(const float* src_boxes, const float* target_boxes, int n, float wx, float wy, float* deltas,
+                                void* stream);
+int ut2_box2box_xyxy_apply_deltas(const float* deltas, const float* boxes, int n, int k, float wx, float wy, float clamp,
+                                  float* pred_boxes, void* stream);
 int ut2_add_f32_bf16(const float* a, const void* b /* bf16, optional */, void* out, long long n, void* stream);
 int ut2_subsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream);   /* [D2] LastLevelMaxPool */
 

@@ -650,3 +650,57 @@ extern "C" int ut2_subsample2x_nhwc(const void* x, void* y, int N, int H, int W,
   subsample2x_kernel<<<(int)g, 256, 0, STREAM>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), N, H, W, P, Q, C / 8);
   return ut2_check_launch("subsample2x");
 }
+
+// ------------------------------------------------------------------------------------ Box2BoxXYXYTransform (stand-alone)
+// box_regression.py:36-75 / :77-129 as two elementwise kernels for the module-level API (ubteacher/modeling/box_regression.py);
+// the training / inference kernels above apply the same arithmetic in registers. Round-to-nearest intrinsics in the
+// reference's evaluation order (no FMA contraction): bit-identical to the torch CPU result.
+__global__ void box2box_xyxy_get_deltas_kernel(const float4* __restrict__ src, const float4* __restrict__ tgt, int n, float wx, float wy,
+                                               float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 s = src[i], t = tgt[i];                       // (l, d, r, u) = (x1, y1, x2, y2)
+  const float w = __fadd_rn(__fsub_rn(s.z, s.x), 1.f), h = __fadd_rn(__fsub_rn(s.w, s.y), 1.f);
+  float4 o;
+  o.x = __fdiv_rn(__fmul_rn(wx, __fsub_rn(t.x, s.x)), w);    // dl
+  o.y = __fdiv_rn(__fmul_rn(wx, __fsub_rn(t.z, s.z)), w);    // dr
+  o.z = __fdiv_rn(__fmul_rn(wy, __fsub_rn(t.y, s.y)), h);    // dd
+  o.w = __fdiv_rn(__fmul_rn(wy, __fsub_rn(t.w, s.w)), h);    // du
+  out[i] = o;
+}
+
+__global__ void box2box_xyxy_apply_deltas_kernel(const float* __restrict__ deltas, const float4* __restrict__ boxes, int n, int k,
+                                                 float wx, float wy, float clamp, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * k) return;
+  const float4 b = boxes[i / k];
+  const float4 d = reinterpret_cast<const float4*>(deltas)[i];
+  const float w = __fsub_rn(b.z, b.x), h = __fsub_rn(b.w, b.y);          // NO +1 here (the reference's asymmetry)
+  const float dl = fminf(fmaxf(__fdiv_rn(d.x, wx), -clamp), clamp), dr = fminf(fmaxf(__fdiv_rn(d.y, wx), -clamp), clamp);
+  const float dd = fminf(fmaxf(__fdiv_rn(d.z, wy), -clamp), clamp), du = fminf(fmaxf(__fdiv_rn(d.w, wy), -clamp), clamp);
+  float4 o;
+  o.x = __fadd_rn(__fmul_rn(dl, w), b.x);
+  o.y = __fadd_rn(__fmul_rn(dd, h), b.y);
+  o.z = __fadd_rn(__fmul_rn(dr, w), b.z);
+  o.w = __fadd_rn(__fmul_rn(du, h), b.w);
+  reinterpret_cast<float4*>(out)[i] = o;
+}
+
+extern "C" int ut2_box2box_xyxy_get_deltas(const float* src_boxes, const float* target_boxes, int n, float wx, float wy, float* deltas,
+                                           void* stream) {
+  if (n <= 0) return 0;
+  if (!src_boxes || !target_boxes || !deltas) return ut2_fail(-1, "box2box_get_deltas: null pointer");
+  box2box_xyxy_get_deltas_kernel<<<(n + 255) / 256, 256, 0, STREAM>>>(reinterpret_cast<const float4*>(src_boxes),
+                                                                     reinterpret_cast<const float4*>(target_boxes), n, wx, wy,
+                                                                     reinterpret_cast<float4*>(deltas));
+  return ut2_check_launch("box2box_get_deltas");
+}
+
+extern "C" int ut2_box2box_xyxy_apply_deltas(const float* deltas, const float* boxes, int n, int k, float wx, float wy, float clamp,
+                                             float* pred_boxes, void* stream) {
+  if (n <= 0 || k <= 0) return 0;
+  if (!deltas || !boxes || !pred_boxes) return ut2_fail(-1, "box2box_apply_deltas: null pointer");
+  box2box_xyxy_apply_deltas_kernel<<<(n * k + 255) / 256, 256, 0, STREAM>>>(deltas, reinterpret_cast<const float4*>(boxes), n, k, wx, wy,
+                                                                           clamp, pred_boxes);
+  return ut2_check_launch("box2box_apply_deltas");
+}

@@ -117,7 +117,13 @@ class FcosEngine(EngineBase):
         tape = {} if train else None
         feats, sizes, (Hp, Wp) = self.trunk_forward(images, train, tape)
         geom = self.level_geom(Hp, Wp)
-        # FPN
+        feat = self.fpn_forward(feats, geom, N, tape)
+        cls_out, box_out = self.head_forward(feat, geom, N, tape)
+        return {"cls_out": cls_out, "box_out": box_out, "geom": geom, "N": N, "image_sizes": sizes, "tape": tape,
+                "padded": (Hp, Wp), "scales": self.scales, "feat": feat}
+
+    def fpn_forward(self, feats, geom, N, tape=None):
+        """FPN over res3..res5 + LastLevelP6P7 (backbone/fpn.py:11-78). Returns the level-major pyramid [N * L, 256]."""
         c3, c4, c5 = feats["res3"], feats["res4"], feats["res5"]
         lat5 = self.fpn_lat[5].fwd(c5)
         lat4 = self.fpn_lat[4].fwd(c4, residual=lat5, res_up2=True)
@@ -126,16 +132,24 @@ class FcosEngine(EngineBase):
         # and predictors share their weights across levels (fcos.py:338-376), so every head layer below is a single
         # launch over the whole pyramid instead of five (the 273- and 77-location levels cannot fill 148 SMs alone).
         feat = torch.empty((geom.L * N, 256), dtype=BF16, device=self.device)
-        lv = [feat[geom.off[l] * N: geom.off[l + 1] * N].view(N, geom.hw[l][0], geom.hw[l][1], 256) for l in range(5)]
-        p3 = self.fpn_out[3].fwd(lat3, out=lv[0])
-        p4 = self.fpn_out[4].fwd(lat4, out=lv[1])
+        lv = self.level_views(feat, geom, N, 256)
+        self.fpn_out[3].fwd(lat3, out=lv[0])
+        self.fpn_out[4].fwd(lat4, out=lv[1])
         p5 = self.fpn_out[5].fwd(lat5, out=lv[2])
         p6 = self.p6.fwd(p5, out=lv[3])
         p6r = ops.relu_bwd(p6, p6)              # relu(p6) = p6 * (p6 > 0)
         self.p7.fwd(p6r, out=lv[4])
-        if train:
+        if tape is not None:
             tape["fpn"] = (c3, c4, c5, lat3, lat4, lat5, p5, p6, p6r)
-        # head
+        return feat
+
+    @staticmethod
+    def level_views(buf, geom, N, C):
+        return [buf[geom.off[l] * N: geom.off[l + 1] * N].view(N, geom.hw[l][0], geom.hw[l][1], C) for l in range(geom.num)]
+
+    def head_forward(self, feat, geom, N, tape=None):
+        """FCOSHead (fcos/fcos.py:338-376) over the level-major pyramid: (cls_out [P, 80], box_out [P, 80] = bbox_pred(68,
+        BEFORE Scale_l) | bbox_pred_std(4) | ctrness(1) | 7 zero columns)."""
         Ptot = geom.L * N
         cls_out = torch.empty((Ptot, 80), dtype=BF16, device=self.device)
         box_out = torch.empty((Ptot, 80), dtype=BF16, device=self.device)
@@ -151,17 +165,24 @@ class FcosEngine(EngineBase):
                 xx = y
             pred.fwd_levels(xx, geom, N, out=out)
             head_tape[t] = (saved, xx)
-        if train:
+        if tape is not None:
             tape["head"] = head_tape
             tape["N"] = N
-        return {"cls_out": cls_out, "box_out": box_out, "geom": geom, "N": N, "image_sizes": sizes, "tape": tape,
-                "padded": (Hp, Wp), "scales": self.scales}
+        return cls_out, box_out
 
     # ------------------------------------------------------------------------------------ backward
     def backward(self, fwd, dcls, dbox):
         """Back-propagate d(loss)/d(cls_out), d(loss)/d(box_out) through head, FPN and res5..res3,
         accumulating into the gradient arena (wgrad uses fp32 atomics, so repeated calls add up)."""
         tape, geom, N = fwd["tape"], fwd["geom"], fwd["N"]
+        dfeat = self.head_backward(tape, geom, N, dcls, dbox)
+        extra = self.fpn_backward(tape, geom, N, dfeat)
+        # trunk: res5 <- dc5 ; res4 <- dc4 + d(res5 input) ; res3 <- dc3 + d(res4 input)
+        self.trunk_backward(tape, extra)
+        return None
+
+    def head_backward(self, tape, geom, N, dcls, dbox):
+        """-> d(loss)/d(pyramid) [N * L, 256] (the two towers' input gradients summed in the last dgrad epilogue)."""
         ctx = tape["head"]
         acc = None
         for t, pred, dout in (("cls_tower", self.cls_logits, dcls), ("bbox_tower", self.box_pred, dbox)):
@@ -176,8 +197,11 @@ class FcosEngine(EngineBase):
                 conv.wgrad_levels(xin, dc, geom, N, bias_done=True)   # bias gradient came out of the GroupNorm backward
                 dx = conv.dgrad_levels(dc, geom, N, residual=acc if i == 0 else None)
             acc = dx
-        d3, d4, d5, d6, d7 = [acc[geom.off[l] * N: geom.off[l + 1] * N].view(N, geom.hw[l][0], geom.hw[l][1], 256)
-                              for l in range(5)]
+        return acc
+
+    def fpn_backward(self, tape, geom, N, dfeat):
+        """-> {"res5": dC5, "res4": dC4, "res3": dC3}: gradients leaving the FPN laterals towards the trunk."""
+        d3, d4, d5, d6, d7 = self.level_views(dfeat, geom, N, 256)
         c3, c4, c5, lat3, lat4, lat5, p5, p6, p6r = tape["fpn"]
         hw = geom.hw
         self.p7.wgrad(p6r, d7)
@@ -199,7 +223,4 @@ class FcosEngine(EngineBase):
         dc3 = self.fpn_lat[3].dgrad(dl3, hw[0])
         dc4 = self.fpn_lat[4].dgrad(dl4, hw[1])
         dc5 = self.fpn_lat[5].dgrad(dl5, hw[2])
-        # trunk: res5 <- dc5 ; res4 <- dc4 + d(res5 input) ; res3 <- dc3 + d(res4 input)
-        self.trunk_backward(tape, {"res5": dc5, "res4": dc4, "res3": dc3})
-        return None
-
+        return {"res5": dc5, "res4": dc4, "res3": dc3}

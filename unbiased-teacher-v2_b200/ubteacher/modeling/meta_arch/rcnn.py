@@ -94,6 +94,14 @@ class TwoStagePseudoLabGeneralizedRCNN(nn.Module):
         if not str(dev).startswith("cuda"):
             raise RuntimeError("the UT2 B200 path has no CPU fallback: MODEL.DEVICE must be a CUDA device")
         self.engine = RcnnEngine(cfg, device=dev, seed=max(cfg.SEED, 0))
+        # the reference's sub-modules, looked up by their registry names ([D2] GeneralizedRCNN.from_config), as views that
+        # share this replica's engine: model.proposal_generator(images, features, gt) / model.roi_heads(images, features, ...)
+        from ..proposal_generator import rpn as _rpn  # noqa: F401  (registers PseudoLabRPN)
+        from ..roi_heads import roi_heads as _rh  # noqa: F401  (registers StandardROIHeadsPseudoLab)
+        from ..backbone.fpn import RcnnResnetFpnBackbone
+        self.backbone = RcnnResnetFpnBackbone(cfg, None, engine=self.engine)
+        self.proposal_generator = PROPOSAL_GENERATOR_REGISTRY.get(cfg.MODEL.PROPOSAL_GENERATOR.NAME)(cfg, None, engine=self.engine)
+        self.roi_heads = ROI_HEADS_REGISTRY.get(cfg.MODEL.ROI_HEADS.NAME)(cfg, None, engine=self.engine)
         self._trigger = torch.zeros(1, device=dev, requires_grad=True)
         self._params = None
         self._gout_cache = {}
@@ -136,6 +144,10 @@ class TwoStagePseudoLabGeneralizedRCNN(nn.Module):
     # ---- forward ---------------------------------------------------------------------------------
     def _images(self, batched_inputs):
         return [x["image"].to(self.device, non_blocking=True) for x in batched_inputs]
+
+    def preprocess_image(self, batched_inputs):
+        from ..one_stage_detector import U8Images
+        return U8Images(self._images(batched_inputs), self.engine.pixel_mean, self.engine.pixel_std)
 
     def _gt(self, batched_inputs):
         g = batched_inputs[0]["instances"]
@@ -195,24 +207,3 @@ class TwoStagePseudoLabGeneralizedRCNN(nn.Module):
             self._gout_cache[key] = (t[0:2].contiguous(), t[2:4].contiguous())
         g_rpn, g_roi = self._gout_cache[key]
         self._run_backward(pending, g_rpn, g_roi)
-
-
-@PROPOSAL_GENERATOR_REGISTRY.register()
-class PseudoLabRPN:
-    """Name kept for config compatibility (modeling/proposal_generator/rpn.py:15); the computation lives in
-    RcnnEngine.forward_features / forward_losses / proposals and csrc/rpn.cu."""
-
-    def __init__(self, engine):
-        self.engine = engine
-
-    def __call__(self, fwd, gt=None, compute_loss=True):
-        return self.engine.proposals(fwd)
-
-
-@ROI_HEADS_REGISTRY.register()
-class StandardROIHeadsPseudoLab:
-    """Name kept for config compatibility (modeling/roi_heads/roi_heads.py:23); see RcnnEngine.box_head /
-    forward_losses / forward_inference and csrc/roi.cu."""
-
-    def __init__(self, engine):
-        self.engine = engine

@@ -13,10 +13,35 @@ Loss tensors are attached to autograd through one custom Function per forward ca
 import torch
 from torch import nn
 
-from ..d2compat.registry import META_ARCH_REGISTRY
+from ..d2compat.registry import BACKBONE_REGISTRY, META_ARCH_REGISTRY, PROPOSAL_GENERATOR_REGISTRY
 from ..d2compat.structures import Instances, detector_postprocess
+from .backbone import fpn as _fpn  # noqa: F401  (registers build_fcos_resnet_fpn_backbone)
+from .fcos import fcos as _fcos  # noqa: F401  (registers FCOS)
 from .fcos.fcos_outputs import BoxSet, FCOSOutputs, as_boxset, dets_to_instances
 from .fcos_engine import FcosEngine
+
+
+class U8Images:
+    """What ``preprocess_image`` returns here: the batch's uint8 BGR images on the device + their sizes. The reference
+    builds a normalised, zero-padded float ``ImageList`` (one_stage_detector.py:165-167); normalisation and padding are
+    fused into the stem kernel, so only ``image_sizes`` (and, lazily, ``tensor``) of that interface are kept."""
+
+    def __init__(self, images_u8, pixel_mean, pixel_std, div=32):
+        self.images_u8 = images_u8
+        self.image_sizes = [(int(im.shape[1]), int(im.shape[2])) for im in images_u8]
+        self._mean, self._std, self._div = pixel_mean, pixel_std, div
+
+    def __len__(self):
+        return len(self.images_u8)
+
+    @property
+    def tensor(self):
+        """The reference's normalised, zero-padded [N, 3, H, W] float batch (compatibility only: not used by the engine)."""
+        from ..d2compat.structures import ImageList
+        dev = self.images_u8[0].device
+        m = torch.tensor(self._mean, device=dev).view(3, 1, 1)
+        s = torch.tensor(self._std, device=dev).view(3, 1, 1)
+        return ImageList.from_tensors([(im.float() - m) / s for im in self.images_u8], self._div).tensor
 
 
 class _LossGraph(torch.autograd.Function):
@@ -47,6 +72,11 @@ class PseudoProposalNetwork(nn.Module):
         self.engine = FcosEngine(cfg, device=dev, seed=max(cfg.SEED, 0))
         self.fcos_outputs = FCOSOutputs(cfg)
         self.yield_proposal = cfg.MODEL.FCOS.YIELD_PROPOSAL
+        # the reference's sub-modules, looked up by their registry names (one_stage_detector.py:52-55), as views that
+        # share this replica's engine: model.backbone(images) / model.proposal_generator(images, features, gt, ...)
+        self.backbone = BACKBONE_REGISTRY.get(cfg.MODEL.BACKBONE.NAME)(cfg, None, engine=self.engine)
+        self.proposal_generator = PROPOSAL_GENERATOR_REGISTRY.get(cfg.MODEL.PROPOSAL_GENERATOR.NAME)(
+            cfg, self.backbone.output_shape(), engine=self.engine, fcos_outputs=self.fcos_outputs)
         self._trigger = torch.zeros(1, device=dev, requires_grad=True)
         self._params = None
         self._gout_cache = {}
@@ -95,6 +125,9 @@ class PseudoProposalNetwork(nn.Module):
     # ---- forward ----------------------------------------------------------------------------------
     def _images(self, batched_inputs):
         return [x["image"].to(self.device, non_blocking=True) for x in batched_inputs]
+
+    def preprocess_image(self, batched_inputs):
+        return U8Images(self._images(batched_inputs), self.engine.pixel_mean, self.engine.pixel_std)
 
     def _scales(self):
         return self.engine.scales

@@ -126,34 +126,50 @@ class RcnnEngine(EngineBase):
         tape = {} if train else None
         feats, sizes, (Hp, Wp) = self.trunk_forward(images, train, tape)
         geom, rgeom = self.level_geom(Hp, Wp)
+        feat, levels = self.fpn_forward(feats, geom, N, tape)
+        rpn_out = self.rpn_head_forward(feat, geom, N, tape)
+        return {"rpn_out": rpn_out, "levels": levels, "geom": geom, "rgeom": rgeom, "N": N, "image_sizes": sizes,
+                "image_hw": self.image_hw(sizes), "tape": tape, "padded": (Hp, Wp), "feat": feat}
+
+    @staticmethod
+    def level_views(buf, geom, N, C):
+        return [buf[geom.off[l] * N: geom.off[l + 1] * N].view(N, geom.hw[l][0], geom.hw[l][1], C) for l in range(geom.num)]
+
+    def fpn_forward(self, feats, geom, N, tape=None):
+        """[D2] FPN over res2..res5 + LastLevelMaxPool. FPN outputs p2..p6 live in ONE level-major buffer
+        [N * sum(H_l W_l), 256]: the RPN head shares its weights across levels (rpn.py:31), so its 3x3 conv and the fused
+        predictor are one launch each over the pyramid. Returns (buffer, per-level NHWC views)."""
         c2, c3, c4, c5 = feats["res2"], feats["res3"], feats["res4"], feats["res5"]
         lat5 = self.fpn_lat[5].fwd(c5)
         lat4 = self.fpn_lat[4].fwd(c4, residual=lat5, res_up2=True)
         lat3 = self.fpn_lat[3].fwd(c3, residual=lat4, res_up2=True)
         lat2 = self.fpn_lat[2].fwd(c2, residual=lat3, res_up2=True)
-        # FPN outputs p2..p6 live in ONE level-major buffer [N * sum(H_l W_l), 256]: the RPN head shares its weights
-        # across levels (rpn.py:31), so its 3x3 conv and the fused predictor are one launch each over the pyramid.
         feat = torch.empty((geom.L * N, 256), dtype=BF16, device=self.device)
-        levels = [feat[geom.off[l] * N: geom.off[l + 1] * N].view(N, geom.hw[l][0], geom.hw[l][1], 256) for l in range(5)]
+        levels = self.level_views(feat, geom, N, 256)
         self.fpn_out[5].fwd(lat5, out=levels[3])
         self.fpn_out[4].fwd(lat4, out=levels[2])
         self.fpn_out[3].fwd(lat3, out=levels[1])
         self.fpn_out[2].fwd(lat2, out=levels[0])
         R.subsample2x(levels[3], out=levels[4])      # [D2] LastLevelMaxPool: max_pool2d(kernel 1, stride 2)
+        if tape is not None:
+            tape["fpn"] = (c2, c3, c4, c5, lat2, lat3, lat4, lat5)
+        return feat, levels
+
+    def rpn_head_forward(self, feat, geom, N, tape=None):
+        """[D2] StandardRPNHead over the level-major pyramid -> rpn_out [N * L, 16] = 3 objectness | 12 deltas | pad."""
         hidden = self.rpn_conv.fwd_levels(feat, geom, N, relu=True)
         rpn_out = torch.empty((geom.L * N, R.RPN_LD), dtype=BF16, device=self.device)
         self.rpn_pred.fwd_levels(hidden, geom, N, out=rpn_out)
-        fwd_feat = feat
-        if train:
-            tape["fpn"] = (c2, c3, c4, c5, lat2, lat3, lat4, lat5)
+        if tape is not None:
             tape["rpn_hidden"] = hidden
-            tape["feat"] = fwd_feat
+            tape["feat"] = feat
+        return rpn_out
+
+    def image_hw(self, sizes):
         key = tuple(map(tuple, sizes))
         if key not in self._image_hw:               # cached: no pinned temporary inside a graph capture
             self._image_hw[key] = torch.tensor(sizes, dtype=torch.float32).pin_memory().to(self.device, non_blocking=True)
-        image_hw = self._image_hw[key]
-        return {"rpn_out": rpn_out, "levels": levels, "geom": geom, "rgeom": rgeom, "N": N, "image_sizes": sizes,
-                "image_hw": image_hw, "tape": tape, "padded": (Hp, Wp)}
+        return self._image_hw[key]
 
     def proposals(self, fwd, test=False):
         """[D2] find_top_rpn_proposals (rpn.py:72-74). The teacher is never put in eval mode (trainer.py:628-629,
@@ -177,23 +193,35 @@ class RcnnEngine(EngineBase):
     def forward_losses(self, fwd, gt, pseudo):
         """supervised / unsup_data_train branches (rcnn.py:26-40, :57-72). gt: BoxSet (boxes, classes, counts and, for
         pseudo labels, scores + reg_pred_std = the teacher's pred_boxes_std). Returns (losses float[4] parts, ctx)."""
+        rpn_losses, ctx = self.rpn_losses(fwd, gt, pseudo)
+        props = self.proposals(fwd)
+        roi_losses, rctx = self.roi_losses(fwd, props, gt, pseudo)
+        ctx.update(rctx)
+        ctx["proposals"] = props
+        return rpn_losses, roi_losses, ctx
+
+    def rpn_losses(self, fwd, gt, pseudo):
+        """PseudoLabRPN: anchor labelling + sampling, objectness BCE (x teacher score for pseudo labels) and L1 box loss."""
         N, geom = fwd["N"], fwd["geom"]
         scores = gt.scores if pseudo else None
         dk = getattr(self, "debug_keys", None) or {}       # parity tests inject the sampling draws (else: hashed seed)
         labels, matched = R.rpn_label_anchors(geom, N, gt.boxes, gt.counts, keys=dk.get("rpn"), seed=self._next_seed(), batch=self.rpn_batch,
                                               pos_frac=self.rpn_pos_frac, lo=self.rpn_thr[0], hi=self.rpn_thr[1], seed_dev=self.seed_dev)
-        rpn_losses = R.rpn_loss_fwd(geom, N, fwd["rpn_out"], labels, matched, gt.boxes, scores, gt.counts, self.rpn_batch)
-        props = self.proposals(fwd)
+        losses = R.rpn_loss_fwd(geom, N, fwd["rpn_out"], labels, matched, gt.boxes, scores, gt.counts, self.rpn_batch)
+        return losses, {"labels": labels, "matched": matched, "gt": gt, "scores": scores}
+
+    def roi_losses(self, fwd, props, gt, pseudo):
+        """StandardROIHeadsPseudoLab: append GT, match, sample 512 ROIs, ROIAlign, box head, focal + box losses."""
+        dk = getattr(self, "debug_keys", None) or {}
+        scores = gt.scores if pseudo else None
         s = R.roi_sample(props["proposal_boxes"], props["count"], gt.boxes, gt.classes, gt.counts, scores,
                          gt.reg_pred_std if pseudo else None, keys=dk.get("roi"), seed=self._next_seed(), batch=self.roi_batch,
                          pos_frac=self.roi_pos_frac, iou_thr=self.roi_iou, num_classes=self.num_classes, append_gt=self.append_gt,
                          seed_dev=self.seed_dev)
         pred = self.box_head(fwd, s["proposal_boxes"], s["count"], True)
         mode = 1 if pseudo else 0
-        roi_losses = R.fastrcnn_loss_fwd(pred, s, mode, self.box_w, ts_better=self.ts_better, t_cert=self.t_cert)
-        ctx = {"labels": labels, "matched": matched, "gt": gt, "scores": scores, "sample": s, "pred": pred, "mode": mode,
-               "proposals": props}
-        return rpn_losses, roi_losses, ctx
+        losses = R.fastrcnn_loss_fwd(pred, s, mode, self.box_w, ts_better=self.ts_better, t_cert=self.t_cert)
+        return losses, {"sample": s, "pred": pred, "mode": mode}
 
     def forward_inference(self, fwd, test=False):
         """unsup_data_weak branch (rcnn.py:42-55): proposals -> box head on all of them -> fast_rcnn_inference."""
@@ -209,21 +237,37 @@ class RcnnEngine(EngineBase):
         """gout_rpn / gout_roi: float[2] device tensors = d(total)/d{loss_rpn_cls, loss_rpn_loc} / d{loss_cls, loss_box_reg}.
         Accumulates into the gradient arena (wgrad uses fp32 atomics, so repeated calls add up)."""
         tape, geom, N = fwd["tape"], fwd["geom"], fwd["N"]
+        dlev = self.roi_backward(fwd, ctx, gout_roi)
+        dfe = self.rpn_backward(fwd, ctx, gout_rpn)
+        extra = self.fpn_backward(tape, geom, N, dfe, dlev)
+        self.trunk_backward(tape, extra)
+
+    def roi_backward(self, fwd, ctx, gout_roi):
+        """Box-head backward -> fp32 gradient maps of p2..p5 (ROIAlign backward accumulates with atomics)."""
+        tape = fwd["tape"]
         s = ctx["sample"]
         Rtot = s["gt_classes"].numel()
-        # ---- box head
         dpred = R.fastrcnn_loss_bwd(ctx["pred"], s, ctx["mode"], gout_roi, self.box_w, ts_better=self.ts_better,
                                     t_cert=self.t_cert).view(1, 1, Rtot, R.PRED_LD)
+        dpool = self.box_head_backward(tape, dpred)
+        dlev = [torch.zeros(f.shape, dtype=torch.float32, device=self.device) for f in fwd["levels"][:4]]
+        R.roi_align_bwd(fwd["rgeom"], dlev, s["proposal_boxes"], s["count"], dpool)
+        return dlev
+
+    def box_head_backward(self, tape, dpred):
+        """fused predictor <- fc2 <- fc1: weight gradients into the arena, returns d(pooled) [1, 1, R, 12544]."""
+        Rtot = dpred.shape[2]
         x, h1, h2 = tape["box"]
         self.box_pred.wgrad(h2, dpred)
         dh2 = self.box_pred.dgrad(dpred, (1, Rtot), relu_mask=h2)
         self.fc2.wgrad(h1, dh2)
         dh1 = self.fc2.dgrad(dh2, (1, Rtot), relu_mask=h1)
         self.fc1.wgrad(x, dh1)
-        dpool = self.fc1.dgrad(dh1, (1, Rtot))                                        # [1, 1, R, 12544]
-        dlev = [torch.zeros(f.shape, dtype=torch.float32, device=self.device) for f in fwd["levels"][:4]]
-        R.roi_align_bwd(fwd["rgeom"], dlev, s["proposal_boxes"], s["count"], dpool)
-        # ---- RPN head
+        return self.fc1.dgrad(dh1, (1, Rtot))
+
+    def rpn_backward(self, fwd, ctx, gout_rpn):
+        """RPN losses -> level-major gradient of the pyramid [N * L, 256]."""
+        tape, geom, N = fwd["tape"], fwd["geom"], fwd["N"]
         gt = ctx["gt"]
         drpn = R.rpn_loss_bwd(geom, N, fwd["rpn_out"], ctx["labels"], ctx["matched"], gt.boxes, ctx["scores"], gt.counts,
                               gout_rpn, self.rpn_batch)
@@ -231,15 +275,17 @@ class RcnnEngine(EngineBase):
         self.rpn_pred.wgrad_levels(t, drpn, geom, N)
         dt = self.rpn_pred.dgrad_levels(drpn, geom, N, relu_mask=t)
         self.rpn_conv.wgrad_levels(tape["feat"], dt, geom, N)
-        dfe = self.rpn_conv.dgrad_levels(dt, geom, N)
+        return self.rpn_conv.dgrad_levels(dt, geom, N)
+
+    def fpn_backward(self, tape, geom, N, dfe, dlev):
+        """dfe: level-major bf16 gradient of p2..p6 (RPN), dlev: fp32 gradients of p2..p5 (ROI heads) or None.
+        -> {"res5": dC5, "res4": dC4, "res3": dC3}."""
         dP = []
-        for l in range(5):
-            g = dfe[geom.off[l] * N: geom.off[l + 1] * N].view(N, geom.hw[l][0], geom.hw[l][1], 256)
-            dP.append(R.add_f32_bf16(dlev[l], g) if l < 4 else g)
+        for l, g in enumerate(self.level_views(dfe, geom, N, 256)):
+            dP.append(R.add_f32_bf16(dlev[l], g) if (l < 4 and dlev is not None) else g)
         d2, d3, d4, d5, d6 = dP
         hw = geom.hw
         d5 = ops.add_bf16(d5, ops.zero_stuff_s2(d6, hw[3][0], hw[3][1]))              # p6 = p5[:, ::2, ::2]
-        # ---- FPN
         c2, c3, c4, c5, lat2, lat3, lat4, lat5 = tape["fpn"]
         dl = {}
         for lvl, lat, d in ((5, lat5, d5), (4, lat4, d4), (3, lat3, d3), (2, lat2, d2)):
@@ -254,4 +300,4 @@ class RcnnEngine(EngineBase):
         dc3 = self.fpn_lat[3].dgrad(dl[3], hw[1])
         dc4 = self.fpn_lat[4].dgrad(dl[4], hw[2])
         dc5 = self.fpn_lat[5].dgrad(dl[5], hw[3])
-        self.trunk_backward(tape, {"res5": dc5, "res4": dc4, "res3": dc3})
+        return {"res5": dc5, "res4": dc4, "res3": dc3}
