@@ -1,4 +1,5 @@
-"""__graft_entry__.smoke(): one small invocation of the hot path on cuda:0, checked against the CPU oracle.
+"""TEST INFRASTRUCTURE (lives beside __graft_entry__.py, outside the product package: it imports the oracle).
+__graft_entry__.smoke(): one small invocation of the hot path on cuda:0, checked against the CPU oracle.
 
 1+1 images at 128x160: EMA copy, teacher forward + two NMS criteria + pseudo-label thresholding, student
 forward/backward on the labeled and unlabeled batches, SGD — then the supervised losses are compared with
@@ -12,22 +13,23 @@ import torch
 def run():
     if not torch.cuda.is_available():
         raise RuntimeError("smoke() needs cuda:0 (the UT2 B200 path has no CPU fallback)")
-    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    if root not in sys.path:
-        sys.path.insert(0, root)
+    root = os.path.dirname(os.path.abspath(__file__))
+    pkg = os.path.join(root, "unbiased-teacher-v2_b200")
+    for p in (root, pkg):
+        if p not in sys.path:
+            sys.path.insert(0, p)
     from oracle import ut2_model as M
     from oracle import ut2_oracle as O
 
-    from . import _C
-    from .config import add_ubteacher_config
-    from .d2compat.config import get_cfg
-    from .d2compat.events import EventStorage
-    from .data.synthetic import SyntheticTwoCropLoader
-    from .engine import UBTeacherTrainer
+    from ubteacher import _C
+    from ubteacher.config import add_ubteacher_config
+    from ubteacher.d2compat.config import get_cfg
+    from ubteacher.d2compat.events import EventStorage
+    from ubteacher.data.synthetic import SyntheticTwoCropLoader
+    from ubteacher.engine import UBTeacherTrainer
 
     cfg = get_cfg()
     add_ubteacher_config(cfg)
-    pkg = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cfg.merge_from_file(os.path.join(pkg, "configs/FCOS/coco-standard/fcos_R_50_ut2_sup1_run0.yaml"))
     cfg.merge_from_list(["SEMISUPNET.BURN_UP_STEP", 0, "SOLVER.IMG_PER_BATCH_LABEL", 1, "SOLVER.IMG_PER_BATCH_UNLABEL", 1,
                          "MODEL.DEVICE", "cuda:0", "SEED", 7])

@@ -12,6 +12,7 @@ What changed underneath (B200-first, same arithmetic):
   * metrics are stacked on the device and read back once every `metrics_period` iterations.
 """
 import logging
+import os
 import time
 
 import numpy as np
@@ -26,6 +27,23 @@ from ..modeling.pseudo_generator import PseudoGenerator
 from ..solver.lr_scheduler import WarmupMultiStepLR
 
 logger = logging.getLogger(__name__)
+_NVTX = os.environ.get("UT2_NVTX", "1") != "0"
+
+
+class nvtx_range:
+    """NVTX phase range (tracing). Host-side markers only: legal during CUDA-graph capture, visible in an
+    Nsight Systems timeline of the eager steps; the replayed step shows up as one `ut2.step.graph_replay` range."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
 
 
 class ArenaSGD:
@@ -320,7 +338,8 @@ class UBTeacherTrainer:
             _C.launch_count = l0
             self._graph_names = self.last_losses[0]
             self._graph_vec = self.last_losses[1]
-        self._graph.replay()
+        with nvtx_range("ut2.step.graph_replay"):
+            self._graph.replay()
         self._prefetch_next()
         from .. import _C
         _C.launch_count += self._graph_launches      # kernels inside the replayed graph
@@ -347,35 +366,46 @@ class UBTeacherTrainer:
                 ema_keep_rate = ss.EMA_KEEP_RATE
             record["ema_rate_1000x"] = ema_keep_rate * 1000
             # teacher on the weak views (trainer.py:231-237) + second NMS criterion (:240-242)
-            pred_teacher, raw_pred_teacher = self.model_teacher(
-                unlabel_data_k, output_raw=True, nms_method=cfg.MODEL.FCOS.NMS_CRITERIA_TRAIN, branch="teacher_weak")
-            raw_pred_teacher["scales"] = self.model_teacher.engine.scales
-            pred_teacher_loc = self.pseudo_generator.nms_from_dense(raw_pred_teacher, cfg.MODEL.FCOS.NMS_CRITERIA_REG_TRAIN)
-            thr = self._threshold(ss.PSEUDO_BBOX_SAMPLE, ss.BBOX_THRESHOLD, ss.BBOX_CTR_THRESHOLD)
-            thr_reg = self._threshold(ss.PSEUDO_BBOX_SAMPLE_REG, ss.BBOX_THRESHOLD_REG, ss.BBOX_CTR_THRESHOLD_REG)
-            pseudo_cls, _ = self.pseudo_generator.process_pseudo_label(pred_teacher, thr, "roih", ss.PSEUDO_BBOX_SAMPLE)
-            pseudo_reg, _ = self.pseudo_generator.process_pseudo_label(pred_teacher_loc, thr_reg, "roih",
-                                                                       ss.PSEUDO_BBOX_SAMPLE_REG)
+            with nvtx_range("ut2.teacher_forward"):
+                pred_teacher, raw_pred_teacher = self.model_teacher(
+                    unlabel_data_k, output_raw=True, nms_method=cfg.MODEL.FCOS.NMS_CRITERIA_TRAIN, branch="teacher_weak")
+            with nvtx_range("ut2.pseudo_labels"):
+                raw_pred_teacher["scales"] = self.model_teacher.engine.scales
+                pred_teacher_loc = self.pseudo_generator.nms_from_dense(raw_pred_teacher, cfg.MODEL.FCOS.NMS_CRITERIA_REG_TRAIN)
+                thr = self._threshold(ss.PSEUDO_BBOX_SAMPLE, ss.BBOX_THRESHOLD, ss.BBOX_CTR_THRESHOLD)
+                thr_reg = self._threshold(ss.PSEUDO_BBOX_SAMPLE_REG, ss.BBOX_THRESHOLD_REG, ss.BBOX_CTR_THRESHOLD_REG)
+                pseudo_cls, _ = self.pseudo_generator.process_pseudo_label(pred_teacher, thr, "roih", ss.PSEUDO_BBOX_SAMPLE)
+                pseudo_reg, _ = self.pseudo_generator.process_pseudo_label(pred_teacher_loc, thr_reg, "roih",
+                                                                           ss.PSEUDO_BBOX_SAMPLE_REG)
             self.last_pseudo = (pseudo_cls, pseudo_reg)          # device-resident; read by benchmarks / analysis only
             unlabel_data_q = self.remove_label(unlabel_data_q)
             unlabel_data_q = self.add_label(unlabel_data_q, pseudo_cls, "class")
             unlabel_data_q = self.add_label(unlabel_data_q, pseudo_reg, "reg")
             lam, mu = ss.UNSUP_LOSS_WEIGHT, ss.UNSUP_REG_LOSS_WEIGHT
             # student: labeled strong + weak (trainer.py:315-322), weights :378-416
-            losses, pending = self.model.forward_train(label_data_q + label_data_k, "labeled")
+            with nvtx_range("ut2.student_labeled_forward"):
+                losses, pending = self.model.forward_train(label_data_q + label_data_k, "labeled")
             record.update(losses)
-            self.model.backward_pending(pending, [[1.0 / (lam + 1.0), 1.0 / (mu + 1.0), 1.0 / (lam + 1.0), 0.0]])
+            with nvtx_range("ut2.student_labeled_backward"):
+                self.model.backward_pending(pending, [[1.0 / (lam + 1.0), 1.0 / (mu + 1.0), 1.0 / (lam + 1.0), 0.0]])
             # student: unlabeled strong with the two pseudo-label sets (trainer.py:331-349)
-            losses_u, pending_u = self.model.forward_train(unlabel_data_q, "unlabeled")
+            with nvtx_range("ut2.student_unlabeled_forward"):
+                losses_u, pending_u = self.model.forward_train(unlabel_data_q, "unlabeled")
             record.update({k + "_pseudo": v for k, v in losses_u.items()})
-            self.model.backward_pending(pending_u, [[lam / (lam + 1.0), 0.0, lam / (lam + 1.0), 0.0],
-                                                    [0.0, mu / (mu + 1.0), 0.0, 0.0]])
+            with nvtx_range("ut2.student_unlabeled_backward"):
+                self.model.backward_pending(pending_u, [[lam / (lam + 1.0), 0.0, lam / (lam + 1.0), 0.0],
+                                                        [0.0, mu / (mu + 1.0), 0.0, 0.0]])
         record["data_time"] = data_time
         self._write_metrics(record, bookkeeping)
+        self._reduce_and_step(device_lr, bookkeeping)
+
+    def _reduce_and_step(self, device_lr, bookkeeping):
         if comm.get_world_size() > 1:       # the DDP gradient all-reduce, one contiguous buffer (mean in the SGD kernel)
-            torch.distributed.all_reduce(self.model.engine.arena.grad)
-        self.optimizer.zero_grad()
-        self.optimizer.step(use_device_lr=device_lr)
+            with nvtx_range("ut2.grad_allreduce"):
+                torch.distributed.all_reduce(self.model.engine.arena.grad)
+        with nvtx_range("ut2.sgd_and_repack"):
+            self.optimizer.zero_grad()
+            self.optimizer.step(use_device_lr=device_lr)
         if not bookkeeping:
             self.optimizer.steps -= 1       # capture does not execute; _graph_step counts the replays
 
@@ -414,8 +444,9 @@ class UBTeacherTrainer:
     @torch.no_grad()
     def _update_teacher_model(self, keep_rate=0.996):
         t = self.model_teacher.engine
-        t.ema_from(self.model.engine, keep_rate)
-        t.refresh_operands(dgrad=False)        # the teacher is never back-propagated
+        with nvtx_range("ut2.ema_teacher_update"):
+            t.ema_from(self.model.engine, keep_rate)
+            t.refresh_operands(dgrad=False)        # the teacher is never back-propagated
 
     @torch.no_grad()
     def _copy_main_model(self):
@@ -481,22 +512,25 @@ class UBRCNNTeacherTrainer(UBTeacherTrainer):
                 self._update_teacher_model(keep_rate=ss.EMA_KEEP_RATE)
             record["EMA_rate"] = ss.EMA_KEEP_RATE
             # teacher on the weak views; never switched to eval (trainer.py:830-837)
-            _, proposals_rpn_unsup_k, proposals_roih_unsup_k, _ = self.model_teacher(unlabel_data_k, branch="unsup_data_weak")
-            pseudo, _ = self.process_pseudo_label(proposals_roih_unsup_k, ss.BBOX_THRESHOLD, "roih", "thresholding")
+            with nvtx_range("ut2.teacher_forward"):
+                _, proposals_rpn_unsup_k, proposals_roih_unsup_k, _ = self.model_teacher(unlabel_data_k, branch="unsup_data_weak")
+            with nvtx_range("ut2.pseudo_labels"):
+                pseudo, _ = self.process_pseudo_label(proposals_roih_unsup_k, ss.BBOX_THRESHOLD, "roih", "thresholding")
             self.last_pseudo = (pseudo,)
             unlabel_data_q = self.add_label(self.remove_label(unlabel_data_q), pseudo)
             unlabel_data_k = self.add_label(self.remove_label(unlabel_data_k), pseudo)
             lam, mu = ss.UNSUP_LOSS_WEIGHT, ss.UNSUP_REG_LOSS_WEIGHT
-            losses, pending = self.model.forward_train(all_label_data, "supervised")
+            with nvtx_range("ut2.student_labeled_forward"):
+                losses, pending = self.model.forward_train(all_label_data, "supervised")
             record.update(losses)
-            self.model.backward_pending(pending, [1.0, 1.0, 1.0, 1.0])
-            losses_u, pending_u = self.model.forward_train(unlabel_data_q, "unsup_data_train")
+            with nvtx_range("ut2.student_labeled_backward"):
+                self.model.backward_pending(pending, [1.0, 1.0, 1.0, 1.0])
+            with nvtx_range("ut2.student_unlabeled_forward"):
+                losses_u, pending_u = self.model.forward_train(unlabel_data_q, "unsup_data_train")
             record.update({k + "_pseudo": v for k, v in losses_u.items()})
             # loss_rpn_loc_pseudo * 0, loss_box_reg_pseudo * UNSUP_REG_LOSS_WEIGHT, the two classification terms * UNSUP_LOSS_WEIGHT
-            self.model.backward_pending(pending_u, [lam, 0.0, lam, mu])
+            with nvtx_range("ut2.student_unlabeled_backward"):
+                self.model.backward_pending(pending_u, [lam, 0.0, lam, mu])
         record["data_time"] = data_time
         self._write_metrics(record, bookkeeping)
-        if comm.get_world_size() > 1:
-            torch.distributed.all_reduce(self.model.engine.arena.grad)
-        self.optimizer.zero_grad()
-        self.optimizer.step(use_device_lr=device_lr)
+        self._reduce_and_step(device_lr, bookkeeping)
