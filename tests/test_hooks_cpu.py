@@ -1,0 +1,68 @@
+"""Host logic of the training-loop hooks, the dataset catalog and the annotation box modes (no GPU needed)."""
+import json
+
+import pytest
+
+
+class _Ckpt:
+    def __init__(self):
+        self.saved = []
+
+    def save(self, name, **kw):
+        self.saved.append((name, kw.get("iteration")))
+
+
+class _Trainer:
+    def __init__(self, max_iter):
+        from ubteacher.d2compat.events import EventStorage
+        self.max_iter, self.iter, self.storage = max_iter, 0, EventStorage(0)
+
+
+def _run(trainer, hooks):
+    for h in hooks:
+        h.trainer = trainer
+        h.before_train()
+    for trainer.iter in range(trainer.max_iter):
+        trainer.storage.put_scalar("loss_x", 1.0 / (trainer.iter + 1))
+        for h in hooks:
+            h.after_step()
+        trainer.storage.step()
+    for h in hooks:
+        h.after_train()
+
+
+def test_periodic_checkpointer_eval_hook_and_writer(tmp_path):
+    from ubteacher.engine import hooks
+    ck, tr, evals = _Ckpt(), _Trainer(10), []
+    w = hooks.JSONWriter(str(tmp_path / "metrics.json"))
+    hs = [hooks.PeriodicCheckpointer(ck, 4), hooks.EvalHook(5, lambda: evals.append(tr.iter) or {"bbox": {"AP": 12.5}}),
+          hooks.PeriodicWriter([w], period=3)]
+    _run(tr, hs)
+    assert ck.saved == [("model_0000003", 3), ("model_0000007", 7), ("model_final", 9)]       # [D2] PeriodicCheckpointer naming
+    assert evals == [4, 9]                                                                      # every 5 iterations + after the last
+    assert tr.storage.latest()["bbox/AP"][0] == 12.5
+    lines = [json.loads(x) for x in open(tmp_path / "metrics.json")]
+    assert [r["iteration"] for r in lines] == [2, 5, 8, 9] and "loss_x" in lines[0]
+
+
+def test_eval_hook_disabled_with_period_zero():
+    from ubteacher.engine import hooks
+    tr, calls = _Trainer(4), []
+    _run(tr, [hooks.EvalHook(0, lambda: calls.append(1))])
+    assert calls == []
+
+
+def test_dataset_catalog_and_bbox_modes(tmp_path):
+    from ubteacher.d2compat.catalog import DatasetCatalog, register_json
+    from ubteacher.data.dataset_mapper import bbox_xyxy
+    p = tmp_path / "d.json"
+    p.write_text(json.dumps([{"file_name": "a.jpg", "height": 4, "width": 6, "image_id": 1,
+                              "annotations": [{"bbox": [1, 2, 3, 4], "bbox_mode": 1, "category_id": 0}]}]))
+    register_json("toy_train", str(p))
+    assert "toy_train" in DatasetCatalog and DatasetCatalog.get("toy_train")[0]["image_id"] == 1
+    with pytest.raises(KeyError):
+        DatasetCatalog.get("missing")
+    assert bbox_xyxy({"bbox": [1, 2, 3, 4], "bbox_mode": 1}) == [1.0, 2.0, 4.0, 6.0]          # XYWH_ABS -> XYXY_ABS
+    assert bbox_xyxy({"bbox": [1, 2, 3, 4]}) == [1.0, 2.0, 3.0, 4.0] == bbox_xyxy({"bbox": [1, 2, 3, 4], "bbox_mode": 0})
+    with pytest.raises(ValueError):
+        bbox_xyxy({"bbox": [0, 0, 1, 1], "bbox_mode": 4})

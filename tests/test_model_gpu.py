@@ -483,14 +483,14 @@ def test_eval_mode_rescales_to_dataset_size():
     torch.testing.assert_close(big.pred_boxes.tensor.cpu(), ref[keep], rtol=0, atol=1e-3)
 
 
-def test_train_loop_burn_in_then_semisup():
+def test_train_loop_burn_in_then_semisup(tmp_path):
     """trainer.train(): burn-in steps (supervised only, teacher untouched), the copy at iter == BURN_UP_STEP, then the
     semi-supervised steps, with [D2] WarmupMultiStepLR driving the learning rate (trainer.py:191-210, SURVEY §8f #4)."""
     from util_cfg import fcos_cfg
     from ubteacher.data.synthetic import SyntheticTwoCropLoader
     from ubteacher.engine import UBTeacherTrainer
     cfg = fcos_cfg(**{"SEMISUPNET.BURN_UP_STEP": 2, "SOLVER.MAX_ITER": 5, "SOLVER.WARMUP_ITERS": 3, "SOLVER.STEPS": (4,),
-                      "SOLVER.BASE_LR": 0.001})
+                      "SOLVER.BASE_LR": 0.001, "TEST.EVAL_PERIOD": 0, "OUTPUT_DIR": str(tmp_path / "run")})
     tr = UBTeacherTrainer(cfg, data_loader=SyntheticTwoCropLoader(1, 1, h=96, w=128, boxes_per_image=2, pool=2))
     t0 = tr.model_teacher.engine.arena.data.clone()
     lrs, seen = [], []
@@ -545,3 +545,58 @@ def test_inference_on_dataset_and_box_ap():
             d["instances"].gt_boxes.tensor[:, 0::2] += 3.0    # shift the ground truth: strictly worse
     res2 = inference_on_dataset(model, batches, BoxAPEvaluator(), cfg)
     assert res2["bbox"]["AP"] < 99.0
+
+
+def test_train_hooks_checkpoint_eval_metrics_and_resume(tmp_path):
+    """train() end to end with the reference's hooks (trainer.py:503-552): periodic + final checkpoints, evaluation of student
+    and teacher every TEST.EVAL_PERIOD iterations (returned by train() like [D2] DefaultTrainer), metrics.json; then a second
+    trainer resumes from the checkpoint this one wrote and continues at the next iteration."""
+    import json
+    import os
+    from util_cfg import fcos_cfg
+    from ubteacher.data.synthetic import SyntheticTwoCropLoader
+    from ubteacher.engine import UBTeacherTrainer
+    out = str(tmp_path / "run")
+    kw = {"SOLVER.MAX_ITER": 4, "SOLVER.CHECKPOINT_PERIOD": 2, "TEST.EVAL_PERIOD": 2, "OUTPUT_DIR": out, "SOLVER.BASE_LR": 0.001,
+          "SOLVER.WARMUP_ITERS": 2}
+    mk = lambda **k: UBTeacherTrainer(fcos_cfg(**dict(kw, **k)), data_loader=SyntheticTwoCropLoader(1, 1, h=96, w=128, boxes_per_image=2, pool=2))
+    UBTeacherTrainer.allow_synthetic = True           # the evaluation loader: synthetic, asked for explicitly
+    try:
+        tr = mk()
+        tr.metrics_period = 2
+        res = tr.train()
+        assert "bbox" in res and "AP" in res["bbox"]                       # the teacher's last evaluation
+        assert tr._last_eval_results_student is not None
+        assert sorted(f for f in os.listdir(out) if f.endswith(".pth")) == ["model_0000001.pth", "model_final.pth"]
+        recs = [json.loads(x) for x in open(os.path.join(out, "metrics.json"))]
+        assert [r["iteration"] for r in recs] == [1, 3] and "total_loss" in recs[0] and "lr" in recs[0]
+        assert any("bbox/AP" in r for r in recs) and any("bbox_student/AP" in r for r in recs)
+        tr2 = mk(**{"SOLVER.MAX_ITER": 6})
+        tr2.resume_or_load(resume=True)
+        assert tr2.start_iter == 4 and torch.equal(tr2.model.engine.arena.data, tr.model.engine.arena.data)
+        tr2.metrics_period = 2
+        tr2.train()
+        assert tr2.iter == 5 and "model_final.pth" in os.listdir(out)
+    finally:
+        UBTeacherTrainer.allow_synthetic = False
+
+
+def test_optimizer_loads_torch_sgd_state_dict(model):
+    """A checkpoint written by the reference holds torch.optim.SGD state ({"state": {i: {"momentum_buffer"}}, "param_groups":
+    [{"params": [i]}...], one group per trainable parameter in named_parameters() order): its momentum buffers land in the arena."""
+    from util_cfg import fcos_cfg
+    from ubteacher.arena import _view
+    from ubteacher.engine.trainer import ArenaSGD
+    opt = ArenaSGD(fcos_cfg(), model)
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    g = torch.Generator().manual_seed(0)
+    state = {i: {"momentum_buffer": torch.randn(dict(model.named_parameters())[n].shape, generator=g)} for i, n in enumerate(names)}
+    sd = {"state": state, "param_groups": [{"params": [i], "lr": 0.01} for i in range(len(names))]}
+    model.engine.arena.mom.zero_()
+    opt.load_state_dict(sd)
+    A = model.engine.arena
+    for i in (0, len(names) // 2, len(names) - 1):
+        v = _view(A.mom, A.offset[names[i]], A.specs[names[i]].shape)
+        assert torch.equal(v.cpu(), state[i]["momentum_buffer"]), names[i]
+    assert opt.steps == 1
+    A.mom.zero_()

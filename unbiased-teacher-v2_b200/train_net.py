@@ -21,6 +21,10 @@ def argument_parser():
     p.add_argument("--resume", action="store_true", help="resume from the last checkpoint of OUTPUT_DIR")
     p.add_argument("--eval-only", action="store_true")
     p.add_argument("--cuda-graph", action="store_true", help="replay the semi-supervised step as one CUDA graph")
+    p.add_argument("--dataset-json", action="append", default=[], metavar="NAME=FILE",
+                   help="register a dataset (JSON list of Detectron2-style dataset dicts) under NAME; NAME must appear in "
+                        "cfg.DATASETS.TRAIN / TEST (the reference registers the COCO splits in data/datasets/builtin.py)")
+    p.add_argument("--synthetic", action="store_true", help="train / evaluate on synthetic random images when no dataset is registered")
     p.add_argument("opts", default=None, nargs=argparse.REMAINDER, help="KEY VALUE pairs merged into the config")
     return p
 
@@ -55,6 +59,11 @@ def main(args):
         args.opts = list(args.opts or []) + ["MODEL.DEVICE", f"cuda:{local}"]
     cfg = setup(args)
     Trainer = pick_trainer(cfg)
+    from ubteacher.d2compat.catalog import register_json
+    for spec in args.dataset_json:
+        name, _, path = spec.partition("=")
+        register_json(name, path)
+    Trainer.allow_synthetic = bool(args.synthetic)
     if args.eval_only:
         from ubteacher.checkpoint import DetectionTSCheckpointer
         from ubteacher.modeling.meta_arch.ts_ensemble import EnsembleTSModel

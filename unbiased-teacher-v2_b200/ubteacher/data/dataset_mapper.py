@@ -107,7 +107,7 @@ class DatasetMapperTwoCropSeparate:
             base.setdefault("width", w)
             if self.is_train and "annotations" in d:
                 annos = [a for a in d["annotations"] if a.get("iscrowd", 0) == 0]
-                boxes, keep = transform_boxes([a["bbox"] for a in annos], h, w, new_h, new_w, flip)
+                boxes, keep = transform_boxes([bbox_xyxy(a) for a in annos], h, w, new_h, new_w, flip)
                 inst = Instances((new_h, new_w))
                 inst.gt_boxes = Boxes(torch.from_numpy(boxes[keep]))
                 inst.gt_classes = torch.tensor([a["category_id"] for a, k in zip(annos, keep) if k], dtype=torch.int64)
@@ -115,3 +115,16 @@ class DatasetMapperTwoCropSeparate:
             out_q.append(dict(base, image=st))
             out_k.append(dict(base, image=wk))
         return out_q, out_k
+
+
+def bbox_xyxy(anno):
+    """[D2] BoxMode.convert(bbox, anno["bbox_mode"], XYXY_ABS) for the two absolute modes dataset dicts carry
+    (XYXY_ABS = 0: the default here; XYWH_ABS = 1: what [D2]'s COCO loader produces). Anything else is refused."""
+    b = [float(v) for v in anno["bbox"]]
+    mode = anno.get("bbox_mode", 0)
+    mode = getattr(mode, "value", mode)
+    if mode in (0, "XYXY_ABS"):
+        return b
+    if mode in (1, "XYWH_ABS"):
+        return [b[0], b[1], b[0] + b[2], b[1] + b[3]]
+    raise ValueError(f"unsupported bbox_mode {mode!r} (XYXY_ABS or XYWH_ABS expected)")

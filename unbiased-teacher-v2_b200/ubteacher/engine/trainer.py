@@ -62,14 +62,14 @@ class ArenaSGD:
         self.grad_scale = 1.0
         dev = model.engine.device
         self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)      # read by the SGD kernel (graph replay)
-        self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     def zero_grad(self, set_to_none=False):
         pass  # the SGD kernel clears the gradient arena in the same pass that consumes it
 
     def push_lr(self):
-        self._lr_host[0] = self.param_groups[0]["lr"]
-        self.lr_dev.copy_(self._lr_host, non_blocking=True)
+        # a fill kernel with the value as a launch argument: stream-ordered, nothing the host could overwrite before the
+        # device reads it (a pinned scalar + async copy would race with the next iteration's write)
+        self.lr_dev.fill_(float(self.param_groups[0]["lr"]))
 
     def step(self, use_device_lr=False):
         eng = self.model.engine
@@ -84,8 +84,33 @@ class ArenaSGD:
                 "param_groups": self.param_groups}
 
     def load_state_dict(self, sd):
-        self.steps = sd["steps"]
-        self.model.engine.arena.mom.copy_(sd["momentum_buffer"])
+        if "steps" in sd:                       # this trainer's own format
+            self.steps = sd["steps"]
+            self.model.engine.arena.mom.copy_(sd["momentum_buffer"])
+            return
+        # a torch.optim.SGD state dict (what the reference's checkpoints hold): {"state": {i: {"momentum_buffer"}},
+        # "param_groups": [{"params": [i, ...]}, ...]}. [D2] builds one group per parameter in named_parameters() order of the
+        # trainable parameters, which is this model's order too; shapes are checked, anything else is skipped loudly.
+        A = self.model.engine.arena
+        names = [n for n, p in self.model.named_parameters() if p.requires_grad]
+        ids = [i for g in sd.get("param_groups", []) for i in g.get("params", [])]
+        state = sd.get("state", {})
+        if len(ids) != len(names):
+            logger.warning("optimizer state has %d parameters, the model %d: momentum buffers not loaded", len(ids), len(names))
+            return
+        from ..arena import _view
+        loaded = 0
+        for i, n in zip(ids, names):
+            buf = state.get(i, {}).get("momentum_buffer")
+            if buf is None:
+                continue
+            v = _view(A.mom, A.offset[n], A.specs[n].shape)
+            if buf.numel() != v.numel():
+                logger.warning("momentum buffer of %s has %d elements, expected %d: skipped", n, buf.numel(), v.numel())
+                continue
+            v.copy_(buf.to(v.device, torch.float32).reshape(v.shape))
+            loaded += 1
+        self.steps = 1 if loaded else 0
 
 
 class UBTeacherTrainer:
@@ -112,6 +137,8 @@ class UBTeacherTrainer:
         self.iter = 0
         self.max_iter = cfg.SOLVER.MAX_ITER
         self.storage = None
+        self._hooks = []
+        self._last_eval_results_teacher = self._last_eval_results_student = None
         self.metrics_period = 20                        # PeriodicWriter period (trainer.py:551)
         self._metric_names, self._metric_buf = None, []
         self.last_losses = None
@@ -125,6 +152,9 @@ class UBTeacherTrainer:
             torch.distributed.broadcast(model.engine.arena.data, 0)
             model.engine.refresh_operands()
             self.optimizer.grad_scale = 1.0 / comm.get_world_size()
+            for m in (model, model_teacher):            # every rank draws its own anchor / proposal samples (the reference's
+                if hasattr(m.engine, "seed"):           # ranks have independent torch RNG streams)
+                    m.engine.seed = (int(m.engine.seed) * 1000003 + comm.get_rank() + 1) & 0x7FFFFFFF
 
     def _make_pseudo_generator(self, cfg):
         return PseudoGenerator(cfg)
@@ -143,13 +173,29 @@ class UBTeacherTrainer:
 
     @classmethod
     def build_lr_scheduler(cls, cfg, optimizer):
+        name = cfg.SOLVER.LR_SCHEDULER_NAME
+        if name != "WarmupMultiStepLR":        # solver/lr_scheduler.py:9-53 (the reference's recipes use nothing else)
+            raise ValueError("Unknown LR scheduler: {}".format(name))
         return WarmupMultiStepLR(optimizer, cfg.SOLVER.STEPS, cfg.SOLVER.GAMMA, cfg.SOLVER.WARMUP_FACTOR,
                                  cfg.SOLVER.WARMUP_ITERS, cfg.SOLVER.WARMUP_METHOD)
 
+    # no dataset ships with this repo: the synthetic loaders are used only when asked for (train_net.py --synthetic,
+    # bench.py and the tests pass their loader explicitly); otherwise cfg.DATASETS.* must be registered in the DatasetCatalog
+    allow_synthetic = False
+
     @classmethod
     def build_train_loader(cls, cfg):
+        from ..d2compat.catalog import DatasetCatalog
+        names = [n for n in cfg.DATASETS.TRAIN if n in DatasetCatalog]
+        if names:       # data/build.py:144-272: label / unlabel split by SUP_PERCENT + RANDOM_DATA_SEED, two-crop device mapper
+            from ..data.build import build_detection_semisup_train_loader_two_crops
+            dicts = [d for n in names for d in DatasetCatalog.get(n)]
+            return build_detection_semisup_train_loader_two_crops(cfg, dataset_dicts=dicts)
+        if not cls.allow_synthetic:
+            raise RuntimeError(f"none of cfg.DATASETS.TRAIN = {tuple(cfg.DATASETS.TRAIN)} is registered in the DatasetCatalog "
+                               "(train_net.py --dataset-json NAME=FILE); pass --synthetic to train on random images")
         from ..data.synthetic import SyntheticTwoCropLoader
-        logger.warning("no dataset on this box: using the synthetic two-crop loader (SURVEY.md §8d)")
+        logger.warning("--synthetic: training on the synthetic two-crop loader (random images, SURVEY.md §8d)")
         w = comm.get_world_size()
         return SyntheticTwoCropLoader(cfg.SOLVER.IMG_PER_BATCH_LABEL // w, cfg.SOLVER.IMG_PER_BATCH_UNLABEL // w,
                                       rank=comm.get_rank())
@@ -163,7 +209,25 @@ class UBTeacherTrainer:
 
     @classmethod
     def build_test_loader(cls, cfg, dataset_name=None, num_batches=4, batch_size=2):
-        """A fixed-length list of synthetic labeled batches (no dataset on this box)."""
+        """A fixed-length list of batches: the registered cfg.DATASETS.TEST split through the weak (test-time) mapper, or —
+        only when synthetic data was asked for — synthetic labeled batches."""
+        from ..d2compat.catalog import DatasetCatalog
+        name = dataset_name or (cfg.DATASETS.TEST[0] if len(cfg.DATASETS.TEST) else None)
+        if name is not None and name in DatasetCatalog:
+            from ..data.build import read_image
+            from ..data.dataset_mapper import DatasetMapperTwoCropSeparate
+            mapper = DatasetMapperTwoCropSeparate(cfg, False)
+            dicts = DatasetCatalog.get(name)
+            out = []
+            for i in range(0, len(dicts), batch_size):
+                chunk = [dict(d, image=read_image(d["file_name"], cfg.INPUT.FORMAT)) for d in dicts[i:i + batch_size]]
+                _, weak = mapper(chunk)
+                for d, src in zip(weak, dicts[i:i + batch_size]):
+                    d["annotations"] = src.get("annotations", [])
+                out.append(weak)
+            return out
+        if not cls.allow_synthetic:
+            raise RuntimeError(f"test dataset {name!r} is not registered in the DatasetCatalog; pass --synthetic for random images")
         from ..data.synthetic import SyntheticTwoCropLoader
         ld = SyntheticTwoCropLoader(batch_size, 1, rank=0, pin=False)
         out = []
@@ -199,16 +263,65 @@ class UBTeacherTrainer:
 
     # ---------------------------------------------------------------- loop
     def train(self):
+        """trainer.py:177-179 + [D2] DefaultTrainer.train: run the loop, return the last teacher evaluation."""
         self.train_loop(self.start_iter, self.max_iter)
+        if self._last_eval_results_teacher is not None and comm.is_main_process():
+            return self._last_eval_results_teacher
+
+    def build_hooks(self):
+        """trainer.py:503-552: periodic checkpoints (rank 0), evaluation of the student and of the teacher every
+        TEST.EVAL_PERIOD iterations, periodic metric writers (rank 0; metrics.json + log line, every 20 iterations)."""
+        from . import hooks
+        cfg = self.cfg
+        ret = []
+        if comm.is_main_process():
+            ret.append(hooks.PeriodicCheckpointer(self.checkpointer, cfg.SOLVER.CHECKPOINT_PERIOD))
+
+        def test_and_save_results_student():
+            self._last_eval_results_student = self.test(self.cfg, self.model)
+            return {k + "_student": v for k, v in self._last_eval_results_student.items()}
+
+        def test_and_save_results_teacher():
+            self._last_eval_results_teacher = self.test(self.cfg, self.model_teacher)
+            return self._last_eval_results_teacher
+
+        ret.append(hooks.EvalHook(cfg.TEST.EVAL_PERIOD, test_and_save_results_student))
+        ret.append(hooks.EvalHook(cfg.TEST.EVAL_PERIOD, test_and_save_results_teacher))
+        if comm.is_main_process():
+            ret.append(hooks.PeriodicWriter(self.build_writers(), period=self.metrics_period))
+        return ret
+
+    def build_writers(self):
+        from . import hooks
+        return [hooks.CommonMetricPrinter(self.max_iter), hooks.JSONWriter(os.path.join(self.cfg.OUTPUT_DIR, "metrics.json"))]
+
+    def register_hooks(self, hook_list):
+        for h in hook_list:
+            if h is not None:
+                h.trainer = self
+                self._hooks.append(h)
 
     def train_loop(self, start_iter, max_iter):
         self.iter = self.start_iter = start_iter
         self.max_iter = max_iter
+        if not self._hooks:
+            self.register_hooks(self.build_hooks())
         with EventStorage(start_iter) as self.storage:
-            for self.iter in range(start_iter, max_iter):
-                self.run_step_full_semisup()
-                self.scheduler.step()
-                self.storage.step()
+            try:
+                for h in self._hooks:
+                    h.before_train()
+                for self.iter in range(start_iter, max_iter):
+                    for h in self._hooks:
+                        h.before_step()
+                    self.run_step_full_semisup()
+                    self.storage.put_scalar("lr", self.optimizer.param_groups[0]["lr"], smoothing_hint=False)
+                    self.scheduler.step()                # [D2] hooks.LRScheduler.after_step
+                    for h in self._hooks:
+                        h.after_step()
+                    self.storage.step()
+            finally:
+                for h in self._hooks:
+                    h.after_train()
 
     # ---------------------------------------------------------------- pseudo-labeling helpers (trainer.py:161-175)
     def remove_label(self, label_data):
@@ -469,10 +582,7 @@ class UBRCNNTeacherTrainer(UBTeacherTrainer):
     def _graph_step(self, data, data_time):
         # the sampling seeds baked into the captured launches are constants: the draw counter lives in device memory
         # (RcnnEngine.seed_dev, mixed into every anchor / proposal sampling key) and is advanced before each replay
-        if getattr(self, "_seed_host", None) is None:
-            self._seed_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-        self._seed_host[0] = (self.iter + 1) & 0x7FFFFFFF
-        self.model.engine.seed_dev.copy_(self._seed_host, non_blocking=True)
+        self.model.engine.seed_dev.fill_(int((self.iter + 1) & 0x7FFFFFFF))     # value travels as a launch argument: no host race
         return super()._graph_step(data, data_time)
 
     # ---------------------------------------------------------------- pseudo-labeling (trainer.py:727-769)

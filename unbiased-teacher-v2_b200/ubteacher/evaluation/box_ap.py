@@ -77,7 +77,8 @@ def coco_box_ap(dets, gts, max_dets=100):
 
 class BoxAPEvaluator:
     """[D2] DatasetEvaluator protocol. Ground truth comes from the inputs themselves: dict["instances"] (gt_boxes,
-    gt_classes, in the coordinates of dict["height"] x dict["width"]) or dict["annotations"] (xyxy boxes)."""
+    gt_classes, in the network-input frame; rescaled to dict["height"] x dict["width"] like the detections) or
+    dict["annotations"] (original-image coordinates, XYXY_ABS or XYWH_ABS)."""
 
     def reset(self):
         self._dets, self._gts = {}, {}
@@ -88,13 +89,17 @@ class BoxAPEvaluator:
             inst = out["instances"]
             self._dets[key] = (inst.pred_boxes.tensor.detach().float().cpu().numpy(), inst.pred_classes.detach().cpu().numpy(),
                                inst.scores.detach().float().cpu().numpy())
-            if "instances" in inp:
-                g = inp["instances"]
-                self._gts[key] = (g.gt_boxes.tensor.detach().float().cpu().numpy(), g.gt_classes.detach().cpu().numpy())
-            else:
-                ann = [a for a in inp.get("annotations", []) if not a.get("iscrowd", 0)]
-                self._gts[key] = (np.array([a["bbox"] for a in ann], dtype=np.float64).reshape(-1, 4),
+            if "annotations" in inp:            # dataset annotations: original-image coordinates, any absolute bbox_mode
+                from ..data.dataset_mapper import bbox_xyxy
+                ann = [a for a in inp["annotations"] if not a.get("iscrowd", 0)]
+                self._gts[key] = (np.array([bbox_xyxy(a) for a in ann], dtype=np.float64).reshape(-1, 4),
                                   np.array([a["category_id"] for a in ann], dtype=np.int64))
+            else:                               # Instances live in the network-input frame: bring them to the frame the
+                g = inp["instances"]            # detections were post-processed to (dict height x width)
+                b = g.gt_boxes.tensor.detach().float().cpu().numpy().astype(np.float64)
+                ih, iw = g.image_size
+                sy, sx = inp.get("height", ih) / float(ih), inp.get("width", iw) / float(iw)
+                self._gts[key] = (b * np.array([sx, sy, sx, sy]), g.gt_classes.detach().cpu().numpy())
 
     def evaluate(self):
         return {"bbox": coco_box_ap(self._dets, self._gts)}
