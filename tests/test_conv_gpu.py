@@ -243,7 +243,9 @@ BIG_FWD = [
     ("dgrad_mask_128", (4, 100, 168, 128, 128, 3, 1, 1), "mask", False),           # 525 tiles, ReLU-mask aux tile (dgrad epilogue)
     ("dgrad_mask_64_aux_dbl", (2, 200, 336, 64, 64, 1, 1, 0), "mask", False),      # 1050 tiles, mask + aux_dbl, N = 64 tile
     ("fpn_lateral_res_up2", (4, 100, 168, 512, 256, 1, 1, 0), "res_up2", False),   # 525 tiles, manual epilogue (nearest-2x residual)
-    ("res_and_mask_manual", (4, 100, 168, 64, 128, 1, 1, 0), "res+mask", False),   # 525 tiles, manual epilogue (both)
+    ("res_and_mask_128", (4, 100, 168, 64, 128, 1, 1, 0), "res+mask", False),      # 525 tiles, residual AND mask tiles (aux_kind 3)
+    ("res_and_mask_1024", (5, 50, 84, 256, 1024, 1, 1, 0), "res+mask", False),     # 660 tiles: block-output ReLU backward fused in conv1.dgrad
+    ("res_and_mask_2048", (8, 25, 42, 512, 2048, 1, 1, 0), "res+mask", False),     # 528 tiles, K = 512, two operand stages
     ("cls_logits_80", (4, 100, 168, 256, 80, 3, 1, 1), None, False),               # 525 tiles, Cout = 80
     ("res3_conv1_s2", (4, 200, 336, 256, 128, 1, 2, 0), None, True),               # 525 tiles, strided 1x1 (STRIDE_IN_1X1)
     ("p6_3x3_s2", (8, 100, 168, 256, 256, 3, 2, 1), None, False),                  # 263 tiles, strided 3x3

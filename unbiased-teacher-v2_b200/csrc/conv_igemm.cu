@@ -79,7 +79,7 @@ struct ConvFwdArgs {
   int stages;                       // operand ring depth (pick_stages)
   int aux_dbl;                      // 1: two aux staging tiles per epilogue warp (memory-bound convs: see the epilogue)
   int no_pad;                       // 1: the dynamic shared buffer must already be 1024-byte aligned
-  int aux_kind;                     // 0 none, 1 residual tile via TMA, 2 relu-mask tile via TMA
+  int aux_kind;                     // 0 none, 1 residual tile via TMA, 2 relu-mask tile via TMA, 3 both (two tiles per warp)
   int manual;                       // 1: epilogue with plain loads/stores (res_up2, residual+mask, Cout < 64)
   const float* scale;
   const float* shift;
@@ -106,7 +106,7 @@ __device__ __forceinline__ uint32_t mask_bf16x2(uint32_t o, uint32_t m) {
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__ CUtensorMap tmap_w,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
-                const ConvFwdArgs a) {
+                const __grid_constant__ CUtensorMap tmap_aux2, const ConvFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer: LDS / STS, not generic LD / ST
   if (a.no_pad && smem != smem_raw) __trap();      // the launch reserved no alignment slack (see smem_bytes)
@@ -133,6 +133,7 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
     prefetch_tmap(&tmaps_x.m[0]);
     prefetch_tmap(&tmap_w);
     if (a.aux_kind) prefetch_tmap(&tmap_aux);
+    if (a.aux_kind == 3) prefetch_tmap(&tmap_aux2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -237,7 +238,11 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
     // (ncu: ~30 % of the epilogue warps' samples sat in this mbarrier wait). With aux_dbl each warp owns two staging
     // tiles and requests tile i+1's chunk BEFORE it processes tile i.
     const bool dbl = use_aux && a.aux_dbl;
-    uint8_t* atile0 = aux_stage + ew * (a.aux_dbl ? 2 : 1) * EPI_TILE_BYTES;
+    // aux_kind 3 (residual AND ReLU mask: the block-output ReLU backward fused into the dgrad that produces the gradient):
+    // two tiles per warp, slot 0 = residual, slot 1 = mask, both loads arrive on the warp's first barrier.
+    const bool both = a.aux_kind == 3;
+    const uint32_t aux_tx = both ? 2 * EPI_TILE_BYTES : EPI_TILE_BYTES;
+    uint8_t* atile0 = aux_stage + ew * ((a.aux_dbl || both) ? 2 : 1) * EPI_TILE_BYTES;
     uint64_t* my_aux_bar = aux_bar + ew * 2;
     uint32_t acc = 0, acc_phase = 0, aux_phase = 0, it = 0;
     int staged_n_tile = -1;
@@ -245,9 +250,12 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
       const int t = blockIdx.x;
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
       const int lv = level_of(a.lt, m_tile);
-      mbar_arrive_expect_tx(&my_aux_bar[0], EPI_TILE_BYTES);
+      mbar_arrive_expect_tx(&my_aux_bar[0], aux_tx);
       tma_load_2d(atile0, &tmap_aux, &my_aux_bar[0], n_tile * a.block_n + c0,
                   a.lt.row_off[lv] + (m_tile - a.lt.tile_off[lv]) * BM + quad * 32);
+      if (both)
+        tma_load_2d(atile0 + EPI_TILE_BYTES, &tmap_aux2, &my_aux_bar[0], n_tile * a.block_n + c0,
+                    a.lt.row_off[lv] + (m_tile - a.lt.tile_off[lv]) * BM + quad * 32);
     }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       if (dbl) {                        // request the next tile's chunk into the other slot (last read in tile it-1)
@@ -328,7 +336,12 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
             if (use_aux) {
               const uint4 t0 = *reinterpret_cast<const uint4*>(atile + swz(lane, 2 * j));
               const uint4 t1 = *reinterpret_cast<const uint4*>(atile + swz(lane, 2 * j + 1));
-              if (a.aux_kind == 1) { x0 = t0; x1 = t1; has_res = 1; } else { y0 = t0; y1 = t1; has_mask = 1; }
+              if (a.aux_kind == 2) { y0 = t0; y1 = t1; has_mask = 1; } else { x0 = t0; x1 = t1; has_res = 1; }
+              if (both) {
+                y0 = *reinterpret_cast<const uint4*>(atile + EPI_TILE_BYTES + swz(lane, 2 * j));
+                y1 = *reinterpret_cast<const uint4*>(atile + EPI_TILE_BYTES + swz(lane, 2 * j + 1));
+                has_mask = 1;
+              }
             } else if (a.manual) {
               if (a.residual) {
                 const uint4* rp = reinterpret_cast<const uint4*>(a.residual + rrow * a.ldr + nj);
@@ -377,9 +390,12 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
         if (lane == 0 && tn < num_tiles) {
           const int n_tile2 = tn % a.n_tiles, m_tile2 = tn / a.n_tiles;
           const int lv2 = level_of(a.lt, m_tile2);
-          mbar_arrive_expect_tx(&my_aux_bar[0], EPI_TILE_BYTES);
+          mbar_arrive_expect_tx(&my_aux_bar[0], aux_tx);
           tma_load_2d(atile0, &tmap_aux, &my_aux_bar[0], n_tile2 * a.block_n + c0,
                       a.lt.row_off[lv2] + (m_tile2 - a.lt.tile_off[lv2]) * BM + quad * 32);
+          if (both)
+            tma_load_2d(atile0 + EPI_TILE_BYTES, &tmap_aux2, &my_aux_bar[0], n_tile2 * a.block_n + c0,
+                        a.lt.row_off[lv2] + (m_tile2 - a.lt.tile_off[lv2]) * BM + quad * 32);
         }
       }
     }
@@ -648,6 +664,14 @@ static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, 
            m_tiles * ((Cout + block_n - 1) / block_n) * 2 <= num_sms())
       block_n /= 2;
   }
+  // residual + mask (aux_kind 3): the 128 KiB of aux tiles leave two operand stages next to a 256-wide tile. Measured against
+  // 128-wide tiles (64 KiB of aux tiles in use, five stages; UT2_AUX3_BN=128) on the res3 / res4 / res5 conv1 data-gradients,
+  // L2 flushed: 161 / 94 / 70 us vs 217 / 121 / 72 us — these launches are bound by their epilogue, not by the main loop.
+  if (residual && relu_mask && !res_up2 && Cout >= 256 && Cout % 128 == 0 && block_n > 128) {
+    static int bn3 = -1;
+    if (bn3 < 0) { const char* e = getenv("UT2_AUX3_BN"); bn3 = e ? atoi(e) : 256; }
+    if (bn3 == 128) block_n = 128;
+  }
   const int P = a.lt.P[0], Q = a.lt.Q[0];
   a.M = (int)out_rows; a.Cout = Cout; a.ldo = Cout;
   a.block_n = block_n; a.n_tiles = (Cout + block_n - 1) / block_n; a.m_tiles = a.lt.tile_off[num_levels];
@@ -657,16 +681,17 @@ static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, 
   a.res_up2 = res_up2; a.relu_mask = static_cast<const __nv_bfloat16*>(relu_mask);
   if (res_up2 && ((P & 1) || (Q & 1))) return ut2_fail(-4, "conv_fwd: res_up2 needs even output H, W");
   a.out = static_cast<__nv_bfloat16*>(y);
-  a.manual = (Cout < 64 && (residual || relu_mask)) || (residual && res_up2) || (residual && relu_mask);
-  a.aux_kind = a.manual ? 0 : (residual ? 1 : (relu_mask ? 2 : 0));
+  a.manual = (Cout < 64 && (residual || relu_mask)) || (residual && res_up2);
+  a.aux_kind = a.manual ? 0 : ((residual && relu_mask) ? 3 : (residual ? 1 : (relu_mask ? 2 : 0)));
   // double-buffered aux tiles for the most epilogue-bound convolutions (K <= 128: res2 / res3 conv3 + shortcut, +11 %
   // measured); from K = 256 on the two operand stages that are left cost more than the exposed aux latency (K = 512:
   // -25 %), and the tensor-bound ones hide it behind their main loop anyway. UT2_AUX_DBL=0 disables (A/B runs).
   static int dbl_on = -1;
   if (dbl_on < 0) { const char* e = getenv("UT2_AUX_DBL"); dbl_on = e ? atoi(e) : 1; }
-  a.aux_dbl = (dbl_on && a.aux_kind != 0 && R * S * Cin <= 128) ? 1 : 0;
-  const int aux_tiles = a.aux_kind ? (a.aux_dbl ? 32 : 16) : 0;
-  a.no_pad = (a.aux_dbl && pick_stages(block_n, aux_tiles, 1024) < 2) ? 1 : 0;
+  a.aux_dbl = (dbl_on && a.aux_kind != 0 && a.aux_kind != 3 && R * S * Cin <= 128) ? 1 : 0;
+  // kind 3 keeps two tiles per ACTIVE epilogue warp (four warps per 64-column chunk of the tile)
+  const int aux_tiles = a.aux_kind == 3 ? 2 * 4 * ((block_n + 63) / 64) : (a.aux_kind ? (a.aux_dbl ? 32 : 16) : 0);
+  a.no_pad = ((a.aux_dbl || a.aux_kind == 3) && pick_stages(block_n, aux_tiles, 1024) < 2) ? 1 : 0;
   const int smem_pad = a.no_pad ? 0 : 1024;
   a.stages = pick_stages(block_n, aux_tiles, smem_pad);
   if (a.stages < 2) return ut2_fail(-5, "conv_fwd: shared memory budget");
@@ -677,9 +702,14 @@ static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, 
   rc = make_tmap_2d_bf16(&to, y, a.M, Cout, Cout, bc, 32);
   if (rc) return ut2_fail(rc, "conv_fwd: output tensor map encode failed");
   ta = to;
+  CUtensorMap ta2 = to;
   if (a.aux_kind) {
-    rc = make_tmap_2d_bf16(&ta, a.aux_kind == 1 ? residual : relu_mask, a.M, Cout, Cout, bc, 32);
+    rc = make_tmap_2d_bf16(&ta, a.aux_kind == 2 ? relu_mask : residual, a.M, Cout, Cout, bc, 32);
     if (rc) return ut2_fail(rc, "conv_fwd: aux tensor map encode failed");
+  }
+  if (a.aux_kind == 3) {
+    rc = make_tmap_2d_bf16(&ta2, relu_mask, a.M, Cout, Cout, bc, 32);
+    if (rc) return ut2_fail(rc, "conv_fwd: mask tensor map encode failed");
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -690,7 +720,7 @@ static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, 
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   conv_fwd_kernel<<<grid, NUM_THREADS, smem_bytes(a.stages, block_n, aux_tiles, smem_pad), static_cast<cudaStream_t>(stream)>>>(
-      tx, tw, to, ta, a);
+      tx, tw, to, ta, ta2, a);
   return ut2_check_launch("conv_fwd");
 }
 

@@ -269,17 +269,21 @@ class EngineBase:
                 tape[stage] = saved
         return feats, sizes, (Hp, Wp)
 
-    def trunk_backward(self, tape, extra):
-        """extra: {"res5": dC5, "res4": dC4, "res3": dC3} gradients arriving from the FPN laterals."""
-        from_next = None          # d(loss)/d(stage output) flowing down from the later stage
+    def trunk_backward(self, tape, lateral):
+        """lateral: {"res5": (conv, dl5, hw), "res4": ..., "res3": ...} — the FPN lateral convolutions with the gradient of their
+        OUTPUT. Their data-gradient is launched here, when the gradient flowing down from the later stage is known, so that the
+        block-output ReLU backward g3 = (dC + d_next) * (y > 0) happens in that dgrad's epilogue (residual + mask tiles) and
+        never as a pass of its own. Likewise every bottleneck hands the previous block an already masked gradient."""
+        from_next = None          # d(loss)/d(stage output) flowing down from the later stage (not yet masked)
         for stage, blks in reversed(self.blocks):
             if stage == "res2":
                 break
-            dy, dy2 = extra[stage], from_next
-            for b, ctx in zip(reversed(blks), reversed(tape[stage])):
-                dy = self._block_bwd(b, ctx, dy, dy2)
-                dy2 = None
-            from_next = dy
+            conv, dl, hw = lateral[stage]
+            saved = tape[stage]
+            g3 = conv.dgrad(dl, hw, residual=from_next, relu_mask=saved[-1][3])
+            for i in range(len(blks) - 1, -1, -1):
+                g3 = self._block_bwd(blks[i], saved[i], g3, mask_input=i > 0)
+            from_next = g3
 
     def _block_fwd(self, b, x, save):
         a = b["conv1"].fwd(x, relu=True)
@@ -288,10 +292,12 @@ class EngineBase:
         y = b["conv3"].fwd(m, residual=sc, relu=True)
         return y, ((x, a, m, y) if save else None)
 
-    def _block_bwd(self, b, ctx, dy, dy2=None):
+    def _block_bwd(self, b, ctx, g3, mask_input=False):
+        """g3 = d(loss)/d(conv3 + shortcut) (the block-output ReLU is already applied to it). Returns d(loss)/d(block input);
+        with mask_input it is multiplied by (input > 0), i.e. it IS the g3 of the previous block of the stage (whose output
+        this input is)."""
         x, a, m, y = ctx
         H, W = x.shape[1], x.shape[2]
-        g3 = ops.relu_bwd(dy, y, dy2)
         b["conv3"].wgrad(m, g3)
         g2 = b["conv3"].dgrad(g3, (m.shape[1], m.shape[2]), relu_mask=m)
         b["conv2"].wgrad(a, g2)
@@ -301,14 +307,16 @@ class EngineBase:
             b["shortcut"].wgrad(x, g3)
         if not b["need_dx"]:
             return None
+        mask = x if mask_input else None
         if "shortcut" in b:
             if b["stride"] == 2:
+                assert mask is None       # strided blocks open a stage: their input gradient is masked by the lateral dgrad
                 xc = b["conv1"].dgrad_compact(g1)
                 xs = b["shortcut"].dgrad_compact(g3, residual=xc)
                 return ops.zero_stuff_s2(xs, H, W)
             xs = b["shortcut"].dgrad(g3, (H, W))
-            return b["conv1"].dgrad(g1, (H, W), residual=xs)
-        return b["conv1"].dgrad(g1, (H, W), residual=g3)
+            return b["conv1"].dgrad(g1, (H, W), residual=xs, relu_mask=mask)
+        return b["conv1"].dgrad(g1, (H, W), residual=g3, relu_mask=mask)
 
     # ------------------------------------------------------------------------------------ optimiser hooks
     def sgd_step(self, lr, momentum, wd, wd_norm, first_step, grad_scale=1.0, lr_dev=None):

@@ -176,9 +176,9 @@ class FcosEngine(EngineBase):
         accumulating into the gradient arena (wgrad uses fp32 atomics, so repeated calls add up)."""
         tape, geom, N = fwd["tape"], fwd["geom"], fwd["N"]
         dfeat = self.head_backward(tape, geom, N, dcls, dbox)
-        extra = self.fpn_backward(tape, geom, N, dfeat)
-        # trunk: res5 <- dc5 ; res4 <- dc4 + d(res5 input) ; res3 <- dc3 + d(res4 input)
-        self.trunk_backward(tape, extra)
+        lateral = self.fpn_backward(tape, geom, N, dfeat)
+        # trunk: res5 <- dC5 ; res4 <- dC4 + d(res5 input) ; res3 <- dC3 + d(res4 input)
+        self.trunk_backward(tape, lateral)
         return None
 
     def head_backward(self, tape, geom, N, dcls, dbox):
@@ -200,7 +200,7 @@ class FcosEngine(EngineBase):
         return acc
 
     def fpn_backward(self, tape, geom, N, dfeat):
-        """-> {"res5": dC5, "res4": dC4, "res3": dC3}: gradients leaving the FPN laterals towards the trunk."""
+        """-> {"res5": (lateral conv, d(lateral output), (H, W)), ...}: what trunk_backward needs to send the gradients down."""
         d3, d4, d5, d6, d7 = self.level_views(dfeat, geom, N, 256)
         c3, c4, c5, lat3, lat4, lat5, p5, p6, p6r = tape["fpn"]
         hw = geom.hw
@@ -220,7 +220,5 @@ class FcosEngine(EngineBase):
         self.fpn_lat[3].wgrad(c3, dl3)
         self.fpn_lat[4].wgrad(c4, dl4)
         self.fpn_lat[5].wgrad(c5, dl5)
-        dc3 = self.fpn_lat[3].dgrad(dl3, hw[0])
-        dc4 = self.fpn_lat[4].dgrad(dl4, hw[1])
-        dc5 = self.fpn_lat[5].dgrad(dl5, hw[2])
-        return {"res5": dc5, "res4": dc4, "res3": dc3}
+        # the laterals' data-gradients are launched by trunk_backward (fused with the stage-output ReLU backward)
+        return {"res5": (self.fpn_lat[5], dl5, hw[2]), "res4": (self.fpn_lat[4], dl4, hw[1]), "res3": (self.fpn_lat[3], dl3, hw[0])}

@@ -239,8 +239,7 @@ class RcnnEngine(EngineBase):
         tape, geom, N = fwd["tape"], fwd["geom"], fwd["N"]
         dlev = self.roi_backward(fwd, ctx, gout_roi)
         dfe = self.rpn_backward(fwd, ctx, gout_rpn)
-        extra = self.fpn_backward(tape, geom, N, dfe, dlev)
-        self.trunk_backward(tape, extra)
+        self.trunk_backward(tape, self.fpn_backward(tape, geom, N, dfe, dlev))
 
     def roi_backward(self, fwd, ctx, gout_roi):
         """Box-head backward -> fp32 gradient maps of p2..p5 (ROIAlign backward accumulates with atomics)."""
@@ -279,7 +278,7 @@ class RcnnEngine(EngineBase):
 
     def fpn_backward(self, tape, geom, N, dfe, dlev):
         """dfe: level-major bf16 gradient of p2..p6 (RPN), dlev: fp32 gradients of p2..p5 (ROI heads) or None.
-        -> {"res5": dC5, "res4": dC4, "res3": dC3}."""
+        -> {"res5": (lateral conv, d(lateral output), (H, W)), ...} for trunk_backward."""
         dP = []
         for l, g in enumerate(self.level_views(dfe, geom, N, 256)):
             dP.append(R.add_f32_bf16(dlev[l], g) if (l < 4 and dlev is not None) else g)
@@ -297,7 +296,5 @@ class RcnnEngine(EngineBase):
         self.fpn_lat[2].wgrad(c2, dl[2])                                              # res2 is frozen: no dgrad below
         for lvl, c in ((3, c3), (4, c4), (5, c5)):
             self.fpn_lat[lvl].wgrad(c, dl[lvl])
-        dc3 = self.fpn_lat[3].dgrad(dl[3], hw[1])
-        dc4 = self.fpn_lat[4].dgrad(dl[4], hw[2])
-        dc5 = self.fpn_lat[5].dgrad(dl[5], hw[3])
-        return {"res5": dc5, "res4": dc4, "res3": dc3}
+        # the laterals' data-gradients are launched by trunk_backward (fused with the stage-output ReLU backward)
+        return {"res5": (self.fpn_lat[5], dl[5], hw[3]), "res4": (self.fpn_lat[4], dl[4], hw[2]), "res3": (self.fpn_lat[3], dl[3], hw[1])}
