@@ -80,7 +80,10 @@ struct ConvFwdArgs {
   int aux_dbl;                      // 1: two aux staging tiles per epilogue warp (memory-bound convs: see the epilogue)
   int no_pad;                       // 1: the dynamic shared buffer must already be 1024-byte aligned
   int aux_kind;                     // 0 none, 1 residual tile via TMA, 2 relu-mask tile via TMA, 3 both (two tiles per warp)
-  int manual;                       // 1: epilogue with plain loads/stores (res_up2, residual+mask, Cout < 64)
+  int manual;                       // 1: epilogue with plain loads/stores (res_up2, Cout < 64)
+  int out_tma;                      // 1: output tiles staged in shared memory and written by TMA stores (memory-bound 1x1 convs);
+                                    // 2: staged IN PLACE in the aux tile the lane has just consumed (no extra shared memory)
+  int aux_bytes;                    // bytes of aux staging in front of the output staging tiles
   const float* scale;
   const float* shift;
   const __nv_bfloat16* residual;
@@ -98,9 +101,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 __device__ __forceinline__ uint32_t swz(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 // zero the bf16 halves of `o` whose mask element is not > 0 (sign set or magnitude zero)
 __device__ __forceinline__ uint32_t mask_bf16x2(uint32_t o, uint32_t m) {
-  if ((m & 0x8000u) || !(m & 0x7FFFu)) o &= 0xFFFF0000u;
-  if ((m & 0x80000000u) || !(m & 0x7FFF0000u)) o &= 0x0000FFFFu;
-  return o;
+  const __nv_bfloat162 mv = *reinterpret_cast<const __nv_bfloat162*>(&m);
+  return o & __hgt2_mask(mv, __float2bfloat162_rn(0.f));      // one HSET2.BM: 0xFFFF per half whose mask element is > 0
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -244,6 +246,10 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
     const uint32_t aux_tx = both ? 2 * EPI_TILE_BYTES : EPI_TILE_BYTES;
     uint8_t* atile0 = aux_stage + ew * ((a.aux_dbl || both) ? 2 : 1) * EPI_TILE_BYTES;
     uint64_t* my_aux_bar = aux_bar + ew * 2;
+    // out_tma: one 4 KiB staging tile per warp behind the aux tiles; the lane's 8 x 16-byte row goes there (same 128B swizzle
+    // as the tensor map) and lane 0 writes the [32 rows x 64 columns] tile with ONE bulk tensor store: full 128-byte lines to
+    // L2 and 32 shared-memory wavefronts instead of 128 scattered-sector global-store wavefronts per warp and tile.
+    uint8_t* otile_sep = aux_stage + a.aux_bytes + ew * EPI_TILE_BYTES;
     uint32_t acc = 0, acc_phase = 0, aux_phase = 0, it = 0;
     int staged_n_tile = -1;
     if (use_aux && lane == 0 && (int)blockIdx.x < num_tiles) {   // aux tile of this CTA's first tile
@@ -261,6 +267,7 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
       if (dbl) {                        // request the next tile's chunk into the other slot (last read in tile it-1)
         __syncwarp();
         const int tn = t + gridDim.x;
+        if (lane == 0 && a.out_tma == 2) bulk_wait_read0();     // ... and by the in-place store of tile it-1
         if (lane == 0 && tn < num_tiles) {
           const int n_tile2 = tn % a.n_tiles, m_tile2 = tn / a.n_tiles;
           const int lv2 = level_of(a.lt, m_tile2);
@@ -270,7 +277,8 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
                       a.lt.row_off[lv2] + (m_tile2 - a.lt.tile_off[lv2]) * BM + quad * 32);
         }
       }
-      const uint8_t* atile = atile0 + (dbl ? (it & 1) : 0) * EPI_TILE_BYTES;
+      uint8_t* atile = atile0 + (dbl ? (it & 1) : 0) * EPI_TILE_BYTES;
+      uint8_t* otile = a.out_tma == 2 ? atile : otile_sep;
       const int n_tile = t % a.n_tiles, m_tile = t / a.n_tiles;
       const int lv = level_of(a.lt, m_tile);
       const int ml = (m_tile - a.lt.tile_off[lv]) * BM + quad * 32 + lane;     // row inside the level
@@ -297,6 +305,10 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (has_chunk) {
+        if (a.out_tma == 1) {            // the previous tile's store must have finished READING the staging tile
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+        }
         if (use_aux) {
           if (dbl) mbar_wait(&my_aux_bar[it & 1], (it >> 1) & 1);
           else mbar_wait(&my_aux_bar[0], aux_phase);
@@ -372,10 +384,23 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 8; ++i) ow[i] = mask_bf16x2(ow[i], yw[i]);
             }
-            // one 256-bit store per lane (STG.256): half the LSU wavefronts of two 128-bit stores
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(a.out + (size_t)m * a.ldo + nj),
-                         "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7])
-                         : "memory");
+            if (a.out_tma) {
+              *reinterpret_cast<uint4*>(otile + swz(lane, 2 * j)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+              *reinterpret_cast<uint4*>(otile + swz(lane, 2 * j + 1)) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+            } else {
+              // one 256-bit store per lane (STG.256): half the LSU wavefronts of two 128-bit stores
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(a.out + (size_t)m * a.ldo + nj),
+                           "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7])
+                           : "memory");
+            }
+          }
+        }
+        if (a.out_tma) {                 // rows past M are clipped by the tensor map (single-level launches only)
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, otile, nbase + c0, m_tile * BM + quad * 32);
+            bulk_commit();
           }
         }
       }
@@ -387,6 +412,7 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
         aux_phase ^= 1;
         __syncwarp();                   // every lane finished reading the aux tile
         const int tn = t + gridDim.x;
+        if (lane == 0 && a.out_tma == 2) bulk_wait_read0();     // the in-place store has read the tile
         if (lane == 0 && tn < num_tiles) {
           const int n_tile2 = tn % a.n_tiles, m_tile2 = tn / a.n_tiles;
           const int lv2 = level_of(a.lt, m_tile2);
@@ -401,6 +427,7 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
     }
   }
 
+  if (a.out_tma && warp >= 2 && lane == 0) bulk_wait0();      // all output tiles written before the CTA retires
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -691,9 +718,24 @@ static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, 
   a.aux_dbl = (dbl_on && a.aux_kind != 0 && a.aux_kind != 3 && R * S * Cin <= 128) ? 1 : 0;
   // kind 3 keeps two tiles per ACTIVE epilogue warp (four warps per 64-column chunk of the tile)
   const int aux_tiles = a.aux_kind == 3 ? 2 * 4 * ((block_n + 63) / 64) : (a.aux_kind ? (a.aux_dbl ? 32 : 16) : 0);
-  a.no_pad = ((a.aux_dbl || a.aux_kind == 3) && pick_stages(block_n, aux_tiles, 1024) < 2) ? 1 : 0;
+  // TMA-store epilogue for the memory-bound 1x1 convolutions (UT2_TMA_STORE=0 disables, =2 forces it for every single-level
+  // launch): 16 more staging tiles; not next to the 32 tiles of aux_dbl / aux_kind 3 with 256-wide tiles (no room).
+  static int tma_store = -1;
+  if (tma_store < 0) { const char* e = getenv("UT2_TMA_STORE"); tma_store = e ? atoi(e) : 1; }
+  a.out_tma = 0;
+  if (tma_store && num_levels == 1 && !a.manual && Cout % 64 == 0 && (tma_store == 2 || R * S == 1)) {
+    const int num_kb = R * S * ((Cin + BK - 1) / BK);
+    const int want = num_kb < 3 ? num_kb : 3;
+    if (a.aux_kind == 0)
+      a.out_tma = (tma_store == 2 || num_kb <= 4) && pick_stages(block_n, 16, 1024) >= (want < 2 ? 2 : want) ? 1 : 0;
+    else if (a.aux_dbl || tma_store == 2)   // the lane's aux row has been consumed when its output row is ready: stage in place
+      a.out_tma = 2;                        // (single aux tile: the next prefetch would wait for the store -> measured slower)
+  }
+  a.aux_bytes = aux_tiles * EPI_TILE_BYTES;
+  const int aux_tiles_total = aux_tiles + (a.out_tma == 1 ? 16 : 0);
+  a.no_pad = ((a.aux_dbl || a.aux_kind == 3) && pick_stages(block_n, aux_tiles_total, 1024) < 2) ? 1 : 0;
   const int smem_pad = a.no_pad ? 0 : 1024;
-  a.stages = pick_stages(block_n, aux_tiles, smem_pad);
+  a.stages = pick_stages(block_n, aux_tiles_total, smem_pad);
   if (a.stages < 2) return ut2_fail(-5, "conv_fwd: shared memory budget");
   CUtensorMap tw, to, ta;
   int rc = make_tmap_2d_bf16(&tw, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64, block_n);
@@ -719,7 +761,7 @@ static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, 
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_fwd_kernel<<<grid, NUM_THREADS, smem_bytes(a.stages, block_n, aux_tiles, smem_pad), static_cast<cudaStream_t>(stream)>>>(
+  conv_fwd_kernel<<<grid, NUM_THREADS, smem_bytes(a.stages, block_n, aux_tiles_total, smem_pad), static_cast<cudaStream_t>(stream)>>>(
       tx, tw, to, ta, ta2, a);
   return ut2_check_launch("conv_fwd");
 }

@@ -78,6 +78,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
 // im2col-mode load of an NHWC activation: coordinates are the *base pixel* {c, w, h, n} of the
 // first output position; {off_w, off_h} select the filter tap. The TMA unit walks W, then H,
 // then N inside the descriptor's bounding box and zero-fills halo / out-of-tensor pixels.
+// shared -> global tile store (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(smem_u32(src)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* m, uint64_t* bar,
                                                    int32_t c, int32_t w, int32_t h, int32_t n,
                                                    uint16_t off_w, uint16_t off_h) {
