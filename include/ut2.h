@@ -75,6 +75,8 @@ int ut2_relu_bwd_bf16(const void* dy, const void* dy2, const void* y, void* g, l
 int ut2_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
 int ut2_zero_stuff_s2_nhwc(const void* in, void* out, int N, int P, int Q, int H, int W, int C, int oh, int ow, void* stream);
 int ut2_colsum_bf16(const void* g, float* db, int M, int C, void* stream);                             /* conv bias gradients */
+/* the same for up to 16 (gradient matrix [M_i, C_i], bias gradient) pairs in one launch; HOST arrays of device pointers */
+int ut2_colsum_bf16_batched(const void* const* gs, float* const* dbs, const int* Ms, const int* Cs, int n, void* stream);
 int ut2_frozen_bn_fold(const float* w, const float* b, const float* mean, const float* var, float eps, float* scale,
                        float* shift, int C, void* stream);                                             /* [D2] FrozenBatchNorm2d */
 int ut2_cast_f32_bf16(const float* x, void* y, long long n, void* stream);

@@ -6,6 +6,7 @@
 //   pixel normalisation + ImageList padding   ubteacher/modeling/one_stage_detector.py:88-90,165-167
 //   BasicStem / max_pool / FPN top-down        ubteacher/modeling/backbone/fpn.py:59-78 -> [D2]
 #include "ut2_internal.h"
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
 
@@ -242,12 +243,70 @@ __global__ void zero_stuff_kernel(const bf16* __restrict__ in, bf16* __restrict_
 // db[c] += sum_m g[m, c]; g is [M, C] bf16, C % 8 == 0. One thread = one 16-byte vector (8 channels) of a row, so a
 // warp reads whole 512-byte rows; per-thread fp32 partials over a strided set of rows, shared-memory reduce across
 // the threads that own the same channel group, one atomicAdd per channel per block.
+template <int UNR>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ g, float* __restrict__ db, int M, int C8, int rows_per_block) {
   const int rpp = 256 / C8;                       // rows per pass
   const int cg = threadIdx.x % C8, ro = threadIdx.x / C8;
   const int m0 = blockIdx.x * rows_per_block;
   const int m1 = min(M, m0 + rows_per_block);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (ro < rpp) {
+    for (int m = m0 + ro; m < m1; m += UNR * rpp) {
+      uint4 v[UNR];
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const int mm = m + q * rpp;
+        v[q] = mm < m1 ? __ldg(reinterpret_cast<const uint4*>(g) + (size_t)mm * C8 + cg) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const uint32_t u[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s[2 * j] += bflo(u[j]); s[2 * j + 1] += bfhi(u[j]); }
+      }
+    }
+  }
+  __shared__ float red[256][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = s[j];
+  __syncthreads();
+  if (ro == 0) {
+    for (int k = 1; k < rpp; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += red[k * C8 + cg][j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(db + cg * 8 + j, s[j]);
+  }
+}
+
+// Batched column sums: up to 16 (gradient matrix, bias-gradient) pairs in ONE launch. The conv bias gradients of a backward
+// pass (FPN laterals / outputs, P6 / P7, predictors, RPN head: a dozen matrices from 77 to 270 000 rows) cost more in launch
+// tails than in bandwidth when they run one by one; here every block takes a row range of one matrix.
+constexpr int CS_MAX = 16;
+struct ColsumBatch {
+  const bf16* g[CS_MAX];
+  float* db[CS_MAX];
+  int M[CS_MAX], C8[CS_MAX], rows[CS_MAX];
+  int blk_off[CS_MAX + 1];
+  int n;
+};
+__global__ void __launch_bounds__(256)
+colsum_batched_kernel(const __grid_constant__ ColsumBatch b) {
+  int e = 0;
+#pragma unroll
+  for (int i = 1; i < CS_MAX; ++i)
+    if (i < b.n && (int)blockIdx.x >= b.blk_off[i]) e = i;
+  const bf16* g = b.g[0];
+  float* db = b.db[0];
+  int M = b.M[0], C8 = b.C8[0], rows = b.rows[0], off = b.blk_off[0];
+#pragma unroll
+  for (int i = 1; i < CS_MAX; ++i)
+    if (e == i) { g = b.g[i]; db = b.db[i]; M = b.M[i]; C8 = b.C8[i]; rows = b.rows[i]; off = b.blk_off[i]; }
+  const int rpp = 256 / C8;
+  const int cg = threadIdx.x % C8, ro = threadIdx.x / C8;
+  const int m0 = ((int)blockIdx.x - off) * rows;
+  const int m1 = min(M, m0 + rows);
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (ro < rpp) {
     for (int m = m0 + ro; m < m1; m += 4 * rpp) {
@@ -395,13 +454,43 @@ extern "C" int ut2_colsum_bf16(const void* g, float* db, int M, int C, void* str
   const int C8 = C / 8;
   // one block per SM, except for the >= 256 MB gradients of the R-CNN p2 level / level-major RPN conv, where more 16-byte
   // loads in flight pay for the extra per-block reductions and atomics (measured: 148 is better below, 4 x 148 above)
-  int blocks = M >= 500000 ? 148 * 4 : 148;
+  static int mult = -1, unr = -1;
+  if (mult < 0) { const char* e = getenv("UT2_COLSUM_MULT"); mult = e ? atoi(e) : 0; e = getenv("UT2_COLSUM_UNR"); unr = e ? atoi(e) : 4; }
+  int blocks = mult > 0 ? 148 * mult : (M >= 500000 ? 148 * 4 : 148);
   int rows = (M + blocks - 1) / blocks;
   const int rpp = 256 / C8;
   if (rows < 8 * rpp) rows = 8 * rpp;
   blocks = (M + rows - 1) / rows;
-  colsum_kernel<<<blocks, 256, 0, STREAM>>>(static_cast<const bf16*>(g), db, M, C8, rows);
+  if (unr == 8) colsum_kernel<8><<<blocks, 256, 0, STREAM>>>(static_cast<const bf16*>(g), db, M, C8, rows);
+  else colsum_kernel<4><<<blocks, 256, 0, STREAM>>>(static_cast<const bf16*>(g), db, M, C8, rows);
   return ut2_check_launch("colsum");
+}
+
+// gs / dbs / Ms / Cs: HOST arrays of n <= 16 device pointers / sizes (C % 8 == 0, C <= 256 so that a block covers whole rows).
+extern "C" int ut2_colsum_bf16_batched(const void* const* gs, float* const* dbs, const int* Ms, const int* Cs, int n, void* stream) {
+  if (n <= 0) return 0;
+  if (n > CS_MAX || !gs || !dbs || !Ms || !Cs) return ut2_fail(-1, "colsum_batched: 1..16 entries");
+  ColsumBatch b;
+  long long total = 0;
+  for (int i = 0; i < n; ++i) {
+    if (Cs[i] % 8 || Cs[i] <= 0 || Cs[i] > 2048 || !gs[i] || !dbs[i]) return ut2_fail(-2, "colsum_batched: need C % 8 == 0, C <= 2048");
+    total += (long long)Ms[i] * Cs[i];
+  }
+  // ~2 blocks per SM in total, shared out by size; at least 8 row passes per block
+  const long long per_block = (total + 148 * 2 - 1) / (148 * 2);
+  b.n = n;
+  b.blk_off[0] = 0;
+  for (int i = 0; i < CS_MAX; ++i) {
+    const int j = i < n ? i : n - 1;
+    b.g[i] = static_cast<const bf16*>(gs[j]); b.db[i] = dbs[j]; b.M[i] = Ms[j]; b.C8[i] = Cs[j] / 8;
+    const int rpp = 256 / b.C8[i] > 0 ? 256 / b.C8[i] : 1;
+    long long rows = per_block / Cs[j];
+    if (rows < 8 * rpp) rows = 8 * rpp;
+    b.rows[i] = (int)rows;
+    b.blk_off[i + 1] = b.blk_off[i] + (i < n ? (int)((Ms[j] + rows - 1) / rows) : 0);
+  }
+  colsum_batched_kernel<<<b.blk_off[n], 256, 0, STREAM>>>(b);
+  return ut2_check_launch("colsum_batched");
 }
 
 extern "C" int ut2_pack_conv_weight(const float* w, void* wf, void* wt, int Cout, int Cin, int R, int S, int CoutT,

@@ -175,10 +175,14 @@ class FcosEngine(EngineBase):
         """Back-propagate d(loss)/d(cls_out), d(loss)/d(box_out) through head, FPN and res5..res3,
         accumulating into the gradient arena (wgrad uses fp32 atomics, so repeated calls add up)."""
         tape, geom, N = fwd["tape"], fwd["geom"], fwd["N"]
-        dfeat = self.head_backward(tape, geom, N, dcls, dbox)
-        lateral = self.fpn_backward(tape, geom, N, dfeat)
-        # trunk: res5 <- dC5 ; res4 <- dC4 + d(res5 input) ; res3 <- dC3 + d(res4 input)
-        self.trunk_backward(tape, lateral)
+        ops.COLSUM_QUEUE = []           # conv bias gradients: queued, one batched launch at the end
+        try:
+            dfeat = self.head_backward(tape, geom, N, dcls, dbox)
+            lateral = self.fpn_backward(tape, geom, N, dfeat)
+            # trunk: res5 <- dC5 ; res4 <- dC4 + d(res5 input) ; res3 <- dC3 + d(res4 input)
+            self.trunk_backward(tape, lateral)
+        finally:
+            ops.colsum_flush()
         return None
 
     def head_backward(self, tape, geom, N, dcls, dbox):

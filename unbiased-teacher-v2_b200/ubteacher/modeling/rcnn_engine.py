@@ -237,9 +237,13 @@ class RcnnEngine(EngineBase):
         """gout_rpn / gout_roi: float[2] device tensors = d(total)/d{loss_rpn_cls, loss_rpn_loc} / d{loss_cls, loss_box_reg}.
         Accumulates into the gradient arena (wgrad uses fp32 atomics, so repeated calls add up)."""
         tape, geom, N = fwd["tape"], fwd["geom"], fwd["N"]
-        dlev = self.roi_backward(fwd, ctx, gout_roi)
-        dfe = self.rpn_backward(fwd, ctx, gout_rpn)
-        self.trunk_backward(tape, self.fpn_backward(tape, geom, N, dfe, dlev))
+        ops.COLSUM_QUEUE = []           # conv bias gradients: queued, one batched launch at the end
+        try:
+            dlev = self.roi_backward(fwd, ctx, gout_roi)
+            dfe = self.rpn_backward(fwd, ctx, gout_rpn)
+            self.trunk_backward(tape, self.fpn_backward(tape, geom, N, dfe, dlev))
+        finally:
+            ops.colsum_flush()
 
     def roi_backward(self, fwd, ctx, gout_roi):
         """Box-head backward -> fp32 gradient maps of p2..p5 (ROIAlign backward accumulates with atomics)."""

@@ -185,9 +185,30 @@ def zero_stuff_s2(g, H, W, oh=0, ow=0):
     return out
 
 
+# set to a list by an engine's backward: conv bias gradients are then queued and flushed as ONE batched launch
+COLSUM_QUEUE = None
+
+
 def colsum(g2d, db):
     M, C = g2d.shape
+    if COLSUM_QUEUE is not None and C <= 256:
+        COLSUM_QUEUE.append((g2d, db))        # keeps the gradient tensor alive until the flush
+        return
     _C.counted_call("ut2_colsum_bf16", g2d, db, M, C)
+
+
+def colsum_flush():
+    """Launch the queued column sums (16 per launch) and leave queueing mode."""
+    global COLSUM_QUEUE
+    q, COLSUM_QUEUE = COLSUM_QUEUE, None
+    for i in range(0, len(q or []), 16):
+        part = q[i:i + 16]
+        n = len(part)
+        gs = (ctypes.c_void_p * n)(*[g.data_ptr() for g, _ in part])
+        dbs = (ctypes.c_void_p * n)(*[d.data_ptr() for _, d in part])
+        Ms = (ctypes.c_int * n)(*[int(g.shape[0]) for g, _ in part])
+        Cs = (ctypes.c_int * n)(*[int(g.shape[1]) for g, _ in part])
+        _C.counted_call("ut2_colsum_bf16_batched", gs, dbs, Ms, Cs, n)
 
 
 def pack_conv_weight(w_master, wf, wt, cout, cin, R, S, coutT):
