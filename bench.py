@@ -333,6 +333,8 @@ def main():
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     if world > 1:
+        # the segment all-reduces run under the backward pass on a few SMs (engine/trainer.py:_begin_overlap)
+        os.environ.setdefault("NCCL_MAX_CTAS", "8")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from ubteacher import _C, ops
     from ubteacher.d2compat.events import EventStorage

@@ -74,6 +74,9 @@ int ut2_downsample2x_sum_nhwc(const void* g, const void* addend, void* gtop, int
 int ut2_relu_bwd_bf16(const void* dy, const void* dy2, const void* y, void* g, long long n, void* stream);
 int ut2_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
 int ut2_zero_stuff_s2_nhwc(const void* in, void* out, int N, int P, int Q, int H, int W, int C, int oh, int ow, void* stream);
+/* SM budget of the persistent conv kernels: lowered by the trainer while NCCL all-reduces of finished gradient segments run
+ * on a side stream (DDP's bucketed all-reduce inside backward, reference engine/trainer.py:60-63,428). 0 = whole device. */
+int ut2_set_sm_limit(int n);
 int ut2_colsum_bf16(const void* g, float* db, int M, int C, void* stream);                             /* conv bias gradients */
 /* the same for up to 16 (gradient matrix [M_i, C_i], bias gradient) pairs in one launch; HOST arrays of device pointers */
 int ut2_colsum_bf16_batched(const void* const* gs, float* const* dbs, const int* Ms, const int* Cs, int n, void* stream);

@@ -629,7 +629,7 @@ static int num_sms() {
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  return g_num_sms;
+  return ut2_sm_budget(g_num_sms);
 }
 
 static int pick_block_n(int cout) {

@@ -26,3 +26,13 @@ extern "C" int ut2_device_sm_count(void) {
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
   return n;
 }
+
+// SM budget of the persistent / one-wave kernels (conv forward + data-gradient, weight-gradient split-K). The trainer lowers
+// it while gradient all-reduces run on a side stream: those kernels size their grids to the device, and a grid that fills
+// all SMs cannot finish before the collective's CTAs release theirs. 0 = the whole device.
+static int g_sm_limit = 0;
+extern "C" int ut2_set_sm_limit(int n) {
+  g_sm_limit = n > 0 ? n : 0;
+  return 0;
+}
+int ut2_sm_budget(int device_sms) { return (g_sm_limit > 0 && g_sm_limit < device_sms) ? g_sm_limit : device_sms; }

@@ -8,3 +8,6 @@ int ut2_fail(int code, const char* msg);
 int ut2_check_launch(const char* what);
 
 static inline int ut2_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// SMs the persistent kernels may fill: the device's count, or the limit set through ut2_set_sm_limit() (ut2_core.cu).
+int ut2_sm_budget(int device_sms);

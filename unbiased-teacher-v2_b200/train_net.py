@@ -55,6 +55,7 @@ def main(args):
     if world > 1:
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
+        os.environ.setdefault("NCCL_MAX_CTAS", "8")      # segment all-reduces run under the backward pass on a few SMs
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
         args.opts = list(args.opts or []) + ["MODEL.DEVICE", f"cuda:{local}"]
     cfg = setup(args)

@@ -148,6 +148,10 @@ class UBTeacherTrainer:
         self.use_cuda_graph = False                     # enable_cuda_graph(): replay the whole semi-sup step
         self._graph = None
         self._static = None
+        # gradient all-reduce overlapped with the last backward pass of a step (UT2_OVERLAP_ALLREDUCE=0: one call after it)
+        self.overlap_allreduce = comm.get_world_size() > 1 and os.environ.get("UT2_OVERLAP_ALLREDUCE", "1") != "0"
+        self._comm_stream = None
+        self._grads_reduced = False
         if comm.get_world_size() > 1:                   # DDP's initial parameter broadcast
             torch.distributed.broadcast(model.engine.arena.data, 0)
             model.engine.refresh_operands()
@@ -506,16 +510,52 @@ class UBTeacherTrainer:
                 losses_u, pending_u = self.model.forward_train(unlabel_data_q, "unlabeled")
             record.update({k + "_pseudo": v for k, v in losses_u.items()})
             with nvtx_range("ut2.student_unlabeled_backward"):
+                self._begin_overlap()
                 self.model.backward_pending(pending_u, [[lam / (lam + 1.0), 0.0, lam / (lam + 1.0), 0.0],
                                                         [0.0, mu / (mu + 1.0), 0.0, 0.0]])
+                self._end_overlap()
         record["data_time"] = data_time
         self._write_metrics(record, bookkeeping)
         self._reduce_and_step(device_lr, bookkeeping)
 
+    # ---------------------------------------------------------------- overlapped gradient all-reduce
+    def _begin_overlap(self):
+        """Arm the engine's segment hook for the LAST backward of the step: as soon as the gradients of a segment (FPN + heads,
+        res5, res4, res3) are final, their NCCL all-reduce is enqueued on a side stream and runs under the rest of the
+        backward pass. The persistent conv kernels are sized to (SMs - NCCL CTAs) meanwhile: a grid that fills the device
+        could not finish before the collective's CTAs release their SMs."""
+        if not self.overlap_allreduce:
+            return
+        from .. import _C
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.model.device)
+            self._sm_total = int(_C.lib().ut2_device_sm_count())
+            self._nccl_ctas = int(os.environ.get("NCCL_MAX_CTAS", "8"))
+        grad = self.model.engine.arena.grad
+
+        def hook(lo, hi):
+            if hi <= lo:
+                return
+            self._comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm_stream), nvtx_range("ut2.grad_allreduce.segment"):
+                torch.distributed.all_reduce(grad[lo:hi])
+            _C.lib().ut2_set_sm_limit(self._sm_total - self._nccl_ctas)
+        self.model.engine.grad_hook = hook
+
+    def _end_overlap(self):
+        if not self.overlap_allreduce:
+            return
+        from .. import _C
+        self.model.engine.grad_hook = None
+        _C.lib().ut2_set_sm_limit(0)
+        torch.cuda.current_stream().wait_stream(self._comm_stream)
+        self._grads_reduced = True
+
     def _reduce_and_step(self, device_lr, bookkeeping):
-        if comm.get_world_size() > 1:       # the DDP gradient all-reduce, one contiguous buffer (mean in the SGD kernel)
+        if comm.get_world_size() > 1 and not self._grads_reduced:   # one contiguous buffer (mean folded into the SGD kernel)
             with nvtx_range("ut2.grad_allreduce"):
                 torch.distributed.all_reduce(self.model.engine.arena.grad)
+        self._grads_reduced = False
         with nvtx_range("ut2.sgd_and_repack"):
             self.optimizer.zero_grad()
             self.optimizer.step(use_device_lr=device_lr)
@@ -640,7 +680,9 @@ class UBRCNNTeacherTrainer(UBTeacherTrainer):
             record.update({k + "_pseudo": v for k, v in losses_u.items()})
             # loss_rpn_loc_pseudo * 0, loss_box_reg_pseudo * UNSUP_REG_LOSS_WEIGHT, the two classification terms * UNSUP_LOSS_WEIGHT
             with nvtx_range("ut2.student_unlabeled_backward"):
+                self._begin_overlap()
                 self.model.backward_pending(pending_u, [lam, 0.0, lam, mu])
+                self._end_overlap()
         record["data_time"] = data_time
         self._write_metrics(record, bookkeeping)
         self._reduce_and_step(device_lr, bookkeeping)

@@ -203,6 +203,24 @@ class EngineBase:
                 assert A.offset[p + ".weight"] == w0 + row * K and A.offset[p + ".bias"] == b0 + row, p
                 row += rows
         self.stem_w = torch.zeros(7, 7, 3, 64, dtype=torch.float32, device=self.device)
+        # Gradient-arena segments in the order the backward pass completes them: everything above the trunk ("top": FPN, heads,
+        # GroupNorm), then res5, res4, res3. `grad_hook(lo, hi)` — set by the trainer for the LAST backward of a step — is called
+        # as soon as a segment's gradients are final, so that its all-reduce overlaps the rest of the backward pass (the
+        # reference's DDP does the same with 25 MB buckets, engine/trainer.py:60-63).
+        self.grad_hook = None
+        bounds, prev = {}, None
+        for n, sp in A.specs.items():
+            if sp.group not in ("decay", "nodecay"):
+                continue
+            key = next((st for st in ("res3", "res4", "res5") if n.startswith(f"backbone.bottom_up.{st}.")), "top")
+            if key != prev:
+                assert key not in bounds, f"gradient arena: segment {key} is not contiguous"
+                bounds[key] = A.offset[n]
+                prev = key
+        order = sorted(bounds, key=bounds.get)
+        assert order == ["res3", "res4", "res5", "top"], order
+        ends = [bounds[k] for k in order[1:]] + [A.n_trainable]
+        self.grad_segments = {k: (bounds[k], e) for k, e in zip(order, ends)}
 
     # ------------------------------------------------------------------------------------ init
     def init_trunk_entry(self, name, v, g):
@@ -284,6 +302,8 @@ class EngineBase:
             for i in range(len(blks) - 1, -1, -1):
                 g3 = self._block_bwd(blks[i], saved[i], g3, mask_input=i > 0)
             from_next = g3
+            if self.grad_hook is not None:
+                self.grad_hook(*self.grad_segments[stage])
 
     def _block_fwd(self, b, x, save):
         a = b["conv1"].fwd(x, relu=True)

@@ -179,10 +179,12 @@ class FcosEngine(EngineBase):
         try:
             dfeat = self.head_backward(tape, geom, N, dcls, dbox)
             lateral = self.fpn_backward(tape, geom, N, dfeat)
-            # trunk: res5 <- dC5 ; res4 <- dC4 + d(res5 input) ; res3 <- dC3 + d(res4 input)
-            self.trunk_backward(tape, lateral)
         finally:
-            ops.colsum_flush()
+            ops.colsum_flush()          # the trunk convolutions have no bias
+        if self.grad_hook is not None:
+            self.grad_hook(*self.grad_segments["top"])
+        # trunk: res5 <- dC5 ; res4 <- dC4 + d(res5 input) ; res3 <- dC3 + d(res4 input)
+        self.trunk_backward(tape, lateral)
         return None
 
     def head_backward(self, tape, geom, N, dcls, dbox):

@@ -241,9 +241,12 @@ class RcnnEngine(EngineBase):
         try:
             dlev = self.roi_backward(fwd, ctx, gout_roi)
             dfe = self.rpn_backward(fwd, ctx, gout_rpn)
-            self.trunk_backward(tape, self.fpn_backward(tape, geom, N, dfe, dlev))
+            lateral = self.fpn_backward(tape, geom, N, dfe, dlev)
         finally:
-            ops.colsum_flush()
+            ops.colsum_flush()          # the trunk convolutions have no bias
+        if self.grad_hook is not None:
+            self.grad_hook(*self.grad_segments["top"])
+        self.trunk_backward(tape, lateral)
 
     def roi_backward(self, fwd, ctx, gout_roi):
         """Box-head backward -> fp32 gradient maps of p2..p5 (ROIAlign backward accumulates with atomics)."""
