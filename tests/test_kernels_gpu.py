@@ -484,3 +484,39 @@ def test_groupnorm_levels_full_size_vs_torch(N):
     for a, b in ((dgam, rg), (dbet, rb), (dbias, rbias)):
         e = (a.cpu() - b).norm() / b.norm()
         assert float(e) < 3e-3, float(e)
+
+
+@pytest.mark.parametrize("sizes,pad", [([(64, 96), (50, 77)], (64, 96)), ([(160, 224), (128, 192), (157, 223)], (160, 224)),
+                                       ([(800, 1333), (771, 1201)], (800, 1344))])
+def test_stem_pool_fused_vs_torch_and_split_kernels(sizes, pad):
+    """csrc/stem_pool.cu (normalise + space-to-depth, then the 7x7 s2 stem as a 4x4 s1 tcgen05 GEMM with FrozenBN / ReLU /
+    3x3 s2 max-pool in the epilogue) against fp32 torch on the same bf16-rounded pixels and filter, and against the separate
+    stem + max-pool kernels it replaces. Images smaller than the padded batch size exercise the ImageList zero padding; the
+    full-size case runs 11 column blocks x 10 row blocks per image (warm-up tiles, ring reuse across work items)."""
+    import torch.nn.functional as F
+    from ubteacher import ops
+    Hp, Wp = pad
+    g = torch.Generator().manual_seed(Hp + len(sizes))
+    imgs = [torch.randint(0, 256, (3, h, w), generator=g, dtype=torch.uint8) for h, w in sizes]
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.05
+    scale = torch.rand(64, generator=g) * 0.1 + 0.02
+    shift = torch.randn(64, generator=g) * 0.3
+    mean, std = [103.53, 116.28, 123.675], [1.0, 1.0, 1.0]
+    w_rsck = w.permute(2, 3, 1, 0).contiguous().cuda()
+    dev = [im.cuda() for im in imgs]
+    y = ops.stem_pool_batched(dev, w_rsck, scale.cuda(), shift.cuda(), mean, std, Hp, Wp)
+    N = len(imgs)
+    x1 = torch.empty((N, Hp // 2, Wp // 2, 64), dtype=torch.bfloat16, device="cuda")
+    ops.stem_conv_batched(dev, w_rsck, scale.cuda(), shift.cuda(), mean, std, x1, Hp // 2, Wp // 2)
+    y_split = ops.maxpool3x3s2(x1)
+    torch.cuda.synchronize()
+    assert y.shape == (N, Hp // 4, Wp // 4, 64)
+    xin = torch.zeros(N, 3, Hp, Wp)
+    for i, im in enumerate(imgs):
+        xin[i, :, :im.shape[1], :im.shape[2]] = ((im.float() - torch.tensor(mean).view(3, 1, 1)) / torch.tensor(std).view(3, 1, 1)).bfloat16().float()
+    ref = F.conv2d(xin, w.bfloat16().float(), None, 2, 3) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    ref = F.max_pool2d(F.relu(ref).bfloat16().float(), 3, 2, 1).permute(0, 2, 3, 1)
+    torch.testing.assert_close(y.float().cpu(), ref, rtol=1 / 128, atol=1e-2)
+    # same arithmetic, different fp32 accumulation order: at most one bf16 ulp on a few elements
+    d = (y.float() - y_split.float()).abs()
+    assert float(d.max()) <= 1 / 64 * float(y_split.float().abs().max()) and float((d > 0).float().mean()) < 0.02

@@ -6,6 +6,7 @@ One engine = one model replica (student or teacher): NHWC bf16 activations, fp32
 forward / backward schedule (no autograd tape, no host synchronisation).
 """
 import math
+import os
 
 import torch
 
@@ -15,6 +16,7 @@ from ..arena import PackPlan, ParamArena, Spec
 BF16 = torch.bfloat16
 RES_STAGES = [("res2", 3, 64, 256, 1), ("res3", 4, 128, 512, 2), ("res4", 6, 256, 1024, 2), ("res5", 3, 512, 2048, 2)]
 BN_EPS = 1e-5
+STEM_FUSED = os.environ.get("UT2_STEM_FUSED", "1") != "0"     # 0: separate stem and max-pool kernels (A/B runs)
 
 
 class Conv:
@@ -272,10 +274,13 @@ class EngineBase:
         N = len(images)
         sizes = [(int(im.shape[1]), int(im.shape[2])) for im in images]
         Hp, Wp = self.padded_size(sizes)
-        P, Q = Hp // 2, Wp // 2
-        x = torch.empty((N, P, Q, 64), dtype=BF16, device=self.device)
-        ops.stem_conv_batched(images, self.stem_w, self.stem.scale, self.stem.shift, self.pixel_mean, self.pixel_std, x, P, Q)
-        x = ops.maxpool3x3s2(x)
+        if STEM_FUSED:      # stem + max-pool in one pass: the 64-channel stem activation never reaches HBM (csrc/stem_pool.cu)
+            x = ops.stem_pool_batched(images, self.stem_w, self.stem.scale, self.stem.shift, self.pixel_mean, self.pixel_std, Hp, Wp)
+        else:
+            P, Q = Hp // 2, Wp // 2
+            x = torch.empty((N, P, Q, 64), dtype=BF16, device=self.device)
+            ops.stem_conv_batched(images, self.stem_w, self.stem.scale, self.stem.shift, self.pixel_mean, self.pixel_std, x, P, Q)
+            x = ops.maxpool3x3s2(x)
         feats = {}
         for stage, blks in self.blocks:
             saved = []

@@ -144,6 +144,26 @@ def stem_conv_batched(images, w_rsck, scale, shift, mean, std, out, P, Q):
                     f32(std[0]), f32(std[1]), f32(std[2]), out, P, Q)
 
 
+def stem_pool_batched(images, w_rsck, scale, shift, mean, std, Hp, Wp):
+    """Fused stem + max-pool: list of uint8 CHW device images -> [N, Hp/4, Wp/4, 64] bf16 (csrc/stem_pool.cu)."""
+    n = len(images)
+    dev = images[0].device
+    lib = _C.lib()
+    lib.ut2_stem_pool_workspace_bytes.restype = ctypes.c_longlong
+    wsb = lib.ut2_stem_pool_workspace_bytes(n, Hp, Wp)
+    if wsb <= 0:
+        raise RuntimeError("stem_pool: the padded size must be a multiple of 4")
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    out = torch.empty((n, Hp // 4, Wp // 4, 64), dtype=BF16, device=dev)
+    ptrs = (ctypes.c_void_p * n)(*[im.data_ptr() for im in images])
+    hs = (ctypes.c_int * n)(*[int(im.shape[1]) for im in images])
+    ws_ = (ctypes.c_int * n)(*[int(im.shape[2]) for im in images])
+    _C.counted_call("ut2_stem_pool_u8_batched", ptrs, hs, ws_, n, w_rsck, scale, shift, f32(mean[0]), f32(mean[1]), f32(mean[2]),
+                    f32(std[0]), f32(std[1]), f32(std[2]), ws, i64(wsb), out, Hp, Wp)
+    _C.launch_count += 1  # two kernels
+    return out
+
+
 def maxpool3x3s2(x):
     N, H, W, C = x.shape
     P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
