@@ -12,9 +12,9 @@
 // 2. stem_pool_tc_kernel: implicit GEMM on tcgen05, M = 128 (2 conv rows x 64 columns), N = 64, K = 4 filter rows x 64. The A
 //    operand of a tile is ONE tiled TMA box [5 rows][64 windows][128 B] of a tensor map whose "window" dimension has a 32-byte
 //    stride under a 128-byte inner extent (overlapping windows): k-block r' is rows (r', r'+1) of the box, no im2col copy, no
-//    per-thread gather. Warp-specialised: TMA producer, MMA issuer (16 MMAs per tile, TMEM double-buffered), four epilogue
-//    warps that apply scale / shift / ReLU, park the two conv rows in a 4-row shared-memory ring and emit one pooled row per
-//    tile from rows (2t-1, 2t, 2t+1). A CTA walks DOWN a 62-column block (31 pooled columns; one warm-up tile on top).
+//    per-thread gather. Warp-specialised: TMA producer, MMA issuer (16 MMAs per tile, TMEM double-buffered), eight epilogue
+//    warps that apply scale / shift / ReLU and park the two conv rows in an 8-row shared-memory ring, four pooling warps that
+//    emit one pooled row per tile from rows (2t-1, 2t, 2t+1), up to two tiles behind the epilogue. A CTA walks DOWN a 62-column block (31 pooled columns; one warm-up tile on top).
 // Same arithmetic as csrc/stem_tc.cu + ut2_maxpool3x3s2_nhwc (bf16 pixels x bf16 filter, fp32 accumulate, FrozenBN in the fp32
 // epilogue, max over bf16 values): results agree up to the fp32 accumulation order.
 #include "sm100_ptx.cuh"
@@ -30,8 +30,10 @@ constexpr int SP_STAGES = 3;
 constexpr int SP_ROW_BYTES = 64 * 128;         // one box row: 64 windows x 128 B
 constexpr int SP_STAGE_BYTES = 5 * SP_ROW_BYTES;      // 40 KiB
 constexpr int SP_B_BYTES = 4 * 64 * 128;       // 4 k-blocks x [64 filters][128 B]
-constexpr int SP_RING_BYTES = 4 * SP_ROW_BYTES;       // 4 conv rows x 64 pixels x 64 channels
-constexpr int SP_THREADS = 192;                // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue + pooling
+constexpr int SP_RING_BYTES = 8 * SP_ROW_BYTES;       // 8 conv rows x 64 pixels x 64 channels (slot = conv row & 7)
+constexpr int SP_THREADS = 448;                // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant), 10-13 pooling
+constexpr int SP_EPI = 256;                    // epilogue threads
+constexpr int SP_POOL = 128;                   // pooling threads
 constexpr int SP_ROWS_PER_ITEM = 20;           // pooled rows per work item (+ 1 warm-up tile)
 constexpr int SP_SMEM = 1024 + SP_STAGES * SP_STAGE_BYTES + SP_B_BYTES + SP_RING_BYTES + 1024;
 constexpr int SP_MAX_IMG = 32;
@@ -105,7 +107,9 @@ stem_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap, const StemPoolArgs
   uint64_t* empty_bar = full_bar + SP_STAGES;
   uint64_t* tfull_bar = empty_bar + SP_STAGES;      // [2]
   uint64_t* tempty_bar = tfull_bar + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* rfull_bar = tempty_bar + 2;             // [2] conv rows of tile it are in the ring (epilogue -> pooling)
+  uint64_t* rfree_bar = rfull_bar + 2;              // [2] pooling of tile it is done (pooling -> epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfree_bar + 2);
   float* s_ss = reinterpret_cast<float*>(tmem_slot + 2);      // scale[64] | shift[64]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -117,7 +121,9 @@ stem_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap, const StemPoolArgs
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], SP_EPI);
+      mbar_init(&rfull_bar[i], SP_EPI);
+      mbar_init(&rfree_bar[i], SP_POOL);
     }
     fence_barrier_init();
   }
@@ -204,53 +210,70 @@ stem_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap, const StemPoolArgs
         }
       }
     }
-  } else {
-    // -------------------------------------------------- epilogue + pooling: 128 threads, thread = one conv pixel of the tile
-    const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+  } else if (warp < 10) {
+    // -------------------------------------------------- epilogue: 256 threads. Two warps per TMEM lane quadrant (hardware
+    // rule: warp w reads lanes 32 (w % 4) ...), each takes 32 of the 64 channels of its 32 pixels; FrozenBN + ReLU, bf16, into
+    // the ring slot of the conv row. Pooling runs on its own warps, two tiles behind at most (rfull / rfree barriers).
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;                // 0: channels 0..31, 1: channels 32..63
     const int m = quad * 32 + lane;                  // accumulator row: conv row (m >> 6) of the pair, column c0 + (m & 63)
     const int ri = m >> 6, px = m & 63;
-    const int et = tid - 64;                         // 0..127
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, it = 0;
     for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
-      const int n = item / per_img, rem = item - n * per_img;
-      const int rb = rem / a.ncb, j = rem - rb * a.ncb;
+      const int rem = item % per_img;
+      const int rb = rem / a.ncb;
       const int t0 = rb * SP_ROWS_PER_ITEM, t1 = min(a.PP, t0 + SP_ROWS_PER_ITEM);
-      for (int tt = t0 > 0 ? t0 - 1 : 0; tt < t1; ++tt) {
+      const int first = t0 > 0 ? t0 - 1 : 0;
+      for (int tt = first; tt < t1; ++tt, ++it) {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 64;
-        uint32_t v[4][16];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 64 + half * 32;
+        uint32_t v[2][16];
         tmem_ld_32x16(taddr, v[0]);
         tmem_ld_32x16(taddr + 16, v[1]);
-        tmem_ld_32x16(taddr + 32, v[2]);
-        tmem_ld_32x16(taddr + 48, v[3]);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&tempty_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        // scale / shift / ReLU -> bf16 -> ring slot of conv row 2 tt + ri (chunks swizzled by the pixel index)
-        uint8_t* rrow = ring + ((2 * tt + ri) & 3) * SP_ROW_BYTES + px * 128;
+        // the slots of this tile's rows were last read by the pooling of tiles it-4 / it-3 (same work item) or by ANY tile of
+        // the previous item: wait for pooling(it-2), and at the top of an item also for pooling(it-1)
+        if (it >= 2) mbar_wait(&rfree_bar[it & 1], ((it - 2) >> 1) & 1);
+        if (tt == first && it >= 1) mbar_wait(&rfree_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+        uint8_t* rrow = ring + ((2 * tt + ri) & 7) * SP_ROW_BYTES + px * 128;
 #pragma unroll
-        for (int jq = 0; jq < 4; ++jq) {
+        for (int jq = 0; jq < 2; ++jq) {
           uint32_t o[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int c = jq * 16 + 2 * i;
+            const int c = half * 32 + jq * 16 + 2 * i;
             const float2 sc2 = *reinterpret_cast<const float2*>(s_ss + c), sh2 = *reinterpret_cast<const float2*>(s_ss + 64 + c);
             const float x0 = fmaxf(fmaf(__uint_as_float(v[jq][2 * i]), sc2.x, sh2.x), 0.f);
             const float x1 = fmaxf(fmaf(__uint_as_float(v[jq][2 * i + 1]), sc2.y, sh2.y), 0.f);
             __nv_bfloat162 hv = __floats2bfloat162_rn(x0, x1);
             o[i] = *reinterpret_cast<uint32_t*>(&hv);
           }
-          *reinterpret_cast<uint4*>(rrow + (((2 * jq) ^ (px & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<uint4*>(rrow + (((2 * jq + 1) ^ (px & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+          const int c16 = half * 4 + 2 * jq;           // 16-byte chunk of the pixel's 128-byte row
+          *reinterpret_cast<uint4*>(rrow + ((c16 ^ (px & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(rrow + (((c16 + 1) ^ (px & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_arrive(&rfull_bar[it & 1]);             // release semantics: the rows are visible to the pooling warps
+      }
+    }
+  } else {
+    // -------------------------------------------------- pooling: 128 threads, pooled row tt, columns 31 j + k:
+    // max over conv rows (2tt-1, 2tt, 2tt+1) x local columns (2k, 2k+1, 2k+2); 248 (column, 16-byte chunk) items per tile
+    const int pt = tid - 320;                        // 0..127
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
+      const int n = item / per_img, rem = item - n * per_img;
+      const int rb = rem / a.ncb, j = rem - rb * a.ncb;
+      const int t0 = rb * SP_ROWS_PER_ITEM, t1 = min(a.PP, t0 + SP_ROWS_PER_ITEM);
+      for (int tt = t0 > 0 ? t0 - 1 : 0; tt < t1; ++tt, ++it) {
+        mbar_wait(&rfull_bar[it & 1], (it >> 1) & 1);
         if (tt >= t0) {
-          // pooled row tt, columns 31 j + k: max over conv rows (2tt-1, 2tt, 2tt+1) x local columns (2k, 2k+1, 2k+2)
 #pragma unroll
           for (int rep = 0; rep < 2; ++rep) {
-            const int id = et + rep * 128;
+            const int id = pt + rep * 128;
             const int k = id >> 3, ch = id & 7;
             const int pq = 31 * j + k;
             if (k < 31 && pq < a.PQ) {
@@ -261,7 +284,7 @@ stem_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap, const StemPoolArgs
               for (int dr = -1; dr <= 1; ++dr) {
                 const int cr = 2 * tt + dr;
                 if (cr < 0) continue;                                              // pooling pad above the image
-                const uint8_t* rr = ring + (cr & 3) * SP_ROW_BYTES;
+                const uint8_t* rr = ring + (cr & 7) * SP_ROW_BYTES;
 #pragma unroll
                 for (int dc = 0; dc < 3; ++dc) {
                   const int lp = 2 * k + dc;
@@ -279,7 +302,7 @@ stem_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap, const StemPoolArgs
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");      // the next tile overwrites the slot of conv row 2 tt - 1
+        mbar_arrive(&rfree_bar[it & 1]);
       }
     }
   }
