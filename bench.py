@@ -411,10 +411,10 @@ def main():
         ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         traffic, traffic_note = None, None
         try:        # DRAM bytes of the dominant launch shape from the committed ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", "r01c_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
                 tj = json.load(f)
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-            traffic_note = (f"NOT measured live: read from the committed ncu --set full capture profiles/r01c_traffic.json; "
+            traffic_note = (f"NOT measured live: read from the committed ncu --set full capture profiles/r02_traffic.json; "
                             f"bytes per launch of the dominant shape {tj['shape']}: algorithmic {tj['algorithmic_bytes']} B; "
                             f"`achieved` averages all {len(prof['conv_fwd']) // prof_steps} conv_fwd launches of a step")
         except Exception:  # noqa: BLE001

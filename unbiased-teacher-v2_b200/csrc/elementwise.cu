@@ -476,8 +476,12 @@ extern "C" int ut2_colsum_bf16_batched(const void* const* gs, float* const* dbs,
     if (Cs[i] % 8 || Cs[i] <= 0 || Cs[i] > 2048 || !gs[i] || !dbs[i]) return ut2_fail(-2, "colsum_batched: need C % 8 == 0, C <= 2048");
     total += (long long)Ms[i] * Cs[i];
   }
-  // ~2 blocks per SM in total, shared out by size; at least 8 row passes per block
-  const long long per_block = (total + 148 * 2 - 1) / (148 * 2);
+  // two blocks per SM in total for the FCOS-sized batches (a few hundred MB), up to 16 per SM for the R-CNN ones (the p2 level
+  // and the level-major RPN gradient alone are 0.5 - 0.7 GB): about one block per MiB; at least 8 row passes per block
+  long long nblk = total * 2 / (1 << 20);
+  if (nblk < 148 * 2) nblk = 148 * 2;
+  if (nblk > 148 * 16) nblk = 148 * 16;
+  const long long per_block = (total + nblk - 1) / nblk;
   b.n = n;
   b.blk_off[0] = 0;
   for (int i = 0; i < CS_MAX; ++i) {

@@ -291,7 +291,7 @@ static int gn_min_px() {
   return v;
 }
 
-inline int fill_gn_levels(GnLevels& lv, int num_levels, const int* hws, int N) {
+inline int fill_gn_levels(GnLevels& lv, int num_levels, const int* hws, int N, bool bwd = false) {
   if (num_levels < 1 || num_levels > GN_MAXL) return -1;
   lv.num = num_levels;
   lv.N = N;
@@ -299,7 +299,13 @@ inline int fill_gn_levels(GnLevels& lv, int num_levels, const int* hws, int N) {
   for (int l = 0; l < num_levels; ++l) total += hws[l];
   // aim for ~148*4 blocks in total, spread over the levels by size, at least 256 pixels each (UT2_GN_MINPX): every block ends
   // in ~500 fp32 / fp64 atomics on the same few addresses, which dominates small batches when the blocks are short
-  const long long target = (total * N + 148 * 4 - 1) / (148 * 4);
+  static int mult_f = -1, mult_b = -1;
+  if (mult_f < 0) {
+    const char* e = getenv("UT2_GN_BLOCKS"); mult_f = e ? atoi(e) : 4; if (mult_f < 1) mult_f = 1;
+    e = getenv("UT2_GN_BLOCKS_BWD"); mult_b = e ? atoi(e) : 2; if (mult_b < 1) mult_b = 1;
+  }
+  const int mult = bwd ? mult_b : mult_f;
+  const long long target = (total * N + 148 * mult - 1) / (148 * mult);
   int row = 0;
   lv.blk_off[0] = 0;
   for (int l = 0; l < GN_MAXL; ++l) {
@@ -339,7 +345,7 @@ static int gn_bwd(const void* dy, const void* x, const double* stats, const floa
                   int C, int G, int relu, void* stream) {
   if (C != 256 || G != 32) return ut2_fail(-2, "groupnorm: only GroupNorm(32, 256) is supported");
   GnLevels lv;
-  if (fill_gn_levels(lv, num_levels, hws, N)) return ut2_fail(-3, "groupnorm: 1..5 levels");
+  if (fill_gn_levels(lv, num_levels, hws, N, true)) return ut2_fail(-3, "groupnorm: 1..5 levels");
   cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * num_levels * N * GN_G * 2, STREAM);
   if (e != cudaSuccess) return ut2_fail((int)e, "groupnorm: memset failed");
   const int grid = lv.blk_off[num_levels];
