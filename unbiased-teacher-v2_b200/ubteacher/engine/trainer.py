@@ -511,9 +511,11 @@ class UBTeacherTrainer:
             record.update({k + "_pseudo": v for k, v in losses_u.items()})
             with nvtx_range("ut2.student_unlabeled_backward"):
                 self._begin_overlap()
-                self.model.backward_pending(pending_u, [[lam / (lam + 1.0), 0.0, lam / (lam + 1.0), 0.0],
-                                                        [0.0, mu / (mu + 1.0), 0.0, 0.0]])
-                self._end_overlap()
+                try:
+                    self.model.backward_pending(pending_u, [[lam / (lam + 1.0), 0.0, lam / (lam + 1.0), 0.0],
+                                                            [0.0, mu / (mu + 1.0), 0.0, 0.0]])
+                finally:
+                    self._end_overlap()
         record["data_time"] = data_time
         self._write_metrics(record, bookkeeping)
         self._reduce_and_step(device_lr, bookkeeping)
@@ -681,8 +683,10 @@ class UBRCNNTeacherTrainer(UBTeacherTrainer):
             # loss_rpn_loc_pseudo * 0, loss_box_reg_pseudo * UNSUP_REG_LOSS_WEIGHT, the two classification terms * UNSUP_LOSS_WEIGHT
             with nvtx_range("ut2.student_unlabeled_backward"):
                 self._begin_overlap()
-                self.model.backward_pending(pending_u, [lam, 0.0, lam, mu])
-                self._end_overlap()
+                try:
+                    self.model.backward_pending(pending_u, [lam, 0.0, lam, mu])
+                finally:
+                    self._end_overlap()
         record["data_time"] = data_time
         self._write_metrics(record, bookkeeping)
         self._reduce_and_step(device_lr, bookkeeping)
