@@ -77,29 +77,63 @@ pack_tiles_kernel(const PackDesc* __restrict__ descs, int num, long long total_t
     const int ci = e % ct; e /= ct;
     const int ni = e % nt; e /= nt;
     const int s = e % d.S, r = e / d.S;
-    const int c = ci * PACK_TC + tx;
     const bool dg = write_dgrad && d.wt >= 0;
+    if ((d.Cin & 1) == 0 && (d.src & 1) == 0 && (d.wf & 1) == 0) {
+      // even Cin (every convolution but ragged test shapes): two channels per thread — 8-byte loads, bf16x2 stores
+      const int tx2 = threadIdx.x & 15, ty2 = threadIdx.x >> 4;
+      const int c = ci * PACK_TC + 2 * tx2;
 #pragma unroll
-    for (int k = 0; k < PACK_TN / 8; ++k) {
-      const int n = ni * PACK_TN + ty + 8 * k;
-      if (n < d.Cout && c < d.Cin) {
-        const long long idx = (((long long)n * d.R + r) * d.S + s) * d.Cin + c;
-        float wv = __ldg(arena + d.src + idx);
-        if (d.scale >= 0) wv *= __ldg(scales + d.scale + n);
-        const bf16 v = __float2bfloat16_rn(wv);
-        if (d.wf >= 0) packed[d.wf + idx] = v;
-        tile[ty + 8 * k][tx] = __bfloat162float(v);
+      for (int k = 0; k < PACK_TN / 16; ++k) {
+        const int n = ni * PACK_TN + ty2 + 16 * k;
+        if (n < d.Cout && c < d.Cin) {
+          const long long idx = (((long long)n * d.R + r) * d.S + s) * d.Cin + c;
+          float2 wv = __ldg(reinterpret_cast<const float2*>(arena + d.src + idx));
+          if (d.scale >= 0) { const float sc = __ldg(scales + d.scale + n); wv.x *= sc; wv.y *= sc; }
+          const __nv_bfloat162 v = __floats2bfloat162_rn(wv.x, wv.y);
+          if (d.wf >= 0) *reinterpret_cast<__nv_bfloat162*>(packed + d.wf + idx) = v;
+          tile[ty2 + 16 * k][2 * tx2] = __low2float(v);
+          tile[ty2 + 16 * k][2 * tx2 + 1] = __high2float(v);
+        }
+      }
+    } else {
+      const int c = ci * PACK_TC + tx;
+#pragma unroll
+      for (int k = 0; k < PACK_TN / 8; ++k) {
+        const int n = ni * PACK_TN + ty + 8 * k;
+        if (n < d.Cout && c < d.Cin) {
+          const long long idx = (((long long)n * d.R + r) * d.S + s) * d.Cin + c;
+          float wv = __ldg(arena + d.src + idx);
+          if (d.scale >= 0) wv *= __ldg(scales + d.scale + n);
+          const bf16 v = __float2bfloat16_rn(wv);
+          if (d.wf >= 0) packed[d.wf + idx] = v;
+          tile[ty + 8 * k][tx] = __bfloat162float(v);
+        }
       }
     }
     if (dg) {
       __syncthreads();
-      const int n = ni * PACK_TN + nl;
+      if (((d.CoutT | d.n_off | d.wt) & 1) == 0) {
+        // two output channels per thread along the transposed operand's rows: bf16x2 stores
+        const int np = threadIdx.x & 31, cb8 = threadIdx.x >> 5;          // 32 channel pairs x 8 input channels per pass
+        const int n = ni * PACK_TN + 2 * np;
 #pragma unroll
-      for (int k = 0; k < PACK_TC / 4; ++k) {
-        const int cl = cb + 4 * k, cc = ci * PACK_TC + cl;
-        if (n < d.Cout && cc < d.Cin)
-          packed[d.wt + (((long long)cc * d.R + (d.R - 1 - r)) * d.S + (d.S - 1 - s)) * d.CoutT + n + d.n_off] =
-              __float2bfloat16_rn(tile[nl][cl]);
+        for (int k = 0; k < PACK_TC / 8; ++k) {
+          const int cl = cb8 + 8 * k, cc = ci * PACK_TC + cl;
+          if (n < d.Cout && cc < d.Cin) {
+            bf16* dst = packed + d.wt + (((long long)cc * d.R + (d.R - 1 - r)) * d.S + (d.S - 1 - s)) * d.CoutT + n + d.n_off;
+            if (n + 1 < d.Cout) *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(tile[2 * np][cl], tile[2 * np + 1][cl]);
+            else *dst = __float2bfloat16_rn(tile[2 * np][cl]);
+          }
+        }
+      } else {
+        const int n = ni * PACK_TN + nl;
+#pragma unroll
+        for (int k = 0; k < PACK_TC / 4; ++k) {
+          const int cl = cb + 4 * k, cc = ci * PACK_TC + cl;
+          if (n < d.Cout && cc < d.Cin)
+            packed[d.wt + (((long long)cc * d.R + (d.R - 1 - r)) * d.S + (d.S - 1 - s)) * d.CoutT + n + d.n_off] =
+                __float2bfloat16_rn(tile[nl][cl]);
+        }
       }
       __syncthreads();
     }
