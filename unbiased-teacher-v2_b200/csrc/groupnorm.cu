@@ -33,6 +33,9 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 constexpr int GN_G = 32;          // groups (== vectors per pixel)
 constexpr int GN_ROWS = 8;        // pixel rows per block iteration (256 threads)
+#ifndef GN_BWD_OCC
+#define GN_BWD_OCC 3
+#endif
 constexpr int GN_UNROLL = 4;      // independent 16-byte loads in flight per thread
 
 // One launch covers up to 5 pyramid levels of a level-major buffer (level l = [N, HW_l, 256] starting at pixel row
@@ -149,7 +152,7 @@ gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ stats, co
 }
 
 // pass 1 of backward: per-(n, group) sums s1 = sum g*gamma, s2 = sum g*gamma*xhat; per-channel dgamma/dbeta
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, GN_BWD_OCC)
 gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const double* __restrict__ stats,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                      double* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, GnLevels lv,
@@ -217,7 +220,7 @@ gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
 }
 
 // pass 2: dx = rstd * (g*gamma - s1/m - xhat*s2/m)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, GN_BWD_OCC)
 gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const double* __restrict__ stats,
                     const double* __restrict__ ws, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float eps, bf16* __restrict__ dx, float* __restrict__ dbias, GnLevels lv, int relu) {
