@@ -11,6 +11,7 @@ What changed underneath (B200-first, same arithmetic):
   * EMA is one kernel over the whole state (trainer.py:468-486 is a ~320-tensor Python loop);
   * metrics are stacked on the device and read back once every `metrics_period` iterations.
 """
+import contextlib
 import logging
 import os
 import time
@@ -482,18 +483,24 @@ class UBTeacherTrainer:
             else:
                 ema_keep_rate = ss.EMA_KEEP_RATE
             record["ema_rate_1000x"] = ema_keep_rate * 1000
-            # teacher on the weak views (trainer.py:231-237) + second NMS criterion (:240-242)
-            with nvtx_range("ut2.teacher_forward"):
-                pred_teacher, raw_pred_teacher = self.model_teacher(
-                    unlabel_data_k, output_raw=True, nms_method=cfg.MODEL.FCOS.NMS_CRITERIA_TRAIN, branch="teacher_weak")
-            with nvtx_range("ut2.pseudo_labels"):
-                raw_pred_teacher["scales"] = self.model_teacher.engine.scales
-                pred_teacher_loc = self.pseudo_generator.nms_from_dense(raw_pred_teacher, cfg.MODEL.FCOS.NMS_CRITERIA_REG_TRAIN)
-                thr = self._threshold(ss.PSEUDO_BBOX_SAMPLE, ss.BBOX_THRESHOLD, ss.BBOX_CTR_THRESHOLD)
-                thr_reg = self._threshold(ss.PSEUDO_BBOX_SAMPLE_REG, ss.BBOX_THRESHOLD_REG, ss.BBOX_CTR_THRESHOLD_REG)
-                pseudo_cls, _ = self.pseudo_generator.process_pseudo_label(pred_teacher, thr, "roih", ss.PSEUDO_BBOX_SAMPLE)
-                pseudo_reg, _ = self.pseudo_generator.process_pseudo_label(pred_teacher_loc, thr_reg, "roih",
-                                                                           ss.PSEUDO_BBOX_SAMPLE_REG)
+            # teacher on the weak views (trainer.py:231-237) + second NMS criterion (:240-242); on a second stream next to the
+            # student's labeled pass when the per-GPU batch is small (_teacher_stream)
+            side = self._teacher_stream(len(unlabel_data_k))
+            main = torch.cuda.current_stream()
+            if side is not None:
+                side.wait_stream(main)
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                with nvtx_range("ut2.teacher_forward"):
+                    pred_teacher, raw_pred_teacher = self.model_teacher(
+                        unlabel_data_k, output_raw=True, nms_method=cfg.MODEL.FCOS.NMS_CRITERIA_TRAIN, branch="teacher_weak")
+                with nvtx_range("ut2.pseudo_labels"):
+                    raw_pred_teacher["scales"] = self.model_teacher.engine.scales
+                    pred_teacher_loc = self.pseudo_generator.nms_from_dense(raw_pred_teacher, cfg.MODEL.FCOS.NMS_CRITERIA_REG_TRAIN)
+                    thr = self._threshold(ss.PSEUDO_BBOX_SAMPLE, ss.BBOX_THRESHOLD, ss.BBOX_CTR_THRESHOLD)
+                    thr_reg = self._threshold(ss.PSEUDO_BBOX_SAMPLE_REG, ss.BBOX_THRESHOLD_REG, ss.BBOX_CTR_THRESHOLD_REG)
+                    pseudo_cls, _ = self.pseudo_generator.process_pseudo_label(pred_teacher, thr, "roih", ss.PSEUDO_BBOX_SAMPLE)
+                    pseudo_reg, _ = self.pseudo_generator.process_pseudo_label(pred_teacher_loc, thr_reg, "roih",
+                                                                               ss.PSEUDO_BBOX_SAMPLE_REG)
             self.last_pseudo = (pseudo_cls, pseudo_reg)          # device-resident; read by benchmarks / analysis only
             unlabel_data_q = self.remove_label(unlabel_data_q)
             unlabel_data_q = self.add_label(unlabel_data_q, pseudo_cls, "class")
@@ -505,6 +512,8 @@ class UBTeacherTrainer:
             record.update(losses)
             with nvtx_range("ut2.student_labeled_backward"):
                 self.model.backward_pending(pending, [[1.0 / (lam + 1.0), 1.0 / (mu + 1.0), 1.0 / (lam + 1.0), 0.0]])
+            if side is not None:
+                main.wait_stream(side)         # the unlabeled pass needs the pseudo labels
             # student: unlabeled strong with the two pseudo-label sets (trainer.py:331-349)
             with nvtx_range("ut2.student_unlabeled_forward"):
                 losses_u, pending_u = self.model.forward_train(unlabel_data_q, "unlabeled")
@@ -519,6 +528,20 @@ class UBTeacherTrainer:
         record["data_time"] = data_time
         self._write_metrics(record, bookkeeping)
         self._reduce_and_step(device_lr, bookkeeping)
+
+    # ---------------------------------------------------------------- teacher forward on a second stream
+    def _teacher_stream(self, n_unlabel):
+        """The teacher forward + pseudo-labelling do not depend on the student's labeled pass (only the unlabeled pass needs the
+        pseudo labels). With small per-GPU batches (the README recipes run 2 + 2 images per GPU) most launches cannot fill 148
+        SMs: the two branches run on two streams — forked and joined inside the captured graph — and share the device.
+        UT2_CONCURRENT_TEACHER = auto (default: per-GPU unlabeled batch <= 8; neutral at 8 + 8, -2 ... -5 % at 2 + 2) | 1 | 0. Returns (side stream | None)."""
+        mode = os.environ.get("UT2_CONCURRENT_TEACHER", "auto")
+        on = mode == "1" or (mode == "auto" and n_unlabel <= 8)
+        if not on:
+            return None
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=self.model.device)
+        return self._side_stream
 
     # ---------------------------------------------------------------- overlapped gradient all-reduce
     def _begin_overlap(self):
@@ -664,10 +687,15 @@ class UBRCNNTeacherTrainer(UBTeacherTrainer):
                 self._update_teacher_model(keep_rate=ss.EMA_KEEP_RATE)
             record["EMA_rate"] = ss.EMA_KEEP_RATE
             # teacher on the weak views; never switched to eval (trainer.py:830-837)
-            with nvtx_range("ut2.teacher_forward"):
-                _, proposals_rpn_unsup_k, proposals_roih_unsup_k, _ = self.model_teacher(unlabel_data_k, branch="unsup_data_weak")
-            with nvtx_range("ut2.pseudo_labels"):
-                pseudo, _ = self.process_pseudo_label(proposals_roih_unsup_k, ss.BBOX_THRESHOLD, "roih", "thresholding")
+            side = self._teacher_stream(len(unlabel_data_k))
+            main = torch.cuda.current_stream()
+            if side is not None:
+                side.wait_stream(main)
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                with nvtx_range("ut2.teacher_forward"):
+                    _, proposals_rpn_unsup_k, proposals_roih_unsup_k, _ = self.model_teacher(unlabel_data_k, branch="unsup_data_weak")
+                with nvtx_range("ut2.pseudo_labels"):
+                    pseudo, _ = self.process_pseudo_label(proposals_roih_unsup_k, ss.BBOX_THRESHOLD, "roih", "thresholding")
             self.last_pseudo = (pseudo,)
             unlabel_data_q = self.add_label(self.remove_label(unlabel_data_q), pseudo)
             unlabel_data_k = self.add_label(self.remove_label(unlabel_data_k), pseudo)
@@ -677,6 +705,8 @@ class UBRCNNTeacherTrainer(UBTeacherTrainer):
             record.update(losses)
             with nvtx_range("ut2.student_labeled_backward"):
                 self.model.backward_pending(pending, [1.0, 1.0, 1.0, 1.0])
+            if side is not None:
+                main.wait_stream(side)         # the unlabeled pass needs the pseudo labels
             with nvtx_range("ut2.student_unlabeled_forward"):
                 losses_u, pending_u = self.model.forward_train(unlabel_data_q, "unsup_data_train")
             record.update({k + "_pseudo": v for k, v in losses_u.items()})
