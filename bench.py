@@ -391,7 +391,14 @@ def main():
         saturate(tr, args.arch)
     # roofline pass: a few eager steps with every tensor-core launch bracketed by CUDA events
     timed(tr, max(args.warmup, 3), False)
+    # per-launch CUDA events need the launches to own the device: no second stream during the two profiled steps
+    prev_ct = os.environ.get("UT2_CONCURRENT_TEACHER")
+    os.environ["UT2_CONCURRENT_TEACHER"] = "0"
     _, _, _, prof, _ = timed(tr, 2, False, profile=True)
+    if prev_ct is None:
+        del os.environ["UT2_CONCURRENT_TEACHER"]
+    else:
+        os.environ["UT2_CONCURRENT_TEACHER"] = prev_ct
     prof_steps = 2
     if not args.no_graph:
         tr.enable_cuda_graph(True)
@@ -465,6 +472,9 @@ def main():
                  other: extra_arm(other, args.label, args.unlabel, args.regime),
                  "per_gpu_2": extra_arm(args.arch, 2, 2, args.regime),
                  other + "_per_gpu_2": extra_arm(other, 2, 2, args.regime)}
+        # BASELINE config #5: the Faster R-CNN per-GPU batch sweep 2 / 4 / 8 / 16 (2 and 8 are above)
+        for b in (4, 16):
+            extra[f"rcnn_per_gpu_{b}"] = extra_arm("rcnn", b, b, args.regime)
     # ---- arm 2: end to end through the public API: pinned host inputs, H2D inside the step, loss read back --
     e2e = None
     if not args.no_e2e:

@@ -1,5 +1,6 @@
 """In-step CUDA-event breakdown of one UT2 training step by C-ABI entry point and conv shape (run under gpurun)."""
 import os, sys, collections, torch
+os.environ.setdefault("UT2_CONCURRENT_TEACHER", "0")   # per-launch events need the launches to own the device
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "unbiased-teacher-v2_b200")]
 import bench
