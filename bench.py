@@ -411,10 +411,17 @@ def main():
     peak_tf, peak_bw, peak_src = peaks()
     roof = None
     if prof:
-        fl = sum(f for _, _, f in prof["conv_fwd"])
-        ms = sum(a.elapsed_time(b) for a, b, _ in prof["conv_fwd"])
-        flw = sum(f for _, _, f in prof["conv_wgrad"])
-        msw = sum(a.elapsed_time(b) for a, b, _ in prof["conv_wgrad"])
+        fl = sum(r[2] for r in prof["conv_fwd"])
+        ms = sum(r[0].elapsed_time(r[1]) for r in prof["conv_fwd"])
+        flw = sum(r[2] for r in prof["conv_wgrad"])
+        msw = sum(r[0].elapsed_time(r[1]) for r in prof["conv_wgrad"])
+        # every conv_fwd launch against ITS OWN bound: max(algorithmic FLOPs / tensor peak, algorithmic bytes / HBM peak)
+        ideal = [max(r[2] / (peak_tf * 1e12), r[3] / (peak_bw * 1e9)) * 1e3 for r in prof["conv_fwd"]]
+        tb = [r[2] / (peak_tf * 1e12) >= r[3] / (peak_bw * 1e9) for r in prof["conv_fwd"]]
+        ms_each = [r[0].elapsed_time(r[1]) for r in prof["conv_fwd"]]
+        ms_tb = sum(m for m, t in zip(ms_each, tb) if t)
+        fl_tb = sum(r[2] for r, t in zip(prof["conv_fwd"], tb) if t)
+        by_mb = sum(r[3] for r, t in zip(prof["conv_fwd"], tb) if not t)
         ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         traffic, traffic_note = None, None
         try:        # DRAM bytes of the dominant launch shape from the committed ncu --set full capture
@@ -430,6 +437,16 @@ def main():
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peak_src,
                 "launches_per_step": len(prof["conv_fwd"]) / prof_steps, "kernel_ms_per_step": ms / prof_steps,
+                "per_launch_bound": {
+                    "note": "the same kernel runs tensor-bound (3x3, head) and HBM-bound (narrow-K 1x1 + fused residual / mask epilogues) "
+                            "launches; each launch is held against max(FLOPs / tensor peak, algorithmic bytes / HBM peak)",
+                    "frac": sum(ideal) / ms if ms > 0 else 0.0, "ideal_ms_per_step": sum(ideal) / prof_steps,
+                    "tensor_bound": {"launches_per_step": sum(tb) / prof_steps, "ms_per_step": ms_tb / prof_steps,
+                                     "achieved_tflops": fl_tb / (ms_tb * 1e-3) / 1e12 if ms_tb > 0 else 0.0,
+                                     "frac": fl_tb / (ms_tb * 1e-3) / 1e12 / peak_tf if ms_tb > 0 else 0.0},
+                    "hbm_bound": {"launches_per_step": (len(tb) - sum(tb)) / prof_steps, "ms_per_step": (ms - ms_tb) / prof_steps,
+                                  "achieved_gbs": by_mb / ((ms - ms_tb) * 1e-3) / 1e9 if ms > ms_tb else 0.0,
+                                  "frac": by_mb / ((ms - ms_tb) * 1e-3) / 1e9 / peak_bw if ms > ms_tb else 0.0}},
                 "flops_per_launch_avg": fl / max(len(prof["conv_fwd"]), 1),
                 "wgrad": {"achieved": flw / (msw * 1e-3) / 1e12 if msw > 0 else 0.0, "kernel_ms_per_step": msw / prof_steps,
                           "launches_per_step": len(prof["conv_wgrad"]) / prof_steps},

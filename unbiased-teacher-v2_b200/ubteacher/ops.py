@@ -14,7 +14,7 @@ BF16 = torch.bfloat16
 PROFILE = None
 
 
-def _timed(kind, flops, name, *args):
+def _timed(kind, flops, name, *args, nbytes=0.0):
     if PROFILE is None:
         tag = None
         if _C.EVENT_PROFILE is not None:   # per-shape breakdown: N,H,W,Cin -> Cout RxS /stride
@@ -26,7 +26,7 @@ def _timed(kind, flops, name, *args):
     e0.record()
     _C.counted_call(name, *args)
     e1.record()
-    PROFILE[kind].append((e0, e1, flops))
+    PROFILE[kind].append((e0, e1, flops, nbytes))
 
 
 def conv_out_hw(H, W, R, S, stride, pad):
@@ -41,8 +41,12 @@ def conv2d(x, w, cout, R, S, stride, pad, scale=None, shift=None, residual=None,
     if out is None:
         out = torch.empty((N, P, Q, cout), dtype=BF16, device=x.device)
     flops = alg_flops if alg_flops is not None else 2.0 * N * P * Q * cout * Cin * R * S
+    # algorithmic bytes (bf16): the input pixels the filter touches, the weights, the output, residual and mask tiles
+    zero_frac = (alg_flops / (2.0 * N * P * Q * cout * Cin * R * S)) if alg_flops is not None else 1.0
+    nbytes = 2.0 * ((N * P * Q if R * S == 1 else N * H * W * zero_frac) * Cin + cout * Cin * R * S +
+                    N * P * Q * cout * (1 + (0.25 if res_up2 else 1) * (residual is not None) + (relu_mask is not None)))
     _timed("conv_fwd", flops, "ut2_conv2d_nhwc_bf16_fwd", x, N, H, W, Cin, w, cout, R, S, stride, pad, scale, shift,
-           residual, int(res_up2), relu_mask, int(relu), out)
+           residual, int(res_up2), relu_mask, int(relu), out, nbytes=nbytes)
     return out
 
 
@@ -50,8 +54,10 @@ def conv2d_wgrad(x, dy, cout, R, S, stride, pad, dw, scale=None, cout_store=0):
     """Accumulates dW (fp32, [cout, R, S, Cin]) += dY^T * im2col(X)."""
     N, H, W, Cin = x.shape
     flops = 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * (cout_store or cout) * Cin * R * S
+    px = dy.shape[0] * dy.shape[1] * dy.shape[2]
+    nbytes = 2.0 * ((px if R * S == 1 else N * H * W) * Cin + px * cout) + 4.0 * cout * Cin * R * S
     _timed("conv_wgrad", flops, "ut2_conv2d_nhwc_bf16_wgrad", x, N, H, W, Cin, dy, cout, R, S, stride, pad, scale, dw,
-           cout_store)
+           cout_store, nbytes=nbytes)
 
 
 def conv2d_levels(x, geom, N, w, cout, R, S, pad, scale=None, shift=None, residual=None, relu=False, out=None, relu_mask=None):
@@ -71,7 +77,7 @@ def conv2d_levels(x, geom, N, w, cout, R, S, pad, scale=None, shift=None, residu
         e0.record()
         _C.counted_call(*args)
         e1.record()
-        PROFILE["conv_fwd"].append((e0, e1, flops))
+        PROFILE["conv_fwd"].append((e0, e1, flops, 2.0 * (rows * (Cin + cout * (1 + (residual is not None) + (relu_mask is not None))) + cout * Cin * R * S)))
     return out
 
 
@@ -87,7 +93,7 @@ def conv2d_wgrad_levels(x, dy, geom, N, cout, R, S, pad, dw, scale=None, cout_st
         e0.record()
         _C.counted_call(*args)
         e1.record()
-        PROFILE["conv_wgrad"].append((e0, e1, flops))
+        PROFILE["conv_wgrad"].append((e0, e1, flops, 2.0 * geom.L * N * (Cin + cout) + 4.0 * cout * Cin * R * S))
 
 
 def groupnorm_relu_levels_fwd(x, geom, N, gamma, beta, eps=1e-5, relu=True):
