@@ -15,6 +15,7 @@ Tensor-core work: every conv, and the three FC layers as 1x1 "convs" over a [1, 
 16-row operator and the three box predictors as one 96-row operator (zero-padded, see EngineBase.add_fused).
 """
 import math
+import os
 
 import torch
 
@@ -193,12 +194,30 @@ class RcnnEngine(EngineBase):
     def forward_losses(self, fwd, gt, pseudo):
         """supervised / unsup_data_train branches (rcnn.py:26-40, :57-72). gt: BoxSet (boxes, classes, counts and, for
         pseudo labels, scores + reg_pred_std = the teacher's pred_boxes_std). Returns (losses float[4] parts, ctx)."""
-        rpn_losses, ctx = self.rpn_losses(fwd, gt, pseudo)
+        # anchor labelling + RPN losses (latency-bound: one CTA per image for the selections) do not feed the proposal -> ROI
+        # sampling -> box head chain: they run on a second stream (forked / joined here, capturable) next to it
+        side = self._side_stream()
+        main = torch.cuda.current_stream()
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                rpn_losses, ctx = self.rpn_losses(fwd, gt, pseudo)
+        else:
+            rpn_losses, ctx = self.rpn_losses(fwd, gt, pseudo)
         props = self.proposals(fwd)
         roi_losses, rctx = self.roi_losses(fwd, props, gt, pseudo)
+        if side is not None:
+            main.wait_stream(side)
         ctx.update(rctx)
         ctx["proposals"] = props
         return rpn_losses, roi_losses, ctx
+
+    def _side_stream(self):
+        if os.environ.get("UT2_RPN_SIDE_STREAM", "1") == "0":
+            return None
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     def rpn_losses(self, fwd, gt, pseudo):
         """PseudoLabRPN: anchor labelling + sampling, objectness BCE (x teacher score for pseudo labels) and L1 box loss."""
