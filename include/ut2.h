@@ -106,6 +106,18 @@ int ut2_groupnorm_relu_levels_bwd(const void* dy, const void* x, const double* s
                                   float eps, void* dx, float* dgamma, float* dbeta, float* dbias_prev, double* ws,
                                   int num_levels, const int* hws, int N, int C, int G, int relu, void* stream);
 
+/* Stand-alone loss operators behind ubteacher.layers.{IOULoss, NLLoss, KLLoss} (ubteacher/layers/iou_loss.py:23-76,
+ * kl_loss.py:17-105); rows [P, 4] f32, value in loss[0], input gradients (d loss / d input) written when the pointers are given.
+ * The training step computes the same terms inside ut2_fcos_loss_fwd / _bwd. */
+int ut2_iou_loss(const float* pred, const float* target, const float* weight /* [P] or NULL */, int P, int type /* 0 iou, 1 linear_iou, 2 giou */,
+                 double* acc /* [1] scratch */, float* loss, float* dpred /* [P,4] or NULL */, void* stream);
+int ut2_nl_loss(const float* mean, const float* std, const float* target, const float* iou_weight, int P, double* acc, float* loss,
+                float* dmean, float* dstd, void* stream);
+int ut2_kl_loss(const float* input, const float* std, const float* target, const float* weight, int P, float beta,
+                int method /* 0 weight_ctr_sum, 1 weight_ctr_mean, 2 sum, 3 mean */, float loss_denorm, double* acc, float* loss,
+                float* dinput, float* dstd, void* stream);
+int ut2_scale_f32(const float* x, const float* s /* device scalar */, float* y, long long n, void* stream);
+
 /* ---------------------------------------------------------------- FCOS targets and losses
  * ut2_fcos_assign_targets: FCOSOutputs._get_ground_truth + compute_targets_for_locations
  * (fcos/fcos_outputs.py:649-698, :772-906; CENTER_SAMPLE False). hw/strides/ranges are HOST arrays
