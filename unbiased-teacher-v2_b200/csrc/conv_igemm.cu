@@ -151,6 +151,8 @@ conv_fwd_kernel(const __grid_constant__ TmapSet tmaps_x, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_wait();        // everything above overlapped the previous kernel's tail (programmatic dependent launch)
+  griddep_launch();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -501,6 +503,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_wait();
+  griddep_launch();
   const uint32_t tmem_base = *tmem_slot;
   const int nblk = a.block_n / 64;
 
@@ -761,8 +765,10 @@ static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, 
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_fwd_kernel<<<grid, NUM_THREADS, smem_bytes(a.stages, block_n, aux_tiles_total, smem_pad), static_cast<cudaStream_t>(stream)>>>(
-      tx, tw, to, ta, ta2, a);
+  ut2_launch_pdl(conv_fwd_kernel, dim3(grid), dim3(NUM_THREADS), smem_bytes(a.stages, block_n, aux_tiles_total, smem_pad),
+                 static_cast<cudaStream_t>(stream),
+                 ut2_est_us(2.0 * a.M * Cout * R * S * Cin, 2.0 * a.M * (Cin + Cout * (1.0 + (a.aux_kind != 0) + (a.aux_kind == 3)))),
+                 tx, tw, to, ta, ta2, a);
   return ut2_check_launch("conv_fwd");
 }
 
@@ -861,12 +867,14 @@ static int conv_wgrad_launch(const void* x, int num_levels, const int* hw, int N
     attr_set = true;
   }
   dim3 grid(out_tiles, splits);
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const double est = ut2_est_us(2.0 * a.Mpix * a.Cout * a.R * a.S * a.Cin, 2.0 * a.Mpix * (a.Cin + a.Cout));
   if (WG_PIX == 128)
-    conv_wgrad_kernel<128><<<grid, WG_THREADS, wg_smem, static_cast<cudaStream_t>(stream)>>>(tg, tx, a);
+    ut2_launch_pdl(conv_wgrad_kernel<128>, grid, dim3(WG_THREADS), wg_smem, st, est, tg, tx, a);
   else if (WG_PIX == 96)
-    conv_wgrad_kernel<96><<<grid, WG_THREADS, wg_smem, static_cast<cudaStream_t>(stream)>>>(tg, tx, a);
+    ut2_launch_pdl(conv_wgrad_kernel<96>, grid, dim3(WG_THREADS), wg_smem, st, est, tg, tx, a);
   else
-    conv_wgrad_kernel<64><<<grid, WG_THREADS, wg_smem, static_cast<cudaStream_t>(stream)>>>(tg, tx, a);
+    ut2_launch_pdl(conv_wgrad_kernel<64>, grid, dim3(WG_THREADS), wg_smem, st, est, tg, tx, a);
   return ut2_check_launch("conv_wgrad");
 }
 

@@ -6,6 +6,7 @@
 // Algorithmic bytes per element (bf16): fwd = read x twice + write y = 6 B; bwd = read x, dy twice +
 // write dx = 10 B.
 #include "ut2_internal.h"
+#include "sm100_ptx.cuh"
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -72,6 +73,8 @@ __device__ __forceinline__ GnBlock gn_locate(const GnLevels& lv) {
 // stats[n][g] = {sum, sumsq} over HW x 8 channels
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats, GnLevels lv) {
+  ut2::griddep_wait();
+  ut2::griddep_launch();
   const GnBlock B = gn_locate(lv);
   const int n = B.n_stat, g = threadIdx.x & 31, row = threadIdx.x >> 5;
   const int p0 = B.p0, p1 = B.p1;
@@ -117,6 +120,8 @@ __device__ __forceinline__ void mean_rstd(const double* stats, int n, int g, int
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, bf16* __restrict__ y, GnLevels lv, int relu) {
+  ut2::griddep_wait();
+  ut2::griddep_launch();
   const GnBlock B = gn_locate(lv);
   const int n = B.n_stat, HW = B.HW, g = threadIdx.x & 31, row = threadIdx.x >> 5;
   float mean, rstd;
@@ -157,6 +162,8 @@ gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                      double* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, GnLevels lv,
                      int relu) {
+  ut2::griddep_wait();
+  ut2::griddep_launch();
   const GnBlock B = gn_locate(lv);
   const int n = B.n_stat, HW = B.HW, g = threadIdx.x & 31, row = threadIdx.x >> 5;
   float mean, rstd;
@@ -224,6 +231,8 @@ __global__ void __launch_bounds__(256, GN_BWD_OCC)
 gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const double* __restrict__ stats,
                     const double* __restrict__ ws, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float eps, bf16* __restrict__ dx, float* __restrict__ dbias, GnLevels lv, int relu) {
+  ut2::griddep_wait();
+  ut2::griddep_launch();
   const GnBlock B = gn_locate(lv);
   const int n = B.n_stat, HW = B.HW, g = threadIdx.x & 31, row = threadIdx.x >> 5;
   float mean, rstd;
@@ -330,6 +339,12 @@ inline int fill_gn_levels(GnLevels& lv, int num_levels, const int* hws, int N, b
 
 #define STREAM static_cast<cudaStream_t>(stream)
 
+static double gn_est_us(int num_levels, const int* hws, int N, double bytes_per_elem) {
+  double px = 0;
+  for (int l = 0; l < num_levels; ++l) px += hws[l];
+  return ut2_est_us(0.0, px * N * 256.0 * bytes_per_elem);
+}
+
 static int gn_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, double* stats, int num_levels,
                   const int* hws, int N, int C, int G, int relu, void* stream) {
   if (C != 256 || G != 32) return ut2_fail(-2, "groupnorm: only GroupNorm(32, 256) is supported");
@@ -338,8 +353,9 @@ static int gn_fwd(const void* x, const float* gamma, const float* beta, float ep
   cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * num_levels * N * GN_G * 2, STREAM);
   if (e != cudaSuccess) return ut2_fail((int)e, "groupnorm: memset failed");
   const int grid = lv.blk_off[num_levels];
-  gn_stats_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(x), stats, lv);
-  gn_apply_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(x), stats, gamma, beta, eps, static_cast<bf16*>(y), lv, relu);
+  gn_stats_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(x), stats, lv);      // follows a memset node: plain launch
+  ut2_launch_pdl(gn_apply_kernel, dim3(grid), dim3(256), 0, STREAM, gn_est_us(num_levels, hws, N, 4.0), static_cast<const bf16*>(x), (const double*)stats, gamma, beta, eps,
+                 static_cast<bf16*>(y), lv, relu);
   return ut2_check_launch("groupnorm_fwd");
 }
 
@@ -354,8 +370,8 @@ static int gn_bwd(const void* dy, const void* x, const double* stats, const floa
   const int grid = lv.blk_off[num_levels];
   gn_bwd_reduce_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats, gamma, beta,
                                                  eps, ws, dgamma, dbeta, lv, relu);
-  gn_bwd_apply_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats, ws, gamma, beta,
-                                                eps, static_cast<bf16*>(dx), dbias_prev, lv, relu);
+  ut2_launch_pdl(gn_bwd_apply_kernel, dim3(grid), dim3(256), 0, STREAM, gn_est_us(num_levels, hws, N, 6.0), static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats,
+                 (const double*)ws, gamma, beta, eps, static_cast<bf16*>(dx), dbias_prev, lv, relu);
   return ut2_check_launch("groupnorm_bwd");
 }
 

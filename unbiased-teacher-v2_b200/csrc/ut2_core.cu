@@ -1,4 +1,5 @@
 // Library-wide C-ABI plumbing: version, error string, launch checking.
+#include <cstdlib>
 #include "ut2_internal.h"
 #include <stdio.h>
 #include <string.h>
@@ -34,5 +35,14 @@ static int g_sm_limit = 0;
 extern "C" int ut2_set_sm_limit(int n) {
   g_sm_limit = n > 0 ? n : 0;
   return 0;
+}
+int ut2_pdl_enabled(double est_us) {
+  static const double limit_us = [] {
+    const char* e = getenv("UT2_PDL");
+    if (e && e[0] == '0') return -1.0;
+    const char* u = getenv("UT2_PDL_US");
+    return u ? atof(u) : 80.0;
+  }();
+  return est_us < limit_us ? 1 : 0;
 }
 int ut2_sm_budget(int device_sms) { return (g_sm_limit > 0 && g_sm_limit < device_sms) ? g_sm_limit : device_sms; }
