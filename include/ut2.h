@@ -120,13 +120,16 @@ int ut2_scale_f32(const float* x, const float* s /* device scalar */, float* y, 
 
 /* ---------------------------------------------------------------- FCOS targets and losses
  * ut2_fcos_assign_targets: FCOSOutputs._get_ground_truth + compute_targets_for_locations
- * (fcos/fcos_outputs.py:649-698, :772-906; CENTER_SAMPLE False). hw/strides/ranges are HOST arrays
+ * (fcos/fcos_outputs.py:649-698, :772-906). hw/strides/ranges are HOST arrays
  * ([H,W] x levels, stride x levels, [lo,hi] x levels). boxes [N,G,4], classes [N,G] (int64), counts [N] (int32),
- * bvar [N,G,4] or NULL (teacher reg_pred_std). norm[2] receives {num_pos, sum of centerness targets}. */
+ * bvar [N,G,4] or NULL (teacher reg_pred_std). center_radius > 0: MODEL.FCOS.CENTER_SAMPLE with POS_RADIUS = center_radius
+ * (get_sample_region, :700-770); 0: a location is positive anywhere inside the box (the shipped recipes). ignore_near != 0:
+ * keep[] drops the locations inside a box but outside every sample region (:841-848). norm[2] receives {num_pos, sum of
+ * centerness targets}. */
 int ut2_fcos_assign_targets(int num_levels, const int* hw, const int* strides, const float* ranges, int N, int G,
                             const float* boxes, const long long* classes, const int* counts, const float* bvar,
-                            int num_classes, long long* labels, long long* tinds, float* reg_t, float* bv_out,
-                            unsigned char* keep, float* norm, void* stream);
+                            int num_classes, float center_radius, int ignore_near, long long* labels, long long* tinds,
+                            float* reg_t, float* bv_out, unsigned char* keep, float* norm, void* stream);
 /* mode 0: FCOSOutputs.fcos_losses (fcos_outputs.py:307-444); mode 1 / 2: fcos_pseudo_losses on the classification /
  * regression pseudo-label set (:492-631). Includes Integral (:44-77), centerness / IoU targets (:80-129), IOULoss giou
  * (layers/iou_loss.py:23-76), NLLoss (layers/kl_loss.py:75-105), [fvcore] sigmoid_focal_loss_jit.

@@ -112,6 +112,17 @@ def main():
                 "targets": {k: [t.clone() for t in v] for k, v in tp.items()}},
                os.path.join(OUT, "fcos_targets_pseudo.pt"))
 
+    # ---------------------------------------------------------------- targets with centre sampling (config.py:151-152 defaults;
+    # the shipped recipes switch it off) and the ignore_near keep mask, on the two box sets above (no new random draws)
+    outputs.center_sample, outputs.radius = True, 1.5
+    rec = {"radius": 1.5}
+    for name, insts in (("labeled", gt), ("pseudo", pseudo)):
+        for ign in (False, True):
+            t = outputs._get_ground_truth(locations, insts, ign)
+            rec[f"{name}_ignore_near{int(ign)}"] = {k: [x.clone() for x in v] for k, v in t.items()}
+    torch.save(rec, os.path.join(OUT, "fcos_targets_center_sample.pt"))
+    outputs.center_sample, outputs.radius = cfg.MODEL.FCOS.CENTER_SAMPLE, cfg.MODEL.FCOS.POS_RADIUS
+
     # ---------------------------------------------------------------- supervised losses (+ grads)
     def leafs(ts):
         return [t.clone().requires_grad_(True) for t in ts]

@@ -43,12 +43,32 @@ def sizes_of_interest(soi: Sequence[int]) -> List[List[float]]:
     return out
 
 
+def center_sample_region(loc: torch.Tensor, b: torch.Tensor, strides: Sequence[int], num_loc: Sequence[int],
+                         radius: float) -> torch.Tensor:
+    """fcos_outputs.py:700-770 (get_sample_region, box centres; no bitmasks): [L, n] mask of the locations strictly inside a
+    box's centre region — centre -/+ stride * radius of the location's level, clipped to the box. The reference's "no gt"
+    test (:736) also fires when the FIRST box has centre x == 0 and then nothing is sampled."""
+    cx = (b[:, 0] + b[:, 2]) * 0.5
+    cy = (b[:, 1] + b[:, 3]) * 0.5
+    if b.shape[0] == 0 or float(cx[0]) == 0.0:
+        return torch.zeros(loc.shape[0], b.shape[0], dtype=torch.bool)
+    sr = torch.cat([torch.full((n, 1), float(strides[i] * radius)) for i, n in enumerate(num_loc)])
+    x, y = loc[:, 0:1], loc[:, 1:2]
+    rx1 = torch.maximum(cx[None] - sr, b[None, :, 0])
+    ry1 = torch.maximum(cy[None] - sr, b[None, :, 1])
+    rx2 = torch.minimum(cx[None] + sr, b[None, :, 2])
+    ry2 = torch.minimum(cy[None] + sr, b[None, :, 3])
+    return torch.stack([x - rx1, y - ry1, rx2 - x, ry2 - y], 2).min(2)[0] > 0
+
+
 def fcos_assign_targets(locations: List[torch.Tensor], boxes: List[torch.Tensor], classes: List[torch.Tensor],
                         strides: Sequence[int], soi: Sequence[int] = (64, 128, 256, 512), num_classes: int = 80,
                         scores: Optional[List[torch.Tensor]] = None, reg_pred_std: Optional[List[torch.Tensor]] = None,
-                        soft_cls_label: bool = False) -> Dict[str, List[torch.Tensor]]:
-    """fcos_outputs.py:649-698 (_get_ground_truth) + :772-906 (compute_targets_for_locations),
-    CENTER_SAMPLE=False, ignore_near=False. Returns level-first lists (image-major inside a level).
+                        soft_cls_label: bool = False, center_sample: bool = False, radius: float = 1.5,
+                        ignore_near: bool = False) -> Dict[str, List[torch.Tensor]]:
+    """fcos_outputs.py:649-698 (_get_ground_truth) + :772-906 (compute_targets_for_locations).
+    Returns level-first lists (image-major inside a level). center_sample / radius: MODEL.FCOS.CENTER_SAMPLE / POS_RADIUS
+    (:823-838); ignore_near: keep_locations per :841-848.
     """
     ranges = sizes_of_interest(soi)
     num_loc = [len(l) for l in locations]
@@ -78,20 +98,29 @@ def fcos_assign_targets(locations: List[torch.Tensor], boxes: List[torch.Tensor]
         inds = torch.empty(L, dtype=torch.long)
         regs = torch.empty(L, 4)
         isbg = torch.empty(L, dtype=torch.bool)
+        keep = torch.ones(L, dtype=torch.bool)
+        region = center_sample_region(loc, b, strides, num_loc, radius) if center_sample else None
         for p in range(L):  # explicit per-location scan (small cases only)
             x, y = loc[p, 0], loc[p, 1]
             best, best_area = 0, float(INF)
+            any_inside = any_region = False
             for j in range(n):
                 l_, t_, r_, b_ = x - b[j, 0], y - b[j, 1], b[j, 2] - x, b[j, 3] - y
                 mn = min(l_, t_, r_, b_)
                 mx = max(l_, t_, r_, b_)
                 a = float(area[j])
-                if not (mn > 0):
+                inside = bool(mn > 0)
+                sampled = bool(region[p, j]) if center_sample else inside
+                any_inside |= inside
+                any_region |= sampled
+                if not sampled:
                     a = float(INF)
                 if not (mx >= lo[p] and mx <= hi[p]):
                     a = float(INF)
                 if a < best_area:  # first minimum wins (torch.min returns the first index on CPU)
                     best, best_area = j, a
+            if ignore_near:  # :841-848 background outside every box + everything inside a sample region
+                keep[p] = (not any_inside) or any_region
             inds[p] = best
             isbg[p] = best_area == float(INF)
             regs[p] = torch.stack([x - b[best, 0], y - b[best, 1], b[best, 2] - x, b[best, 3] - y])
@@ -105,7 +134,7 @@ def fcos_assign_targets(locations: List[torch.Tensor], boxes: List[torch.Tensor]
         per_im["box_weights"].append(bw)
         per_im["reg_targets"].append(regs)
         per_im["target_inds"].append(inds + num_targets)
-        per_im["keep_locations"].append(torch.ones(L, dtype=torch.bool))
+        per_im["keep_locations"].append(keep)
         per_im["boundary_vars"].append(bv)
         num_targets += n
     per_im["locations"] = [loc.clone() for _ in boxes]
@@ -120,7 +149,8 @@ def fcos_assign_targets(locations: List[torch.Tensor], boxes: List[torch.Tensor]
 
 
 def fcos_assign_targets_fast(locations, boxes, classes, strides, soi=(64, 128, 256, 512), num_classes=80,
-                             scores=None, reg_pred_std=None, soft_cls_label=False):
+                             scores=None, reg_pred_std=None, soft_cls_label=False, center_sample=False, radius=1.5,
+                             ignore_near=False):
     """Vectorised twin of fcos_assign_targets for full-size inputs (same tie rule: first minimum)."""
     ranges = sizes_of_interest(soi)
     num_loc = [len(l) for l in locations]
@@ -147,10 +177,12 @@ def fcos_assign_targets_fast(locations, boxes, classes, strides, soi=(64, 128, 2
         x, y = loc[:, 0:1], loc[:, 1:2]
         ltrb = torch.stack([x - b[None, :, 0], y - b[None, :, 1], b[None, :, 2] - x, b[None, :, 3] - y], 2)
         inside = ltrb.min(2)[0] > 0
+        sampled = center_sample_region(loc, b, strides, num_loc, radius) if center_sample else inside
+        keep = (~inside.any(1)) | sampled.any(1) if ignore_near else torch.ones(L, dtype=torch.bool)
         mx = ltrb.max(2)[0]
         cared = (mx >= lo) & (mx <= hi)
         area = ((b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1]))[None].repeat(L, 1)
-        area[~inside] = INF
+        area[~sampled] = INF
         area[~cared] = INF
         amin, inds = area.min(1)
         isbg = amin == INF
@@ -164,7 +196,7 @@ def fcos_assign_targets_fast(locations, boxes, classes, strides, soi=(64, 128, 2
         per_im["box_weights"].append(bw)
         per_im["reg_targets"].append(ltrb[torch.arange(L), inds])
         per_im["target_inds"].append(inds + num_targets)
-        per_im["keep_locations"].append(torch.ones(L, dtype=torch.bool))
+        per_im["keep_locations"].append(keep)
         per_im["boundary_vars"].append(bv)
         num_targets += n
     per_im["locations"] = [loc.clone() for _ in boxes]

@@ -281,6 +281,54 @@ def test_assign_targets_full_size_vs_oracle():
     torch.testing.assert_close(out["norm"].cpu(), torch.stack([pos.sum().float(), ctr.sum()]), rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("ignore_near", [False, True])
+@pytest.mark.parametrize("which", ["labeled", "pseudo"])
+def test_assign_targets_center_sample_golden(which, ignore_near):
+    """MODEL.FCOS.CENTER_SAMPLE True / POS_RADIUS 1.5 (get_sample_region) and the ignore_near keep mask: bit-exact against
+    the reference's _get_ground_truth on the two golden box sets."""
+    from ubteacher import ops
+    g = load(f"fcos_targets_{which}.pt")
+    ref = load("fcos_targets_center_sample.pt")
+    tg = ref[f"{which}_ignore_near{int(ignore_near)}"]
+    b, c, cnt, s = pack_gt(g["boxes"], g["classes"], g.get("reg_pred_std"))
+    out = ops.fcos_assign_targets(geom(), len(g["boxes"]), b, c, cnt, s, center_radius=ref["radius"], ignore_near=ignore_near)
+    cat = {k: torch.cat([t.reshape(t.shape[0], -1) if t.dim() > 1 else t for t in v]) for k, v in tg.items()}
+    assert torch.equal(out["labels"].cpu(), cat["labels"])
+    assert torch.equal(out["target_inds"].cpu(), cat["target_inds"])
+    assert torch.equal(out["reg_targets"].cpu(), cat["reg_targets"])
+    assert torch.equal(out["boundary_vars"].cpu(), cat["boundary_vars"].float())
+    assert torch.equal(out["keep_locations"].cpu().bool(), cat["keep_locations"])
+    plain = load(f"fcos_targets_{which}.pt")["targets"]
+    assert not torch.equal(cat["labels"], torch.cat(plain["labels"]))          # the option changes the assignment on this set
+    if ignore_near:
+        assert not bool(cat["keep_locations"].all())
+
+
+def test_assign_targets_center_sample_full_size_vs_oracle():
+    from oracle import ut2_oracle as O
+    from ubteacher import ops
+    hw = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+    gm = ops.LevelGeom(hw, STRIDES, [64, 128, 256, 512])
+    gen = torch.Generator().manual_seed(16)
+    N = 3
+    boxes, classes = [], []
+    for i in range(N):
+        n = [40, 0, 100][i]
+        xy = torch.rand(n, 2, generator=gen) * torch.tensor([1000.0, 600.0])
+        wh = torch.exp(torch.rand(n, 2, generator=gen) * 2.77 + 3.46)
+        boxes.append(torch.cat([xy, xy + wh], 1))
+        classes.append(torch.randint(0, 80, (n,), generator=gen))
+    b, c, cnt, _ = pack_gt(boxes, classes, None, G=128)
+    out = ops.fcos_assign_targets(gm, N, b, c, cnt, None, center_radius=1.5, ignore_near=True)
+    L = [O.compute_locations(h, w, s) for (h, w), s in zip(hw, STRIDES)]
+    ref = O.fcos_assign_targets_fast(L, boxes, classes, STRIDES, center_sample=True, radius=1.5, ignore_near=True)
+    assert torch.equal(out["labels"].cpu(), torch.cat(ref["labels"]))
+    assert torch.equal(out["target_inds"].cpu(), torch.cat(ref["target_inds"]))
+    assert torch.equal(out["reg_targets"].cpu(), torch.cat(ref["reg_targets"]))
+    assert torch.equal(out["keep_locations"].cpu().bool(), torch.cat(ref["keep_locations"]))
+    assert 0 < int(out["keep_locations"].sum()) < out["keep_locations"].numel()
+
+
 def _run_loss(g, mode, tg_kw, gout, scales=None):
     from ubteacher import ops
     N = g["logits"][0].shape[0]

@@ -148,6 +148,36 @@ def test_labeled_loss_and_gradients_match_oracle(model):
     model.engine.arena.grad.zero_()
 
 
+def test_center_sample_and_ignore_near_losses_match_oracle(model):
+    """MODEL.FCOS.CENTER_SAMPLE True (POS_RADIUS 1.5: config.py:151-152, off in the shipped recipes) and ignore_near through the
+    detector: the labeled losses follow the oracle's with the same options (keep_locations filters the focal term)."""
+    import functools
+    from util_cfg import fcos_cfg
+    from oracle import ut2_model as M
+    from oracle import ut2_oracle as O
+    from ubteacher.modeling.fcos.fcos_outputs import FCOSOutputs
+    cfg = fcos_cfg()
+    cfg.MODEL.FCOS.CENTER_SAMPLE = True
+    assert FCOSOutputs(cfg).center_radius == 1.5
+    batch = make_batch(3, [(160, 224), (128, 192)], 5, nbox=6)
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    model.train()
+    plain, _ = model.forward_train(batch, "labeled")
+    model.fcos_outputs.center_radius = 1.5
+    try:
+        losses, _ = model.forward_train(batch, "labeled", ignore_near=True)
+    finally:
+        model.fcos_outputs.center_radius = 0.0
+    with torch.no_grad():
+        s = M.forward_dense(sd, [b["image"] for b in batch])
+        assign = functools.partial(O.fcos_assign_targets_fast, center_sample=True, radius=1.5, ignore_near=True)
+        ref, _ = O.fcos_losses_labeled(s["logits"], s["reg"], s["std"], s["ctr"], s["locations"], [b["boxes"] for b in batch],
+                                       [b["classes"] for b in batch], assign=assign)
+    for k in ref:
+        torch.testing.assert_close(losses[k].cpu(), ref[k], rtol=3e-2, atol=1e-3)
+    assert abs(float(losses["loss_fcos_cls"]) - float(plain["loss_fcos_cls"])) > 1e-3 * float(plain["loss_fcos_cls"])
+
+
 def _cosr(a, b):
     a, b = a.float().cpu().double().flatten(), b.double().flatten()
     return float((a * b).sum() / (a.norm() * b.norm() + 1e-30)), float(a.norm() / (b.norm() + 1e-30))

@@ -43,6 +43,25 @@ def test_fcos_targets(name, fast):
                 assert torch.equal(a.long(), b.long()), (k, lvl)
 
 
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("ignore_near", [False, True])
+@pytest.mark.parametrize("which", ["labeled", "pseudo"])
+def test_fcos_targets_center_sample(which, ignore_near, fast):
+    """CENTER_SAMPLE / POS_RADIUS (get_sample_region) and ignore_near against the reference's _get_ground_truth."""
+    g = load(f"fcos_targets_{which}.pt")
+    ref = load("fcos_targets_center_sample.pt")
+    fn = O.fcos_assign_targets_fast if fast else O.fcos_assign_targets
+    out = fn(locs(), g["boxes"], g["classes"], STRIDES, scores=g.get("scores"), reg_pred_std=g.get("reg_pred_std"),
+             center_sample=True, radius=ref["radius"], ignore_near=ignore_near)
+    for k, r in ref[f"{which}_ignore_near{int(ignore_near)}"].items():
+        for lvl, (a, b) in enumerate(zip(out[k], r)):
+            assert a.shape == b.shape, (k, lvl)
+            if a.dtype.is_floating_point:
+                assert torch.equal(a, b.to(a.dtype)), (k, lvl)
+            else:
+                assert torch.equal(a.long(), b.long()), (k, lvl)
+
+
 def test_loss_pieces():
     g = load("loss_pieces.pt")
     tc = lambda a, b: torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)

@@ -49,7 +49,7 @@ __device__ __forceinline__ float ctr_target(const float (&t)[4]) {
 __global__ void __launch_bounds__(256)
 assign_targets_kernel(Levels lv, int N, int G, const float* __restrict__ boxes, const long long* __restrict__ classes,
                       const int* __restrict__ counts, const float* __restrict__ bvar, int num_classes,
-                      long long* __restrict__ labels, long long* __restrict__ tinds, float* __restrict__ reg_t,
+                      float center_radius, int ignore_near, long long* __restrict__ labels, long long* __restrict__ tinds, float* __restrict__ reg_t,
                       float* __restrict__ bv_out, uint8_t* __restrict__ keep, float* __restrict__ norm) {
   const long long P = (long long)lv.off[lv.num] * N;
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -69,16 +69,34 @@ assign_targets_kernel(Levels lv, int N, int G, const float* __restrict__ boxes, 
       int best = 0;
       float best_area = BG_AREA;
       const float* b = boxes + (size_t)img * G * 4;
+      // CENTER_SAMPLE (get_sample_region, fcos_outputs.py:700-770): a location is positive for a box only inside the box's
+      // centre region, [centre -/+ stride * radius] clipped to the box. The reference returns an all-false mask when the
+      // FIRST box of the image has centre x == 0 (its "no gt" test, :736).
+      const bool center = center_radius > 0.f;
+      const float sr = __fmul_rn((float)lv.stride[l], center_radius);
+      const bool center_none = center && __fmul_rn(b[0] + b[2], 0.5f) == 0.f;
+      bool any_inside = false, any_region = false;
       for (int j = 0; j < n; ++j) {
         const float x1 = b[4 * j], y1 = b[4 * j + 1], x2 = b[4 * j + 2], y2 = b[4 * j + 3];
         const float dl = x - x1, dt = y - y1, dr = x2 - x, db = y2 - y;
         const float mn = fminf(fminf(dl, dt), fminf(dr, db));
         const float mx = fmaxf(fmaxf(dl, dt), fmaxf(dr, db));
         float a = __fmul_rn(x2 - x1, y2 - y1);
-        if (!(mn > 0.f)) a = BG_AREA;
+        bool in = mn > 0.f;
+        any_inside |= in;
+        if (center) {
+          const float cx = __fmul_rn(x1 + x2, 0.5f), cy = __fmul_rn(y1 + y2, 0.5f);
+          const float xmin = cx - sr, ymin = cy - sr, xmax = cx + sr, ymax = cy + sr;
+          const float rx1 = xmin > x1 ? xmin : x1, ry1 = ymin > y1 ? ymin : y1;
+          const float rx2 = xmax > x2 ? x2 : xmax, ry2 = ymax > y2 ? y2 : ymax;
+          in = !center_none && fminf(fminf(x - rx1, y - ry1), fminf(rx2 - x, ry2 - y)) > 0.f;
+        }
+        any_region |= in;
+        if (!in) a = BG_AREA;
         if (!(mx >= lv.lo[l] && mx <= lv.hi[l])) a = BG_AREA;
         if (a < best_area) { best_area = a; best = j; }     // first minimum wins
       }
+      if (ignore_near) kp = (!any_inside || any_region) ? 1 : 0;      // :841-848: drop locations inside a box but off every centre region
       int prefix = 0;
       for (int i = 0; i < img; ++i) prefix += counts[i];
       ti = (long long)best + prefix;
@@ -430,15 +448,16 @@ int fill_levels(Levels& lv, int num_levels, const int* hw, const int* strides, c
 // hw / strides / ranges are HOST arrays (level geometry is a launch parameter, not data).
 extern "C" int ut2_fcos_assign_targets(int num_levels, const int* hw, const int* strides, const float* ranges, int N,
                                        int G, const float* boxes, const long long* classes, const int* counts,
-                                       const float* bvar, int num_classes, long long* labels, long long* tinds,
-                                       float* reg_t, float* bv_out, unsigned char* keep, float* norm, void* stream) {
+                                       const float* bvar, int num_classes, float center_radius, int ignore_near,
+                                       long long* labels, long long* tinds, float* reg_t, float* bv_out,
+                                       unsigned char* keep, float* norm, void* stream) {
   Levels lv;
   if (fill_levels(lv, num_levels, hw, strides, ranges)) return ut2_fail(-2, "assign_targets: bad level count");
   const long long P = (long long)lv.off[lv.num] * N;
   if (P <= 0) return ut2_fail(-2, "assign_targets: empty");
   cudaMemsetAsync(norm, 0, 2 * sizeof(float), STREAM);
   assign_targets_kernel<<<ut2_ceil_div(P, 256), 256, 0, STREAM>>>(lv, N, G, boxes, classes, counts, bvar, num_classes,
-                                                                  labels, tinds, reg_t, bv_out, keep, norm);
+                                                                  center_radius, ignore_near, labels, tinds, reg_t, bv_out, keep, norm);
   return ut2_check_launch("fcos_assign_targets");
 }
 

@@ -516,7 +516,7 @@ class UBTeacherTrainer:
                 main.wait_stream(side)         # the unlabeled pass needs the pseudo labels
             # student: unlabeled strong with the two pseudo-label sets (trainer.py:331-349)
             with nvtx_range("ut2.student_unlabeled_forward"):
-                losses_u, pending_u = self.model.forward_train(unlabel_data_q, "unlabeled")
+                losses_u, pending_u = self.model.forward_train(unlabel_data_q, "unlabeled", ss.PSEUDO_CLS_IGNORE_NEAR)    # trainer.py:340,347
             record.update({k + "_pseudo": v for k, v in losses_u.items()})
             with nvtx_range("ut2.student_unlabeled_backward"):
                 self._begin_overlap()

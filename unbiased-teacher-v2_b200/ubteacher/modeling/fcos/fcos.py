@@ -234,8 +234,6 @@ class FCOS(nn.Module):
                 ignore_near=False, branch="labeled"):
         if top_module is not None:
             raise NotImplementedError("top_module (AdelaiDet mask branches) is not part of the UT2 recipes")
-        if ignore_near:
-            raise NotImplementedError("PSEUDO_CLS_IGNORE_NEAR=True is not part of the shipped recipes")
         xs = [features[f] for f in self.in_features]
         eng = self.engine
         need_loss = self.training and branch in ("labeled", "unlabeled")
@@ -248,12 +246,13 @@ class FCOS(nn.Module):
         if self.training:
             if branch == "labeled":
                 gt = as_boxset(gt_instances, eng.device)
-                vals, ctxs = self.fcos_outputs.losses(fwd, eng.scales, gt)
+                vals, ctxs = self.fcos_outputs.losses(fwd, eng.scales, gt, ignore_near)
                 names = [[(0, "loss_fcos_cls"), (1, "loss_fcos_loc"), (2, "loss_fcos_ctr")]]
             elif branch == "unlabeled":
                 # one_stage_detector.py:170-181: {"cls": instances_class, "reg": instances_reg}
                 gt_cls, gt_reg = (gt_instances["cls"], gt_instances["reg"]) if isinstance(gt_instances, dict) else gt_instances
-                vals, ctxs = self.fcos_outputs.pseudo_losses(fwd, eng.scales, as_boxset(gt_cls, eng.device), as_boxset(gt_reg, eng.device))
+                vals, ctxs = self.fcos_outputs.pseudo_losses(fwd, eng.scales, as_boxset(gt_cls, eng.device), as_boxset(gt_reg, eng.device),
+                                                             ignore_near)
                 names = [[(0, "loss_fcos_cls"), (2, "loss_fcos_ctr")], [(3, "teacher_better_student"), (1, "loss_fcos_loc")]]
             elif branch == "raw":
                 ctxs, names = [], []

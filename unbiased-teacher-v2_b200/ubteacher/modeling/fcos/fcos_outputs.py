@@ -93,6 +93,7 @@ class FCOSOutputs:
         self.nms_thresh = f.NMS_TH
         self.ts_better, self.ts_cert = cfg.SEMISUPNET.TS_BETTER, cfg.SEMISUPNET.TS_BETTER_CERT
         self.reg_unsup_loss = cfg.SEMISUPNET.CONSIST_REG_LOSS
+        self.center_radius = float(f.POS_RADIUS) if f.CENTER_SAMPLE else 0.0     # get_sample_region (fcos_outputs.py:700-770)
         assert f.KL_LOSS_TYPE == "nlloss" and f.LOC_LOSS_TYPE == "giou" and f.QUALITY_EST == "centerness" and \
             cfg.SEMISUPNET.CLS_LOSS_METHOD == "focal" and not f.THRESH_WITH_CTR and not cfg.SEMISUPNET.SOFT_CLS_LABEL, \
             "the B200 loss kernels implement the shipped UT2 recipe (focal / centerness / nlloss+giou)"
@@ -107,31 +108,33 @@ class FCOSOutputs:
         return self.train(False)
 
     # ---------------------------------------------------------------- losses
-    def _targets(self, fwd, boxset):
+    def _targets(self, fwd, boxset, ignore_near=False):
         tg = ops.fcos_assign_targets(fwd["geom"], fwd["N"], boxset.boxes, boxset.classes, boxset.counts,
-                                     boxset.reg_pred_std, self.num_classes)
+                                     boxset.reg_pred_std, self.num_classes, self.center_radius, ignore_near)
         world = comm.get_world_size()
         if world > 1:  # fcos_outputs.py:319-321,362 — normalisers are world-averaged; one tiny all-reduce
             torch.distributed.all_reduce(tg["norm"])
         return tg, float(world)
 
-    def _fwd(self, fwd, scales, boxset, mode):
-        tg, world = self._targets(fwd, boxset)
+    def _fwd(self, fwd, scales, boxset, mode, ignore_near=False):
+        tg, world = self._targets(fwd, boxset, ignore_near)
         losses, acc = ops.fcos_loss_fwd(fwd["geom"], fwd["N"], fwd["cls_out"], fwd["box_out"], scales, tg, mode,
                                         self.alpha, self.gamma, self.kl_w, self.ts_better, self.ts_cert, world,
                                         self.num_classes)
         return LossCtx(mode, tg, acc, losses)
 
-    def losses(self, fwd, scales, gt):
-        """Supervised branch (fcos_outputs.py:212-305 + :307-444). Returns (dict of loss scalars, ctx)."""
-        ctx = self._fwd(fwd, scales, gt, 0)
+    def losses(self, fwd, scales, gt, ignore_near=False):
+        """Supervised branch (fcos_outputs.py:212-305 + :307-444). Returns (dict of loss scalars, ctx). ``ignore_near`` drops
+        the locations inside a box but off its sample region from the classification loss (keep_locations, :310-311)."""
+        ctx = self._fwd(fwd, scales, gt, 0, ignore_near)
         L = ctx.losses
         return {"loss_fcos_cls": L[0], "loss_fcos_loc": L[1], "loss_fcos_ctr": L[2]}, [ctx]
 
-    def pseudo_losses(self, fwd, scales, gt_cls, gt_reg):
-        """Unsupervised branch (fcos_outputs.py:447-490 + :492-631)."""
-        c1 = self._fwd(fwd, scales, gt_cls, 1)
-        c2 = self._fwd(fwd, scales, gt_reg, 2)
+    def pseudo_losses(self, fwd, scales, gt_cls, gt_reg, ignore_near=False):
+        """Unsupervised branch (fcos_outputs.py:447-490 + :492-631). ``ignore_near`` (SEMISUPNET.PSEUDO_CLS_IGNORE_NEAR) only
+        changes the keep_locations the targets carry: fcos_pseudo_losses never reads them (:492-631), here as there."""
+        c1 = self._fwd(fwd, scales, gt_cls, 1, ignore_near)
+        c2 = self._fwd(fwd, scales, gt_reg, 2, ignore_near)
         return {"loss_fcos_cls": c1.losses[0], "loss_fcos_ctr": c1.losses[2], "teacher_better_student": c2.losses[3],
                 "loss_fcos_loc": c2.losses[1]}, [c1, c2]
 

@@ -31,7 +31,7 @@ class FcosEngine(EngineBase):
         assert f.NUM_CLASSES == 80 and f.REG_DISCRETE and f.REG_MAX == 16 and f.KL_LOSS and f.NORM == "GN", \
             "the B200 engine implements the shipped UT2 FCOS recipe (80 classes, REG_DISCRETE(16), KL_LOSS, GN)"
         assert f.NUM_CLS_CONVS == 4 and f.NUM_BOX_CONVS == 4 and f.NUM_SHARE_CONVS == 0 and f.TOP_LEVELS == 2
-        assert not f.CENTER_SAMPLE and f.USE_SCALE
+        assert f.USE_SCALE      # CENTER_SAMPLE / POS_RADIUS are target-assignment options (FCOSOutputs), not engine ones
         self._build()
         if init:
             self.init_weights(seed)

@@ -160,9 +160,7 @@ class OneStageDetector(PseudoProposalNetwork):
             if output_raw:
                 return super().forward(batched_inputs, output_raw, nms_method, branch=branch)
             return [{"instances": r["proposals"]} for r in super().forward(batched_inputs, False, nms_method, branch=branch)]
-        if ignore_near:
-            raise NotImplementedError("PSEUDO_CLS_IGNORE_NEAR=True is not part of the shipped recipes")
-        losses, pending = self.forward_train(batched_inputs, branch)
+        losses, pending = self.forward_train(batched_inputs, branch, ignore_near)
         vec = _LossGraph.apply(self._trigger, self, pending)
         out, i = {}, 0
         for ctx_names in pending["names"]:
@@ -173,7 +171,7 @@ class OneStageDetector(PseudoProposalNetwork):
             return out, pending["fwd"], self.last_proposals
         return out
 
-    def forward_train(self, batched_inputs, branch):
+    def forward_train(self, batched_inputs, branch, ignore_near=False):
         """Explicit (autograd-free) training forward: returns (dict of detached loss scalars, pending ctx)."""
         eng = self.engine
         fwd = eng.forward(self._images(batched_inputs), train=True)
@@ -185,14 +183,14 @@ class OneStageDetector(PseudoProposalNetwork):
                 as_boxset([x["instances_reg"] for x in batched_inputs], self.device)
             if branch != "unlabeled":
                 raise ValueError("Incorrect branch name")
-            losses, ctxs = self.fcos_outputs.pseudo_losses(fwd, eng.scales, gt_cls, gt_reg)
+            losses, ctxs = self.fcos_outputs.pseudo_losses(fwd, eng.scales, gt_cls, gt_reg, ignore_near)
             names = [[(0, "loss_fcos_cls"), (2, "loss_fcos_ctr")], [(3, "teacher_better_student"), (1, "loss_fcos_loc")]]
         elif "instances" in b0 and branch != "teacher_weak":
             if branch != "labeled":
                 raise ValueError("Incorrect branch name")
             gt = b0["instances"] if isinstance(b0["instances"], BoxSet) else \
                 as_boxset([x["instances"] for x in batched_inputs], self.device)
-            losses, ctxs = self.fcos_outputs.losses(fwd, eng.scales, gt)
+            losses, ctxs = self.fcos_outputs.losses(fwd, eng.scales, gt, ignore_near)
             names = [[(0, "loss_fcos_cls"), (1, "loss_fcos_loc"), (2, "loss_fcos_ctr")]]
         else:
             raise ValueError("Unknown branch")

@@ -278,8 +278,9 @@ class LevelGeom:
         self.off = off
 
 
-def fcos_assign_targets(geom, N, boxes, classes, counts, bvar, num_classes=80):
-    """boxes [N,G,4] f32, classes [N,G] i64, counts [N] i32, bvar [N,G,4] f32 or None."""
+def fcos_assign_targets(geom, N, boxes, classes, counts, bvar, num_classes=80, center_radius=0.0, ignore_near=False):
+    """boxes [N,G,4] f32, classes [N,G] i64, counts [N] i32, bvar [N,G,4] f32 or None. center_radius > 0: CENTER_SAMPLE
+    with that POS_RADIUS; ignore_near: keep_locations per fcos_outputs.py:841-848."""
     dev = boxes.device
     P = geom.L * N
     G = boxes.shape[1]
@@ -292,7 +293,7 @@ def fcos_assign_targets(geom, N, boxes, classes, counts, bvar, num_classes=80):
         "norm": torch.empty(2, dtype=torch.float32, device=dev),
     }
     _C.counted_call("ut2_fcos_assign_targets", geom.num, geom.c_hw, geom.c_strides, geom.c_ranges, N, G, boxes,
-                    classes, counts, bvar, num_classes, out["labels"], out["target_inds"], out["reg_targets"],
+                    classes, counts, bvar, num_classes, f32(center_radius), int(bool(ignore_near)), out["labels"], out["target_inds"], out["reg_targets"],
                     out["boundary_vars"], out["keep_locations"], out["norm"])
     return out
 
