@@ -5,7 +5,7 @@
 set -u
 OUT=gpurun_out
 mkdir -p $OUT
-TESTS="tests/test_conv_gpu.py tests/test_kernels_gpu.py"
+TESTS="tests/test_conv_gpu.py tests/test_kernels_gpu.py tests/test_layers_gpu.py"
 SEL='not stage_width'    # that case spawns a child interpreter (not followed by the tool)
 for tool in memcheck racecheck synccheck; do
   timeout 1500 compute-sanitizer --tool $tool --error-exitcode 99 --print-limit 20 \

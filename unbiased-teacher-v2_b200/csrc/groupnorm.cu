@@ -35,7 +35,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 constexpr int GN_G = 32;          // groups (== vectors per pixel)
 constexpr int GN_ROWS = 8;        // pixel rows per block iteration (256 threads)
 #ifndef GN_BWD_OCC
-#define GN_BWD_OCC 3
+#define GN_BWD_OCC 2
 #endif
 constexpr int GN_UNROLL = 4;      // independent 16-byte loads in flight per thread
 
@@ -177,14 +177,17 @@ gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
   float dg[8], db[8], s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) { dg[j] = 0.f; db[j] = 0.f; }
-  for (int p = p0 + row; p < p1; p += GN_ROWS * GN_UNROLL) {
-    uint4 vx[GN_UNROLL], vd[GN_UNROLL];
+  // Two register batches in ping-pong: the loads of the next GN_UNROLL rows are in flight while this batch is reduced (ncu on the
+  // single-buffered loop: 24 % of the warp slots active and ~60 % of the samples waiting on these loads).
+  auto load = [&](uint4 (&vx)[GN_UNROLL], uint4 (&vd)[GN_UNROLL], int p) {
 #pragma unroll
     for (int u = 0; u < GN_UNROLL; ++u) {
       const int pp = p + u * GN_ROWS;
       vx[u] = pp < p1 ? __ldg(xv + (size_t)pp * GN_G + g) : make_uint4(0, 0, 0, 0);
       vd[u] = pp < p1 ? __ldg(dv + (size_t)pp * GN_G + g) : make_uint4(0, 0, 0, 0);   // zero gradient: no contribution
     }
+  };
+  auto reduce = [&](const uint4 (&vx)[GN_UNROLL], const uint4 (&vd)[GN_UNROLL]) {
 #pragma unroll
     for (int u = 0; u < GN_UNROLL; ++u) {
       float f[8], d[8];
@@ -200,6 +203,25 @@ gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
         const float gg = gj * ga[j];
         s1 += gg;
         s2 = fmaf(gg, xh, s2);
+      }
+    }
+  };
+  {
+    constexpr int STEP = GN_ROWS * GN_UNROLL;
+    uint4 ax[GN_UNROLL], ad[GN_UNROLL], bx[GN_UNROLL], bd[GN_UNROLL];
+    int p = p0 + row;
+    if (p < p1) {
+      load(ax, ad, p);
+#pragma unroll 1
+      while (true) {
+        load(bx, bd, p + STEP);
+        reduce(ax, ad);
+        p += STEP;
+        if (p >= p1) break;
+        load(ax, ad, p + STEP);
+        reduce(bx, bd);
+        p += STEP;
+        if (p >= p1) break;
       }
     }
   }
@@ -248,14 +270,15 @@ gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, con
   const uint4* dv = reinterpret_cast<const uint4*>(dy) + B.base;
   uint4* ov = reinterpret_cast<uint4*>(dx) + B.base;
   float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // column sums of dx (the bias gradient of the conv before)
-  for (int p = p0 + row; p < p1; p += GN_ROWS * GN_UNROLL) {
-    uint4 vx[GN_UNROLL], vd[GN_UNROLL];
+  auto load = [&](uint4 (&vx)[GN_UNROLL], uint4 (&vd)[GN_UNROLL], int p) {
 #pragma unroll
     for (int u = 0; u < GN_UNROLL; ++u) {
       const int pp = p + u * GN_ROWS;
       vx[u] = pp < p1 ? __ldg(xv + (size_t)pp * GN_G + g) : make_uint4(0, 0, 0, 0);
       vd[u] = pp < p1 ? __ldg(dv + (size_t)pp * GN_G + g) : make_uint4(0, 0, 0, 0);
     }
+  };
+  auto apply = [&](const uint4 (&vx)[GN_UNROLL], const uint4 (&vd)[GN_UNROLL], int p) {
 #pragma unroll
     for (int u = 0; u < GN_UNROLL; ++u) {
       const int pp = p + u * GN_ROWS;
@@ -278,6 +301,25 @@ gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, con
 #pragma unroll
           for (int j = 0; j < 8; ++j) cs[j] += r8[j];
         }
+      }
+    }
+  };
+  {
+    constexpr int STEP = GN_ROWS * GN_UNROLL;      // ping-pong register batches, as in the reduce pass
+    uint4 ax[GN_UNROLL], ad[GN_UNROLL], bx[GN_UNROLL], bd[GN_UNROLL];
+    int p = p0 + row;
+    if (p < p1) {
+      load(ax, ad, p);
+#pragma unroll 1
+      while (true) {
+        load(bx, bd, p + STEP);
+        apply(ax, ad, p);
+        p += STEP;
+        if (p >= p1) break;
+        load(ax, ad, p + STEP);
+        apply(bx, bd, p);
+        p += STEP;
+        if (p >= p1) break;
       }
     }
   }
