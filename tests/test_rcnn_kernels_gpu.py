@@ -290,6 +290,8 @@ def test_roi_align_fwd_bwd():
         b = rand_boxes(g, Rcap, 256, 320, 2.0)
         b[:8] = b[:8] * 0.2 + 5                                    # small boxes -> level 0
         b[8] = torch.tensor([-20.0, -10.0, 400.0, 300.0])          # out of bounds + largest level
+        b[9] = torch.tensor([-500.0, 100.0, 800.0, 104.0])         # 47 samples per bin along x: the per-sample path of the backward
+        b[10] = torch.tensor([30.0, 20.0, 33.0, 140.0])            # thin and tall
         rois[i] = b
     rg = R.RoiGeom(hw, scales)
     nhwc = [f.permute(0, 2, 3, 1).contiguous().bfloat16().cuda() for f in feats]

@@ -12,6 +12,7 @@
 // Layouts: features NHWC bf16 per level; pooled ROI features [R, 7, 7, C] bf16 (== the [R, 12544] GEMM operand of fc1,
 // k = (ph*7 + pw)*C + c); fused predictor output [R, 96] bf16: 0..80 class scores | 81..84 deltas (l, r, d, u) |
 // 85..88 delta std | pad. ROIs are fixed-capacity [N, Rcap] rows + a per-image count; rows >= count are inert.
+#include <stdlib.h>
 #include "ut2_internal.h"
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -211,6 +212,117 @@ roi_align_kernel(RoiLevels lv, int Rcap, int C, const float* __restrict__ rois, 
           ow[i] = *reinterpret_cast<uint32_t*>(&hh);
         }
         *reinterpret_cast<uint4*>(orow + (size_t)pw * C + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+    }
+  }
+}
+
+// Backward with the sample points of a bin merged per feature pixel. The bilinear weight of a sample is separable,
+// w(sample, pixel) = wy(iy, py) * wx(ix, px), and so is the validity test, hence the total weight of pixel (py, px) in bin
+// (ph, pw) is Wy[ph][py] * Wx[pw][px] with Wy / Wx the per-axis sums over the bin's samples: (gh + 1)(gw + 1) vector atomics per
+// bin and lane instead of 4 gh gw (gh = gw = 2..4 for ROIs on their canonical level: 16..64 -> 9..25). Warp w builds the row table
+// of output row w and the column table of output column w in shared memory (lane e = pixel offset e); ROIs whose bins span
+// more than 32 pixel rows / columns (degenerate aspect ratios) take the per-sample path of roi_align_kernel<true>.
+constexpr int RA_T = 32;
+struct AxisSample { int lo, hi; float wl, wh; bool ok; };
+__device__ __forceinline__ AxisSample axis_sample(float v, int L) {
+  AxisSample r;
+  r.ok = !(v < -1.f || v > (float)L);
+  float vv = fmaxf(v, 0.f);
+  r.lo = (int)vv;
+  if (r.lo >= L - 1) { r.hi = r.lo = L - 1; vv = (float)r.lo; } else r.hi = r.lo + 1;
+  r.wh = vv - r.lo;
+  r.wl = 1.f - r.wh;
+  return r;
+}
+// pixel range [lo, lo + n) and weights of bin `b` along one axis (start v1, bin size bs, g samples, L pixels)
+__device__ __forceinline__ void axis_table(float v1, float bs, int g, int L, int b, int lane, float* tab, int* lo_out, int* n_out) {
+  int lo = 1 << 30, hi = -1;
+  for (int i = 0; i < g; ++i) {
+    const AxisSample a = axis_sample(v1 + b * bs + (i + 0.5f) * bs / (float)g, L);
+    if (a.ok) { lo = min(lo, a.lo); hi = max(hi, a.hi); }
+  }
+  const int n = hi >= lo ? hi - lo + 1 : 0;
+  if (n > 0 && n <= RA_T && lane < n) {
+    const int p = lo + lane;
+    float w = 0.f;
+    for (int i = 0; i < g; ++i) {
+      const AxisSample a = axis_sample(v1 + b * bs + (i + 0.5f) * bs / (float)g, L);
+      if (a.ok) w += (a.lo == p ? a.wl : 0.f) + (a.hi == p ? a.wh : 0.f);
+    }
+    tab[lane] = w;
+  }
+  if (lane == 0) { *lo_out = lo; *n_out = n; }
+}
+
+__global__ void __launch_bounds__(224)
+roi_align_bwd_kernel(RoiLevels lv, int Rcap, int C, const float* __restrict__ rois, const int* __restrict__ roi_cnt,
+                     const bf16* __restrict__ dout) {
+  const int r = blockIdx.x;
+  const int img = r / Rcap, k = r - img * Rcap;
+  const int ph = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (k >= roi_cnt[img]) return;
+  const float4 b = reinterpret_cast<const float4*>(rois)[r];
+  const int l = roi_level(b, lv.num);
+  const int H = lv.H[l], W = lv.W[l];
+  const float sc = lv.scale[l];
+  const float x1 = b.x * sc - 0.5f, y1 = b.y * sc - 0.5f;
+  const float rw = b.z * sc - 0.5f - x1, rh = b.w * sc - 0.5f - y1;
+  const float bw = rw / 7.f, bh = rh / 7.f;
+  const int gh = (int)ceilf(rh / 7.f), gw = (int)ceilf(rw / 7.f);
+  const float inv_cnt = 1.f / fmaxf((float)(gh * gw), 1.f);
+  float* df = lv.dfeat[l] + (size_t)img * H * W * C;
+  __shared__ float sWy[7][RA_T], sWx[7][RA_T];
+  __shared__ int sYlo[7], sYn[7], sXlo[7], sXn[7];
+  axis_table(y1, bh, gh, H, ph, lane, sWy[ph], &sYlo[ph], &sYn[ph]);
+  axis_table(x1, bw, gw, W, ph, lane, sWx[ph], &sXlo[ph], &sXn[ph]);
+  __syncthreads();
+  bool merged = true;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) merged = merged && sYn[i] <= RA_T && sXn[i] <= RA_T;
+  const int ylo = sYlo[ph], yn = sYn[ph];
+  for (int pw = 0; pw < 7; ++pw) {
+    const int xlo = sXlo[pw], xn = sXn[pw];
+    for (int c0 = lane * 8; c0 < C; c0 += 256) {
+      float acc[8];
+      const uint4 g = *reinterpret_cast<const uint4*>(dout + ((size_t)r * 49 + ph * 7 + pw) * C + c0);
+      const uint32_t gw4[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] = __uint_as_float(gw4[i] << 16) * inv_cnt;
+        acc[2 * i + 1] = __uint_as_float(gw4[i] & 0xFFFF0000u) * inv_cnt;
+      }
+      if (merged) {
+        for (int iy = 0; iy < yn; ++iy) {
+          const float wy = sWy[ph][iy];
+          if (wy == 0.f) continue;
+          float* drow = df + ((size_t)(ylo + iy) * W + xlo) * C + c0;
+          for (int ix = 0; ix < xn; ++ix) {
+            const float w = wy * sWx[pw][ix];
+            if (w == 0.f) continue;
+            float* d = drow + (size_t)ix * C;
+            atomicAdd(reinterpret_cast<float4*>(d), make_float4(acc[0] * w, acc[1] * w, acc[2] * w, acc[3] * w));
+            atomicAdd(reinterpret_cast<float4*>(d + 4), make_float4(acc[4] * w, acc[5] * w, acc[6] * w, acc[7] * w));
+          }
+        }
+      } else {
+        for (int iy = 0; iy < gh; ++iy) {
+          const AxisSample ay = axis_sample(y1 + ph * bh + (iy + 0.5f) * bh / (float)gh, H);
+          if (!ay.ok) continue;
+          for (int ix = 0; ix < gw; ++ix) {
+            const AxisSample ax = axis_sample(x1 + pw * bw + (ix + 0.5f) * bw / (float)gw, W);
+            if (!ax.ok) continue;
+            const float w4[4] = {ay.wl * ax.wl, ay.wl * ax.wh, ay.wh * ax.wl, ay.wh * ax.wh};
+            const size_t o4[4] = {((size_t)ay.lo * W + ax.lo) * C + c0, ((size_t)ay.lo * W + ax.hi) * C + c0,
+                                  ((size_t)ay.hi * W + ax.lo) * C + c0, ((size_t)ay.hi * W + ax.hi) * C + c0};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float* d = df + o4[q];
+              atomicAdd(reinterpret_cast<float4*>(d), make_float4(acc[0] * w4[q], acc[1] * w4[q], acc[2] * w4[q], acc[3] * w4[q]));
+              atomicAdd(reinterpret_cast<float4*>(d + 4), make_float4(acc[4] * w4[q], acc[5] * w4[q], acc[6] * w4[q], acc[7] * w4[q]));
+            }
+          }
+        }
       }
     }
   }
@@ -567,7 +679,10 @@ extern "C" int ut2_roi_align_bwd(int num_levels, float* const* dfeats, const int
   if (fill_roi_levels(lv, num_levels, nullptr, dfeats, hw, scales)) return ut2_fail(-2, "roi_align: 1..4 levels");
   if (C % 8) return ut2_fail(-3, "roi_align: C must be a multiple of 8");
   if (N * Rcap <= 0) return 0;
-  roi_align_kernel<true><<<N * Rcap, 224, 0, STREAM>>>(lv, Rcap, C, rois, roi_cnt, nullptr, static_cast<const bf16*>(dout));
+  static int merged = -1;      // UT2_ROI_BWD_MERGED=0: the per-sample kernel (A/B runs)
+  if (merged < 0) { const char* e = getenv("UT2_ROI_BWD_MERGED"); merged = e ? atoi(e) : 1; }
+  if (merged) roi_align_bwd_kernel<<<N * Rcap, 224, 0, STREAM>>>(lv, Rcap, C, rois, roi_cnt, static_cast<const bf16*>(dout));
+  else roi_align_kernel<true><<<N * Rcap, 224, 0, STREAM>>>(lv, Rcap, C, rois, roi_cnt, nullptr, static_cast<const bf16*>(dout));
   return ut2_check_launch("roi_align_bwd");
 }
 
