@@ -1,5 +1,7 @@
 """GPU parity of the tcgen05 implicit-GEMM convolution (fwd / dgrad-as-fwd / wgrad) against a plain
 PyTorch fp32 reference of the same op (floating-point kernel: tolerance stated below)."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -250,7 +252,21 @@ BIG_FWD = [
     ("res3_conv1_s2", (4, 200, 336, 256, 128, 1, 2, 0), None, True),               # 525 tiles, strided 1x1 (STRIDE_IN_1X1)
     ("p6_3x3_s2", (8, 100, 168, 256, 256, 3, 2, 1), None, False),                  # 263 tiles, strided 3x3
     ("dgrad_ragged_cin", (4, 100, 168, 80, 256, 3, 1, 1), None, False),            # 525 tiles, Cin = 80 (zero-filled ragged chunk)
+    # narrow 3x3 / stride 1 convolutions: 2-D patch kernel (conv3x3_halo.cu), like "dgrad_mask_128" above
+    ("halo_res2_conv2", (2, 200, 336, 64, 64, 3, 1, 1), None, True),               # 2 x 25 x 21 = 1050 full patches, N = 64
+    ("halo_res3_conv2", (3, 100, 168, 128, 128, 3, 1, 1), None, True),             # 13 x 11 patches per image, ragged in both axes
+    ("halo_ragged_mask", (3, 77, 101, 64, 128, 3, 1, 1), "mask", False),           # 10 x 7 patches per image, odd sizes, mask loads
+    ("halo_cin256", (2, 90, 120, 256, 128, 3, 1, 1), None, True),                  # four 64-channel slices per patch
 ]
+HALO_CASES = {"dgrad_mask_128", "halo_res2_conv2", "halo_res3_conv2", "halo_ragged_mask", "halo_cin256"}
+
+
+def _halo_launches():
+    import ctypes
+    from ubteacher import _C
+    fn = _C.lib().ut2_conv3x3_halo_launches
+    fn.restype = ctypes.c_longlong
+    return int(fn())
 
 
 @pytest.mark.parametrize("name,case,aux,relu", BIG_FWD, ids=[c[0] for c in BIG_FWD])
@@ -274,9 +290,12 @@ def test_conv_fwd_many_tiles_per_cta(name, case, aux, relu):
         mask = torch.randn(N, P, Q, Cout, generator=g).relu().bfloat16()      # half of it exactly zero, like a ReLU output
     y = torch.full((N, P, Q, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
     cu = lambda t: t.cuda() if t is not None else None
+    halo0 = _halo_launches()
     _C.call("ut2_conv2d_nhwc_bf16_fwd", x.cuda(), N, H, W, Cin, w.cuda(), Cout, R, R, stride, pad,
             None, shift.cuda(), cu(res), int(aux == "res_up2"), cu(mask), int(relu), y)
     torch.cuda.synchronize()
+    if os.environ.get("UT2_HALO3", "1") != "0":
+        assert _halo_launches() - halo0 == (1 if name in HALO_CASES else 0), "2-D patch kernel taken exactly where expected"
     r = res
     if aux == "res_up2":
         r = res.float().repeat_interleave(2, 1).repeat_interleave(2, 2)
