@@ -8,7 +8,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "unbiased-teacher-v2_b200", "lib", "libut2_sm100.so")
-WANT = ("conv_fwd_kernel", "conv_wgrad_kernel", "stem_tc_kernel", "stem_pool_tc_kernel")
+WANT = ("conv_fwd_kernel", "conv3x3_halo_kernel", "conv_wgrad_kernel", "stem_tc_kernel", "stem_pool_tc_kernel")
 KEYS = ("UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UTMAPF", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "SYNCS", "REDG", "RED.E",
         "STG.E.ENL2.256", "LDS", "STS", "HMMA", "LDG", "ATOMG")
 txt = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
@@ -32,7 +32,8 @@ for ln in txt.splitlines():
                 per[cur][k] += 1
 print(f"# cuobjdump -sass {os.path.relpath(LIB, ROOT)}  (sm_100a) — tensor-core / TMEM / TMA mnemonics per kernel")
 for name, c in per.items():
-    print(f"\n== {name.split('(')[0]}   ({len(lines[name])} SASS instructions)")
+    short = name.replace('(anonymous namespace)::', '').split('(')[0]
+    print(f"\n== {short}   ({len(lines[name])} SASS instructions)")
     print("   " + "  ".join(f"{k}x{v}" for k, v in c.items() if v))
     shown = 0
     for ins in lines[name]:
