@@ -36,8 +36,8 @@ int ut2_device_sm_count(void);
 int ut2_conv2d_nhwc_bf16_fwd(const void* x, int N, int H, int W, int Cin, const void* w, int Cout, int R, int S,
                              int stride, int pad, const float* scale, const float* shift, const void* residual,
                              int res_up2, const void* relu_mask, int relu, void* y, void* stream);
-/* 3x3 / stride 1 / pad 1 launches with 64 or 128 output channels, no scale vector and no residual (the res2 / res3 conv2 of the
- * bottlenecks and their data-gradients) run on 2-D output patches with tiled-mode TMA (csrc/conv3x3_halo.cu: each input slice is
+/* 3x3 / stride 1 / pad 1 launches with 64, 80 or 128 output channels, no scale vector and no residual (the res2 / res3 conv2 of the
+ * bottlenecks, their data-gradients, the FCOS predictors through ut2_conv2d_levels_bf16_fwd) run on 2-D output patches with tiled-mode TMA (csrc/conv3x3_halo.cu: each input slice is
  * fetched 3x instead of 9x) when they have at least one patch per SM; same results up to fp32 summation order.
  * UT2_HALO3=0 disables. Number of such launches so far (tests check that the path is taken): */
 long long ut2_conv3x3_halo_launches(void);

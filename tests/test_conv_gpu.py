@@ -258,7 +258,7 @@ BIG_FWD = [
     ("halo_ragged_mask", (3, 77, 101, 64, 128, 3, 1, 1), "mask", False),           # 10 x 7 patches per image, odd sizes, mask loads
     ("halo_cin256", (2, 90, 120, 256, 128, 3, 1, 1), None, True),                  # four 64-channel slices per patch
 ]
-HALO_CASES = {"dgrad_mask_128", "halo_res2_conv2", "halo_res3_conv2", "halo_ragged_mask", "halo_cin256"}
+HALO_CASES = {"dgrad_mask_128", "halo_res2_conv2", "halo_res3_conv2", "halo_ragged_mask", "halo_cin256", "cls_logits_80"}
 
 
 def _halo_launches():
@@ -389,7 +389,10 @@ def test_conv_levels_full_size_pyramid(cout, relu):
     w = (torch.randn(cout, 3, 3, 256, generator=g) / (9 * 256) ** 0.5).bfloat16()
     shift = torch.randn(cout, generator=g)
     dy = torch.randn(geom.L * N, cout, generator=g).bfloat16()
+    halo0 = _halo_launches()
     y = ops.conv2d_levels(x.cuda(), geom, N, w.cuda(), cout, 3, 3, 1, None, shift.cuda(), None, relu)
+    if os.environ.get("UT2_HALO3", "1") != "0":     # the 80-channel predictors run on 2-D patches, level-major (conv3x3_halo.cu)
+        assert _halo_launches() - halo0 == (1 if cout == 80 else 0)
     dw = torch.zeros(cout, 3, 3, 256, device="cuda")
     ops.conv2d_wgrad_levels(x.cuda(), dy.cuda(), geom, N, cout, 3, 3, 1, dw)
     torch.cuda.synchronize()

@@ -33,10 +33,14 @@ constexpr int H3_MAX_STAGES = 5;
 constexpr int H3_SMEM_LIMIT = 232448;
 constexpr int H3_BAR_BYTES = 1024;
 
+constexpr int H3_MAXL = 5;      // pyramid levels one launch can cover (level-major buffers, like conv_igemm.cu)
 struct Halo3Args {
-  int N, H, W, Cin, Cout;
-  int block_n;             // == Cout (64 or 128)
-  int tiles_y, tiles_x, num_tiles;
+  int N, Cin, Cout;
+  int block_n;             // == Cout (64, 80 or 128)
+  int num_levels, num_tiles;
+  int H[H3_MAXL], W[H3_MAXL], tiles_x[H3_MAXL], per_img[H3_MAXL];      // per_img = tiles_y * tiles_x
+  int tile_off[H3_MAXL + 1];                                            // first patch of level l (all images)
+  int row_off[H3_MAXL];                                                 // first pixel row of level l in the level-major buffers
   int stages;
   int relu;
   const float* shift;
@@ -51,8 +55,23 @@ __device__ __forceinline__ void tma_load_tile_4d(void* dst, const CUtensorMap* m
                : "memory");
 }
 
+struct Halo3Maps {
+  CUtensorMap m[H3_MAXL];
+};
+struct Halo3Tile { int lv, img, h0, w0; };
+__device__ __forceinline__ Halo3Tile halo_tile(const Halo3Args& a, int t) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < H3_MAXL; ++i)
+    if (i < a.num_levels && t >= a.tile_off[i]) l = i;
+  const int rem0 = t - a.tile_off[l];
+  const int img = rem0 / a.per_img[l], rem = rem0 - img * a.per_img[l];
+  const int ty = rem / a.tiles_x[l], tx = rem - ty * a.tiles_x[l];
+  return Halo3Tile{l, img, ty * H3_TH, tx * H3_TW};
+}
+
 __global__ void __launch_bounds__(H3_THREADS, 1)
-conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Halo3Args a) {
+conv3x3_halo_kernel(const __grid_constant__ Halo3Maps tmaps_x, const __grid_constant__ CUtensorMap tmap_w, const Halo3Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int STAGES = a.stages;
@@ -70,7 +89,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   const int num_sb = 3 * (a.Cin / 64);                 // (64-channel slice, s) super-blocks per tile
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmaps_x.m[0]);
     prefetch_tmap(&tmap_w);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -95,17 +114,16 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       // ------------------------------------------------ TMA producer
       uint32_t stage = 0, phase = 0;
       const uint32_t tx_bytes = H3_A_BYTES + 3 * B_TAP_BYTES;
-      const int per_img = a.tiles_y * a.tiles_x;
       for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-        const int img = t / per_img, rem = t - img * per_img;
-        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-        const int h0 = ty * H3_TH, w0 = tx * H3_TW;
+        const Halo3Tile T = halo_tile(a, t);
+        const CUtensorMap* tmap_x = &tmaps_x.m[T.lv];
+        const int img = T.img, h0 = T.h0, w0 = T.w0;
         for (int c = 0; c < a.Cin; c += 64) {
           for (int s = 0; s < 3; ++s) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * STAGE_BYTES;
             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_tile_4d(sa, &tmap_x, &full_bar[stage], c, w0 + s - 1, h0 - 1, img);
+            tma_load_tile_4d(sa, tmap_x, &full_bar[stage], c, w0 + s - 1, h0 - 1, img);
 #pragma unroll
             for (int r = 0; r < 3; ++r)
               tma_load_2d(sa + H3_A_BYTES + r * B_TAP_BYTES, &tmap_w, &full_bar[stage], (r * 3 + s) * a.Cin + c, 0);
@@ -148,11 +166,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // -------------------------------------------------- epilogue: 8 warps, TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int cw = a.block_n / 2;                       // 32 or 64 columns per warp
-    const int c0 = half * cw;
+    const int cw0 = ((a.block_n / 16 + 1) / 2) * 16;    // columns of half 0: 32 / 48 / 64 of 64 / 80 / 128
+    const int c0 = half * cw0;
+    const int cw = half ? a.block_n - cw0 : cw0;
     const int row = quad * 32 + lane;                   // tile row = y * 16 + x
     const int y = row >> 4, x = row & 15;
-    const int per_img = a.tiles_y * a.tiles_x;
     if (threadIdx.x < 64 + 128) {                       // shift vector of the (single) n-tile, staged once
       const int n = threadIdx.x - 64;
       s_shift[n] = (a.shift && n < a.Cout) ? __ldg(a.shift + n) : 0.f;
@@ -160,11 +178,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps only
     uint32_t acc = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-      const int img = t / per_img, rem = t - img * per_img;
-      const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-      const int h = ty * H3_TH + y, w = tx * H3_TW + x;
-      const bool ok = h < a.H && w < a.W;
-      const size_t orow = (((size_t)img * a.H + h) * a.W + w) * a.Cout;
+      const Halo3Tile T = halo_tile(a, t);
+      const int h = T.h0 + y, w = T.w0 + x;
+      const int H = a.H[T.lv], W = a.W[T.lv];
+      const bool ok = h < H && w < W;
+      const size_t orow = ((size_t)a.row_off[T.lv] + ((size_t)T.img * H + h) * W + w) * a.Cout;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 128 + c0;
@@ -246,17 +264,30 @@ int make_tmap_halo(CUtensorMap* m, const void* ptr, int N, int H, int W, int C) 
 
 static long long g_halo_launches = 0;
 
-// Returns 1 when the launch was taken (0: not eligible, the caller uses the im2col kernel; < 0: error).
-int conv3x3_halo_try(const void* x, int N, int H, int W, int Cin, const void* w, int Cout, const float* shift,
+// Returns 1 when the launch was taken (0: not eligible, the caller uses the im2col kernel; < 0: error). hw: [H, W] per
+// level; several levels = one launch over a level-major pyramid (the FCOS predictors: Cout = 80).
+int conv3x3_halo_try(const void* x, int num_levels, const int* hw, int N, int Cin, const void* w, int Cout, const float* shift,
                      const void* relu_mask, int relu, void* y, int sm_budget, void* stream) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("UT2_HALO3"); on = e ? atoi(e) : 1; }
-  if (!on || (Cout != 64 && Cout != 128) || Cin % 64 || Cin > 512) return 0;
+  static int on80 = -1;      // UT2_HALO80=0: the 80-channel predictors stay on the im2col kernel (A/B runs)
+  if (on80 < 0) { const char* e = getenv("UT2_HALO80"); on80 = e ? atoi(e) : 1; }
+  if (Cout == 80 && !on80) return 0;
+  if (!on || (Cout != 64 && Cout != 80 && Cout != 128) || Cin % 64 || Cin > 512 || num_levels < 1 || num_levels > H3_MAXL) return 0;
   Halo3Args a;
-  a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.block_n = Cout;
-  a.tiles_y = (H + H3_TH - 1) / H3_TH;
-  a.tiles_x = (W + H3_TW - 1) / H3_TW;
-  a.num_tiles = N * a.tiles_y * a.tiles_x;
+  a.N = N; a.Cin = Cin; a.Cout = Cout; a.block_n = Cout; a.num_levels = num_levels;
+  a.tile_off[0] = 0;
+  long long rows = 0;
+  for (int l = 0; l < H3_MAXL; ++l) {
+    const int ll = l < num_levels ? l : num_levels - 1;
+    a.H[l] = hw[2 * ll]; a.W[l] = hw[2 * ll + 1];
+    a.tiles_x[l] = (a.W[l] + H3_TW - 1) / H3_TW;
+    a.per_img[l] = ((a.H[l] + H3_TH - 1) / H3_TH) * a.tiles_x[l];
+    a.row_off[l] = l < num_levels ? (int)rows : 0;
+    a.tile_off[l + 1] = a.tile_off[l] + (l < num_levels ? N * a.per_img[l] : 0);
+    if (l < num_levels) rows += (long long)N * a.H[l] * a.W[l];
+  }
+  a.num_tiles = a.tile_off[num_levels];
   if (a.num_tiles < sm_budget) return 0;               // less than one wave of patches: the im2col kernel's narrow tiles do better
   const int stage = H3_A_BYTES + 3 * Cout * 128;
   a.stages = (H3_SMEM_LIMIT - 1024 - H3_BAR_BYTES) / stage;
@@ -265,9 +296,17 @@ int conv3x3_halo_try(const void* x, int N, int H, int W, int Cin, const void* w,
   a.relu = relu; a.shift = shift;
   a.relu_mask = static_cast<const __nv_bfloat16*>(relu_mask);
   a.out = static_cast<__nv_bfloat16*>(y);
-  CUtensorMap tx, tw;
-  int rc = make_tmap_halo(&tx, x, N, H, W, Cin);
-  if (rc) return ut2_fail(rc, "conv3x3_halo: activation tensor map encode failed");
+  Halo3Maps tx;
+  CUtensorMap tw;
+  int rc = 0;
+  for (int l = 0; l < H3_MAXL; ++l) {
+    if (l < num_levels) {
+      rc = make_tmap_halo(&tx.m[l], static_cast<const __nv_bfloat16*>(x) + (size_t)a.row_off[l] * Cin, N, a.H[l], a.W[l], Cin);
+      if (rc) return ut2_fail(rc, "conv3x3_halo: activation tensor map encode failed");
+    } else {
+      tx.m[l] = tx.m[num_levels - 1];
+    }
+  }
   rc = make_tmap_2d_bf16(&tw, w, Cout, (uint64_t)9 * Cin, (uint64_t)9 * Cin, 64, Cout);
   if (rc) return ut2_fail(rc, "conv3x3_halo: weight tensor map encode failed");
   static bool attr_set = false;
@@ -278,7 +317,7 @@ int conv3x3_halo_try(const void* x, int N, int H, int W, int Cin, const void* w,
   }
   const int grid = a.num_tiles < sm_budget ? a.num_tiles : sm_budget;
   const size_t smem = 1024 + (size_t)a.stages * stage + H3_BAR_BYTES;
-  const double M = (double)N * H * W;
+  const double M = (double)rows;
   ut2_launch_pdl(conv3x3_halo_kernel, dim3(grid), dim3(H3_THREADS), smem, static_cast<cudaStream_t>(stream),
                  ut2_est_us(2.0 * M * Cout * 9 * Cin, 2.0 * M * (Cin + Cout * (relu_mask ? 2.0 : 1.0))), tx, tw, a);
   rc = ut2_check_launch("conv3x3_halo");

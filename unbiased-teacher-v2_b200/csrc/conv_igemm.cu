@@ -660,8 +660,8 @@ static int conv_fwd_launch(const void* x, int num_levels, const int* hw, int N, 
   if (stride < 1 || stride > 8 || pad < 0 || R < 1 || S < 1) return ut2_fail(-4, "conv_fwd: bad geometry");
   if (num_levels < 1 || num_levels > MAX_LV) return ut2_fail(-4, "conv_fwd: 1..5 levels");
   if (num_levels > 1 && (stride != 1 || res_up2)) return ut2_fail(-4, "conv_fwd: multi-level launches are stride 1, no res_up2");
-  if (num_levels == 1 && R == 3 && S == 3 && stride == 1 && pad == 1 && !scale && !residual) {
-    const int rc = conv3x3_halo_try(x, N, hw[0], hw[1], Cin, w, Cout, shift, relu_mask, relu, y, num_sms(), stream);
+  if (R == 3 && S == 3 && stride == 1 && pad == 1 && !scale && !residual) {
+    const int rc = conv3x3_halo_try(x, num_levels, hw, N, Cin, w, Cout, shift, relu_mask, relu, y, num_sms(), stream);
     if (rc) return rc < 0 ? rc : 0;      // taken (or failed): narrow 3x3 convolutions run on 2-D patches, see conv3x3_halo.cu
   }
   ConvFwdArgs a;

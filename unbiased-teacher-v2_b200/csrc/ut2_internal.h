@@ -12,10 +12,10 @@ static inline int ut2_ceil_div(long long a, long long b) { return (int)((a + b -
 // SMs the persistent kernels may fill: the device's count, or the limit set through ut2_set_sm_limit() (ut2_core.cu).
 int ut2_sm_budget(int device_sms);
 
-// 3x3 / stride 1 / pad 1 convolutions with 64 or 128 output channels on 2-D patches (conv3x3_halo.cu): 1 = launched,
+// 3x3 / stride 1 / pad 1 convolutions with 64, 80 or 128 output channels on 2-D patches (conv3x3_halo.cu): 1 = launched,
 // 0 = not eligible (the caller falls back to the im2col kernel), < 0 = error.
 namespace ut2 {
-int conv3x3_halo_try(const void* x, int N, int H, int W, int Cin, const void* w, int Cout, const float* shift,
+int conv3x3_halo_try(const void* x, int num_levels, const int* hw, int N, int Cin, const void* w, int Cout, const float* shift,
                      const void* relu_mask, int relu, void* y, int sm_budget, void* stream);
 }
 
