@@ -140,15 +140,17 @@ int ut2_fcos_assign_targets(int num_levels, const int* hw, const int* strides, c
  * (layers/iou_loss.py:23-76), NLLoss (layers/kl_loss.py:75-105), [fvcore] sigmoid_focal_loss_jit.
  * cls_out / box_out are [P, ld] bf16 (box_out: 68 distribution logits | 4 std | 1 centerness | pad); scales[levels] is
  * the learnable Scale (fcos/fcos.py:22-29,367). norm is the (all-reduced) output of ut2_fcos_assign_targets, world the
- * number of ranks. acc: double[8] scratch kept for backward; losses: float[4] = {cls, loc, ctr, teacher_better_student}. */
+ * number of ranks. kl_mode: MODEL.FCOS.KL_LOSS_TYPE / LOC_FUN_ALL of the supervised branch (:377-416) — 0 "nlloss" (the shipped
+ * recipes), 1..4 "klloss" reduced by "mean" / "sum" / "weight_ctr_sum" / "weight_ctr_mean" (layers/kl_loss.py:17-66).
+ * acc: double[8] scratch kept for backward; losses: float[4] = {cls, loc, ctr, teacher_better_student}. */
 int ut2_fcos_loss_fwd(int num_levels, const int* hw, const int* strides, int N, const void* cls_out, const void* box_out,
                       int ld, const float* scales, const long long* labels, const unsigned char* keep, const float* reg_t,
                       const float* bvar, int num_classes, int mode, float alpha, float gamma, float kl_w, float ts_better,
-                      float ts_cert, const float* norm, float world, double* acc, float* losses, void* stream);
+                      float ts_cert, const float* norm, float world, int kl_mode, double* acc, float* losses, void* stream);
 int ut2_fcos_loss_bwd(int num_levels, const int* hw, const int* strides, int N, const void* cls_out, const void* box_out,
                       int ld, const float* scales, const long long* labels, const unsigned char* keep, const float* reg_t,
                       const float* bvar, int num_classes, int mode, float alpha, float gamma, float kl_w, float ts_better,
-                      float ts_cert, const float* norm, float world, const double* acc, const float* gout, void* dcls,
+                      float ts_cert, const float* norm, float world, int kl_mode, const double* acc, const float* gout, void* dcls,
                       void* dbox, float* dscales, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------- proposals, NMS, pseudo labels

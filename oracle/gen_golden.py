@@ -139,6 +139,23 @@ def main():
                           "std": [t.grad for t in S], "ctr": [t.grad for t in C]}},
                os.path.join(OUT, "fcos_losses_labeled.pt"))
 
+    # the same inputs through the KL_LOSS_TYPE "klloss" branch (config.py:198 default; the shipped recipes use "nlloss") for the
+    # four LOC_FUN_ALL reductions (fcos_outputs.py:380-397, layers/kl_loss.py:11-73); no new random draws
+    kl_mod = sys.modules["ubteacher.layers.kl_loss"]
+    saved = (outputs.kl_loss_type, outputs.kl_loc_loss_func, outputs.loc_fun_all)
+    outputs.kl_loss_type, outputs.kl_loc_loss_func = "klloss", kl_mod.KLLoss()
+    rec_kl = {}
+    for method in ("mean", "sum", "weight_ctr_sum", "weight_ctr_mean"):
+        outputs.loc_fun_all = method
+        L2, R2, S2, C2 = leafs(logits), leafs(reg), leafs(std), leafs(ctr)
+        _, lk = outputs.losses(L2, R2, C2, locations, gt, S2, [], False, branch="labeled")
+        sum(v * (i + 1) for i, v in enumerate(lk.values())).backward()
+        rec_kl[method] = {"losses": {k: v.detach() for k, v in lk.items()}}
+        if method in ("mean", "weight_ctr_mean"):       # gradients of the regression / uncertainty maps (the others do not change)
+            rec_kl[method]["grads"] = {"reg": [t.grad for t in R2], "std": [t.grad for t in S2]}
+    outputs.kl_loss_type, outputs.kl_loc_loss_func, outputs.loc_fun_all = saved
+    torch.save(rec_kl, os.path.join(OUT, "fcos_losses_labeled_klloss.pt"))
+
     # supervised loss with no positive location at all (all-background batch -> every loss * 0)
     gt0 = []
     for _ in range(2):

@@ -307,9 +307,10 @@ def _flatten_level_first(xs: List[torch.Tensor], C: int) -> torch.Tensor:
 
 def fcos_losses_labeled(logits, reg, std, ctr, locations, boxes, classes, strides=(8, 16, 32, 64, 128),
                         num_classes=80, kl_w=0.05, alpha=0.25, gamma=2.0, world_size=1,
-                        allreduce=lambda t: t, assign=fcos_assign_targets_fast):
+                        allreduce=lambda t: t, assign=fcos_assign_targets_fast, kl_loss_type="nlloss", loc_fun_all="mean"):
     """fcos_outputs.py:212-305 (losses) + :307-444 (fcos_losses), sup1 recipe:
-    focal cls, centerness quality, REG_DISCRETE, KL_LOSS nlloss, giou. Returns (losses, extras)."""
+    focal cls, centerness quality, REG_DISCRETE, KL_LOSS nlloss, giou. Returns (losses, extras).
+    kl_loss_type "klloss" (:380-397, config.py:198 default) swaps the NLL term for KLLoss with the LOC_FUN_ALL reduction."""
     tg = assign(locations, boxes, classes, strides, num_classes=num_classes)
     labels = torch.cat(tg["labels"])
     reg_t = torch.cat(tg["reg_targets"])
@@ -332,7 +333,10 @@ def fcos_losses_labeled(logits, reg, std, ctr, locations, boxes, classes, stride
     if pos.numel() > 0:
         iou_t = iou_targets(pred.detach(), rt)
         ctr_loss = F.binary_cross_entropy_with_logits(ct[pos], ctr_t, reduction="sum") / num_pos_avg
-        nll = kl_w * nl_loss_fcos(pred, sd[pos], rt, iou_t)          # :400-408
+        if kl_loss_type == "klloss":                                  # :380-389
+            nll = kl_w * kl_loss(pred, sd[pos], rt, ctr_t, 1.0, denorm, loc_fun_all)
+        else:
+            nll = kl_w * nl_loss_fcos(pred, sd[pos], rt, iou_t)      # :400-408
         giou = iou_loss(pred, rt, ctr_t, "giou") / denorm            # :410-415
         reg_loss = kl_w * nll + giou                                 # :416 (weight applied twice)
     else:

@@ -329,7 +329,7 @@ def test_assign_targets_center_sample_full_size_vs_oracle():
     assert 0 < int(out["keep_locations"].sum()) < out["keep_locations"].numel()
 
 
-def _run_loss(g, mode, tg_kw, gout, scales=None):
+def _run_loss(g, mode, tg_kw, gout, scales=None, kl_mode=0):
     from ubteacher import ops
     N = g["logits"][0].shape[0]
     cls, box = pack_head(g["logits"], g["reg"], g["std"], g["ctr"])
@@ -337,11 +337,11 @@ def _run_loss(g, mode, tg_kw, gout, scales=None):
     gm = geom()
     tg = ops.fcos_assign_targets(gm, N, b, c, cnt, s)
     sc = (scales if scales is not None else torch.ones(5)).cuda()
-    losses, acc = ops.fcos_loss_fwd(gm, N, cls, box, sc, tg, mode, 0.25, 2.0, 0.05, 0.1, 0.8, 1.0)
+    losses, acc = ops.fcos_loss_fwd(gm, N, cls, box, sc, tg, mode, 0.25, 2.0, 0.05, 0.1, 0.8, 1.0, kl_mode=kl_mode)
     dcls = torch.full_like(cls, float("nan")) if mode != 2 else None
     dbox = torch.full_like(box, float("nan"))
     dsc = torch.zeros(5, device="cuda")
-    ops.fcos_loss_bwd(gm, N, cls, box, sc, tg, mode, 0.25, 2.0, 0.05, 0.1, 0.8, 1.0, acc, gout.cuda(), dcls, dbox, dsc)
+    ops.fcos_loss_bwd(gm, N, cls, box, sc, tg, mode, 0.25, 2.0, 0.05, 0.1, 0.8, 1.0, acc, gout.cuda(), dcls, dbox, dsc, kl_mode=kl_mode)
     return losses.cpu(), dcls, dbox, dsc.cpu()
 
 
@@ -375,6 +375,30 @@ def test_fcos_losses_labeled_vs_oracle_and_golden():
     (ref["loss_fcos_cls"] * 1 + ref["loss_fcos_loc"] * 2 + ref["loss_fcos_ctr"] * 3).backward()
     gr = _unpack_grads(dcls, dbox, 3)
     for name, leaves in (("logits", L), ("reg", R), ("std", S), ("ctr", C)):
+        for a, b in zip(gr[name], leaves):
+            scale = float(b.grad.abs().max()) + 1e-12
+            torch.testing.assert_close(a, b.grad, rtol=1e-2, atol=1e-2 * scale)   # bf16 gradient storage
+
+
+@pytest.mark.parametrize("method", ["mean", "sum", "weight_ctr_sum", "weight_ctr_mean"])
+def test_fcos_losses_labeled_klloss(method):
+    """MODEL.FCOS.KL_LOSS_TYPE "klloss" (config.py:198 default, not used by the shipped recipes) with the four LOC_FUN_ALL
+    reductions: the fused loss kernels against the oracle on the device's inputs and against the reference's numbers."""
+    from oracle import ut2_oracle as O
+    from ubteacher import ops
+    g, gold = load("fcos_losses_labeled.pt"), load("fcos_losses_labeled_klloss.pt")[method]
+    losses, dcls, dbox, _ = _run_loss(g, 0, {"boxes": g["boxes"], "classes": g["classes"]}, torch.tensor([1.0, 2.0, 3.0, 0.0]),
+                                      kl_mode=ops.KL_MODES[method])
+    leaf = lambda ts: [rb(t).requires_grad_(True) for t in ts]
+    L, R, S, C = leaf(g["logits"]), leaf(g["reg"]), leaf(g["std"]), leaf(g["ctr"])
+    ref, _ = O.fcos_losses_labeled(L, R, S, C, locs(), g["boxes"], g["classes"], kl_loss_type="klloss", loc_fun_all=method)
+    got = {"loss_fcos_cls": losses[0], "loss_fcos_loc": losses[1], "loss_fcos_ctr": losses[2]}
+    for k in ref:
+        torch.testing.assert_close(got[k], ref[k].detach(), rtol=2e-5, atol=1e-5)
+        torch.testing.assert_close(got[k], gold["losses"][k], rtol=2e-2, atol=1e-2)   # vs the reference on fp32 inputs
+    (ref["loss_fcos_cls"] * 1 + ref["loss_fcos_loc"] * 2 + ref["loss_fcos_ctr"] * 3).backward()
+    gr = _unpack_grads(dcls, dbox, 3)
+    for name, leaves in (("reg", R), ("std", S)):
         for a, b in zip(gr[name], leaves):
             scale = float(b.grad.abs().max()) + 1e-12
             torch.testing.assert_close(a, b.grad, rtol=1e-2, atol=1e-2 * scale)   # bf16 gradient storage

@@ -90,6 +90,22 @@ def test_fcos_losses_labeled_and_grads():
             torch.testing.assert_close(a.grad, b, rtol=1e-4, atol=1e-7)
 
 
+@pytest.mark.parametrize("method", ["mean", "sum", "weight_ctr_sum", "weight_ctr_mean"])
+def test_fcos_losses_labeled_klloss(method):
+    """KL_LOSS_TYPE "klloss" with the four LOC_FUN_ALL reductions, on the inputs of fcos_losses_labeled.pt."""
+    g, ref = load("fcos_losses_labeled.pt"), load("fcos_losses_labeled_klloss.pt")[method]
+    leaf = lambda ts: [t.clone().requires_grad_(True) for t in ts]
+    L, R, S, C = leaf(g["logits"]), leaf(g["reg"]), leaf(g["std"]), leaf(g["ctr"])
+    losses, _ = O.fcos_losses_labeled(L, R, S, C, locs(), g["boxes"], g["classes"], kl_loss_type="klloss", loc_fun_all=method)
+    for k, r in ref["losses"].items():
+        torch.testing.assert_close(losses[k].detach(), r, rtol=1e-5, atol=1e-6)
+    if "grads" in ref:
+        sum(losses[k] * (i + 1) for i, k in enumerate(ref["losses"].keys())).backward()
+        for name, leaves in (("reg", R), ("std", S)):
+            for a, b in zip(leaves, ref["grads"][name]):
+                torch.testing.assert_close(a.grad, b, rtol=1e-4, atol=1e-7)
+
+
 def test_fcos_losses_labeled_no_positive():
     g = load("fcos_losses_labeled_empty.pt")
     empty = [torch.zeros(0, 4)] * 2

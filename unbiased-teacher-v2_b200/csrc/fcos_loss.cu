@@ -221,7 +221,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 // the coefficients c_*), and dscale receives sum_i r_i * dz_i.
 template <bool BWD>
 __device__ __forceinline__ PosOut pos_terms(const bf16* __restrict__ row, float scale, const float (&t)[4],
-                                            const float (&bvar)[4], int mode, float ts_better, float ts_cert,
+                                            const float (&bvar)[4], int mode, int kl_mode, float ts_better, float ts_cert,
                                             float c_bce, float c_giou, float c_nll, float c_l1, float* grow,
                                             float* dscale) {
   PosOut o = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -261,19 +261,34 @@ __device__ __forceinline__ PosOut pos_terms(const bf16* __restrict__ row, float 
     const float iou = (inter + 1.f) / (uni + 1.f);
     const float giou = iou - (ac - uni) / ac;
     o.giou_w = (1.f - giou) * ct;
-    // NLL: sum_k (t-mu)^2 / (2 s^2) + 0.5 log s^2, + 2 log(2 pi), times IoU (detached)
-    float nll = 0.f, dmu[4], dsd[4];
+    float nll = 0.f, dmu[4], dsd[4], wrow = iou;
+    if (kl_mode == 0) {
+      // NLL: sum_k (t-mu)^2 / (2 s^2) + 0.5 log s^2, + 2 log(2 pi), times IoU (detached)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float sg = sigmoidf_(std_[k]);
-      const float s2 = sg * sg;
-      const float d = t[k] - pred[k];
-      nll += d * d / (2.f * s2) + 0.5f * logf(s2);
-      dmu[k] = -d / s2;
-      dsd[k] = (1.f - d * d / s2) * (1.f - sg);
+      for (int k = 0; k < 4; ++k) {
+        const float sg = sigmoidf_(std_[k]);
+        const float s2 = sg * sg;
+        const float d = t[k] - pred[k];
+        nll += d * d / (2.f * s2) + 0.5f * logf(s2);
+        dmu[k] = -d / s2;
+        dsd[k] = (1.f - d * d / s2) * (1.f - sg);
+      }
+      nll += 2.f * logf(2.f * 3.14159265358979323846f);
+    } else {
+      // KLLoss (layers/kl_loss.py:17-66, beta = 1): exp(-s) * smooth_l1(mu - t) + s / 2 on the RAW uncertainty output, summed over
+      // the four sides; the centerness target weights the row for the weight_ctr_* reductions (kl_mode 3, 4)
+      wrow = kl_mode >= 3 ? ct : 1.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float d = pred[k] - t[k], n = fabsf(d);
+        const float sl1 = n < 1.f ? 0.5f * n * n : n - 0.5f;
+        const float e = expf(-std_[k]);
+        nll += e * sl1 + 0.5f * std_[k];
+        dmu[k] = e * (n < 1.f ? d : (d > 0.f ? 1.f : -1.f));
+        dsd[k] = 0.5f - e * sl1;
+      }
     }
-    nll += 2.f * logf(2.f * 3.14159265358979323846f);
-    o.nll = nll * iou;
+    o.nll = nll * wrow;
     if (BWD) {
       // d(1-giou)/dpred
       const float dwi[4] = {min_grad(pred[0], t[0]), 0.f, min_grad(pred[2], t[2]), 0.f};
@@ -288,8 +303,8 @@ __device__ __forceinline__ PosOut pos_terms(const bf16* __restrict__ row, float 
         const float dac = dgw[k] * gh + gw * dgh[k];
         const float diou = (dinter * (uni + 1.f) - (inter + 1.f) * duni) / ((uni + 1.f) * (uni + 1.f));
         const float dgiou = diou + (duni * ac - uni * dac) / (ac * ac);
-        dpred[k] = -c_giou * ct * dgiou + c_nll * iou * dmu[k];
-        grow[68 + k] = c_nll * iou * dsd[k];
+        dpred[k] = -c_giou * ct * dgiou + c_nll * wrow * dmu[k];
+        grow[68 + k] = c_nll * wrow * dsd[k];
       }
     }
   } else {  // mode 2
@@ -331,7 +346,7 @@ __device__ __forceinline__ PosOut pos_terms(const bf16* __restrict__ row, float 
 __global__ void __launch_bounds__(128)
 pos_fwd_kernel(Levels lv, int N, const bf16* __restrict__ box_out, int ld, const float* __restrict__ scales,
                const long long* __restrict__ labels, const float* __restrict__ reg_t, const float* __restrict__ bvar,
-               int num_classes, int mode, float ts_better, float ts_cert, double* __restrict__ acc) {
+               int num_classes, int mode, int kl_mode, float ts_better, float ts_cert, double* __restrict__ acc) {
   const long long P = (long long)lv.off[lv.num] * N;
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -341,7 +356,7 @@ pos_fwd_kernel(Levels lv, int N, const bf16* __restrict__ box_out, int ld, const
     const float4 t4 = reinterpret_cast<const float4*>(reg_t)[p];
     const float4 b4 = reinterpret_cast<const float4*>(bvar)[p];
     const float t[4] = {t4.x, t4.y, t4.z, t4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
-    const PosOut o = pos_terms<false>(box_out + p * ld, scales[l], t, bv, mode, ts_better, ts_cert, 0, 0, 0, 0,
+    const PosOut o = pos_terms<false>(box_out + p * ld, scales[l], t, bv, mode, kl_mode, ts_better, ts_cert, 0, 0, 0, 0,
                                       nullptr, nullptr);
     v[0] = o.bce; v[1] = o.giou_w; v[2] = o.nll; v[3] = o.l1; v[4] = o.sel; v[5] = 1.f;
   }
@@ -363,15 +378,21 @@ pos_fwd_kernel(Levels lv, int N, const bf16* __restrict__ box_out, int ld, const
 }
 
 // losses[0..3] = cls, loc, ctr, teacher_better_student  (mode semantics as above)
+// divisor of the summed uncertainty term: NLLoss = mean over the positives; KLLoss by LOC_FUN_ALL (kl_mode 1 mean over
+// 4 * positives, 2 sum, 3 weight_ctr_sum, 4 weight_ctr_mean = / loss_denorm)
+__device__ __forceinline__ double kl_divisor(int kl_mode, double npos, float denorm) {
+  return kl_mode == 0 ? npos : (kl_mode == 1 ? 4.0 * npos : (kl_mode == 4 ? (double)denorm : 1.0));
+}
+
 __global__ void finalize_kernel(const double* __restrict__ acc, const float* __restrict__ norm, float world, int mode,
-                                float kl_w, float* __restrict__ losses) {
+                                int kl_mode, float kl_w, float* __restrict__ losses) {
   const float num_pos_avg = fmaxf(norm[0] / world, 1.0f);
   const float denorm = fmaxf(norm[1] / world, 1e-6f);
   const double npos = acc[6];
   float cls = (float)(acc[0] / num_pos_avg), loc = 0.f, ctr = 0.f, tbs = 0.f;
   if (npos > 0.0) {
     ctr = (float)(acc[1] / num_pos_avg);
-    if (mode == 0) loc = (float)(kl_w * kl_w * (acc[3] / npos) + acc[2] / denorm);
+    if (mode == 0) loc = (float)(kl_w * kl_w * (acc[3] / kl_divisor(kl_mode, npos, denorm)) + acc[2] / denorm);
     if (mode == 2) { loc = acc[5] > 0.0 ? (float)(acc[4] / acc[5]) : 0.f; tbs = (float)acc[5]; }
   }
   if (mode == 0 && npos == 0.0) cls = 0.f;    // fcos_outputs.py:430-434
@@ -381,7 +402,7 @@ __global__ void finalize_kernel(const double* __restrict__ acc, const float* __r
 __global__ void __launch_bounds__(128)
 pos_bwd_kernel(Levels lv, int N, const bf16* __restrict__ box_out, int ld, const float* __restrict__ scales,
                const long long* __restrict__ labels, const float* __restrict__ reg_t, const float* __restrict__ bvar,
-               int num_classes, int mode, float ts_better, float ts_cert, float kl_w, const double* __restrict__ acc,
+               int num_classes, int mode, int kl_mode, float ts_better, float ts_cert, float kl_w, const double* __restrict__ acc,
                const float* __restrict__ norm, float world, const float* __restrict__ gout /*[cls, loc, ctr]*/,
                bf16* __restrict__ dbox, float* __restrict__ dscales, int accumulate) {
   const long long P = (long long)lv.off[lv.num] * N;
@@ -400,7 +421,7 @@ pos_bwd_kernel(Levels lv, int N, const bf16* __restrict__ box_out, int ld, const
   const float npos = (float)acc[6];
   const float c_bce = gout[2] / num_pos_avg;
   const float c_giou = gout[1] / denorm;
-  const float c_nll = gout[1] * kl_w * kl_w / npos;
+  const float c_nll = gout[1] * kl_w * kl_w / (float)kl_divisor(kl_mode, (double)npos, denorm);
   const float c_l1 = acc[5] > 0.0 ? gout[1] / (float)acc[5] : 0.f;
   int l, img, hw;
   locate(lv, N, p, l, img, hw);
@@ -411,7 +432,7 @@ pos_bwd_kernel(Levels lv, int N, const bf16* __restrict__ box_out, int ld, const
 #pragma unroll
   for (int j = 0; j < 80; ++j) grow[j] = 0.f;
   float ds = 0.f;
-  pos_terms<true>(box_out + p * ld, scales[l], t, bv, mode, ts_better, ts_cert, c_bce, c_giou, c_nll, c_l1, grow, &ds);
+  pos_terms<true>(box_out + p * ld, scales[l], t, bv, mode, kl_mode, ts_better, ts_cert, c_bce, c_giou, c_nll, c_l1, grow, &ds);
   if (accumulate) {
     const bf16* old = dbox + p * ld;
 #pragma unroll
@@ -466,7 +487,8 @@ extern "C" int ut2_fcos_loss_fwd(int num_levels, const int* hw, const int* strid
                                  const void* box_out, int ld, const float* scales, const long long* labels,
                                  const unsigned char* keep, const float* reg_t, const float* bvar, int num_classes,
                                  int mode, float alpha, float gamma, float kl_w, float ts_better, float ts_cert,
-                                 const float* norm, float world, double* acc, float* losses, void* stream) {
+                                 const float* norm, float world, int kl_mode, double* acc, float* losses, void* stream) {
+  if (kl_mode < 0 || kl_mode > 4) return ut2_fail(-2, "fcos_loss_fwd: kl_mode 0 (nlloss) or 1..4 (klloss: mean, sum, weight_ctr_sum, weight_ctr_mean)");
   Levels lv;
   if (fill_levels(lv, num_levels, hw, strides, nullptr)) return ut2_fail(-2, "fcos_loss_fwd: bad level count");
   const long long P = (long long)lv.off[lv.num] * N;
@@ -479,8 +501,8 @@ extern "C" int ut2_fcos_loss_fwd(int num_levels, const int* hw, const int* strid
                                                  mode == 0 ? keep : nullptr, P, alpha, gamma, acc);
   }
   pos_fwd_kernel<<<ut2_ceil_div(P, 128), 128, 0, STREAM>>>(lv, N, static_cast<const bf16*>(box_out), ld, scales, labels,
-                                                           reg_t, bvar, num_classes, mode, ts_better, ts_cert, acc);
-  finalize_kernel<<<1, 1, 0, STREAM>>>(acc, norm, world, mode, kl_w, losses);
+                                                           reg_t, bvar, num_classes, mode, kl_mode, ts_better, ts_cert, acc);
+  finalize_kernel<<<1, 1, 0, STREAM>>>(acc, norm, world, mode, kl_mode, kl_w, losses);
   return ut2_check_launch("fcos_loss_fwd");
 }
 
@@ -491,8 +513,9 @@ extern "C" int ut2_fcos_loss_bwd(int num_levels, const int* hw, const int* strid
                                  const void* box_out, int ld, const float* scales, const long long* labels,
                                  const unsigned char* keep, const float* reg_t, const float* bvar, int num_classes,
                                  int mode, float alpha, float gamma, float kl_w, float ts_better, float ts_cert,
-                                 const float* norm, float world, const double* acc, const float* gout, void* dcls,
+                                 const float* norm, float world, int kl_mode, const double* acc, const float* gout, void* dcls,
                                  void* dbox, float* dscales, int accumulate, void* stream) {
+  if (kl_mode < 0 || kl_mode > 4) return ut2_fail(-2, "fcos_loss_bwd: kl_mode 0..4");
   Levels lv;
   if (fill_levels(lv, num_levels, hw, strides, nullptr)) return ut2_fail(-2, "fcos_loss_bwd: bad level count");
   const long long P = (long long)lv.off[lv.num] * N;
@@ -505,7 +528,7 @@ extern "C" int ut2_fcos_loss_bwd(int num_levels, const int* hw, const int* strid
                                                  mode == 0, static_cast<bf16*>(dcls));
   }
   pos_bwd_kernel<<<ut2_ceil_div(P, 128), 128, 0, STREAM>>>(lv, N, static_cast<const bf16*>(box_out), ld, scales, labels,
-                                                           reg_t, bvar, num_classes, mode, ts_better, ts_cert, kl_w, acc,
+                                                           reg_t, bvar, num_classes, mode, kl_mode, ts_better, ts_cert, kl_w, acc,
                                                            norm, world, gout, static_cast<bf16*>(dbox), dscales,
                                                            accumulate);
   return ut2_check_launch("fcos_loss_bwd");

@@ -94,9 +94,11 @@ class FCOSOutputs:
         self.ts_better, self.ts_cert = cfg.SEMISUPNET.TS_BETTER, cfg.SEMISUPNET.TS_BETTER_CERT
         self.reg_unsup_loss = cfg.SEMISUPNET.CONSIST_REG_LOSS
         self.center_radius = float(f.POS_RADIUS) if f.CENTER_SAMPLE else 0.0     # get_sample_region (fcos_outputs.py:700-770)
-        assert f.KL_LOSS_TYPE == "nlloss" and f.LOC_LOSS_TYPE == "giou" and f.QUALITY_EST == "centerness" and \
+        assert f.KL_LOSS_TYPE in ("nlloss", "klloss") and f.LOC_LOSS_TYPE == "giou" and f.QUALITY_EST == "centerness" and \
             cfg.SEMISUPNET.CLS_LOSS_METHOD == "focal" and not f.THRESH_WITH_CTR and not cfg.SEMISUPNET.SOFT_CLS_LABEL, \
-            "the B200 loss kernels implement the shipped UT2 recipe (focal / centerness / nlloss+giou)"
+            "the B200 loss kernels implement the shipped UT2 recipe (focal / centerness / nlloss|klloss + giou)"
+        # supervised uncertainty term (fcos_outputs.py:377-416): NLLoss, or KLLoss reduced by LOC_FUN_ALL
+        self.kl_mode = ops.KL_MODES["nlloss" if f.KL_LOSS_TYPE == "nlloss" else f.LOC_FUN_ALL]
         assert self.reg_unsup_loss == "ts_locvar_better_nms_nll_l1"
         self.training = True
 
@@ -120,7 +122,7 @@ class FCOSOutputs:
         tg, world = self._targets(fwd, boxset, ignore_near)
         losses, acc = ops.fcos_loss_fwd(fwd["geom"], fwd["N"], fwd["cls_out"], fwd["box_out"], scales, tg, mode,
                                         self.alpha, self.gamma, self.kl_w, self.ts_better, self.ts_cert, world,
-                                        self.num_classes)
+                                        self.num_classes, self.kl_mode)
         return LossCtx(mode, tg, acc, losses)
 
     def losses(self, fwd, scales, gt, ignore_near=False):
@@ -147,7 +149,8 @@ class FCOSOutputs:
         for ctx, gout in zip(ctxs, gouts):
             ops.fcos_loss_bwd(fwd["geom"], fwd["N"], fwd["cls_out"], fwd["box_out"], scales, ctx.tg, ctx.mode, self.alpha,
                               self.gamma, self.kl_w, self.ts_better, self.ts_cert, world, ctx.acc, gout,
-                              dcls if ctx.mode != 2 else None, dbox, dscales, self.num_classes, accumulate=not first)
+                              dcls if ctx.mode != 2 else None, dbox, dscales, self.num_classes, accumulate=not first,
+                              kl_mode=self.kl_mode)
             first = False
         return dcls, dbox
 

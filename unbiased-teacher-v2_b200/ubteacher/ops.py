@@ -298,23 +298,26 @@ def fcos_assign_targets(geom, N, boxes, classes, counts, bvar, num_classes=80, c
     return out
 
 
+KL_MODES = {"nlloss": 0, "mean": 1, "sum": 2, "weight_ctr_sum": 3, "weight_ctr_mean": 4}     # kl_mode of ut2_fcos_loss_*
+
+
 def fcos_loss_fwd(geom, N, cls_out, box_out, scales, tg, mode, alpha, gamma, kl_w, ts_better, ts_cert, world,
-                  num_classes=80):
+                  num_classes=80, kl_mode=0):
     dev = box_out.device
     acc = torch.empty(8, dtype=torch.float64, device=dev)
     losses = torch.empty(4, dtype=torch.float32, device=dev)
     _C.counted_call("ut2_fcos_loss_fwd", geom.num, geom.c_hw, geom.c_strides, N, cls_out, box_out, box_out.shape[-1],
                     scales, tg["labels"], tg["keep_locations"], tg["reg_targets"], tg["boundary_vars"], num_classes, mode, f32(alpha),
-                    f32(gamma), f32(kl_w), f32(ts_better), f32(ts_cert), tg["norm"], f32(world), acc, losses)
+                    f32(gamma), f32(kl_w), f32(ts_better), f32(ts_cert), tg["norm"], f32(world), int(kl_mode), acc, losses)
     _C.launch_count += 2 if mode != 2 else 1
     return losses, acc
 
 
 def fcos_loss_bwd(geom, N, cls_out, box_out, scales, tg, mode, alpha, gamma, kl_w, ts_better, ts_cert, world, acc,
-                  gout, dcls, dbox, dscales, num_classes=80, accumulate=False):
+                  gout, dcls, dbox, dscales, num_classes=80, accumulate=False, kl_mode=0):
     _C.counted_call("ut2_fcos_loss_bwd", geom.num, geom.c_hw, geom.c_strides, N, cls_out, box_out, box_out.shape[-1],
                     scales, tg["labels"], tg["keep_locations"], tg["reg_targets"], tg["boundary_vars"], num_classes, mode, f32(alpha),
-                    f32(gamma), f32(kl_w), f32(ts_better), f32(ts_cert), tg["norm"], f32(world), acc, gout, dcls, dbox,
+                    f32(gamma), f32(kl_w), f32(ts_better), f32(ts_cert), tg["norm"], f32(world), int(kl_mode), acc, gout, dcls, dbox,
                     dscales, int(accumulate))
     if mode != 2:
         _C.launch_count += 1
