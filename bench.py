@@ -433,7 +433,7 @@ def main():
                             f"`achieved` averages all {len(prof['conv_fwd']) // prof_steps} conv_fwd launches of a step")
         except Exception:  # noqa: BLE001
             pass
-        roof = {"bound": "tensor", "kernel": "conv_fwd_kernel (implicit-GEMM fwd + dgrad, tcgen05)", "achieved": ach,
+        roof = {"bound": "tensor", "kernel": "conv_fwd_kernel (implicit-GEMM fwd + dgrad, tcgen05; the ~29 narrow 3x3 launches per step that ut2_conv2d_* hands to conv3x3_halo_kernel are counted here too)", "achieved": ach,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peak_src,
                 "launches_per_step": len(prof["conv_fwd"]) / prof_steps, "kernel_ms_per_step": ms / prof_steps,
