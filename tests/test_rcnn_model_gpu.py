@@ -436,7 +436,7 @@ def test_cuda_graph_step_matches_eager():
 
     eager, ps, _ = run(False)
     graph, gs, tr = run(True)
-    assert tr._graph is not None, "the step was never captured"
+    assert any(e["graph"] is not None for e in tr._graphs.values()), "the step was never captured"
     assert int(tr.model.engine.seed_dev.item()) == 4      # advanced before every replay
     for i, (a, b) in enumerate(zip(eager, graph)):
         assert torch.isfinite(b).all()

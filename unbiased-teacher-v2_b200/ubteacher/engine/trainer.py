@@ -145,10 +145,12 @@ class UBTeacherTrainer:
         self.last_losses = None
         self.last_pseudo = None
         self._prefetched = None                         # next batch, when its H2D copy was started early (graph mode)
-        self._staged = None
         self.use_cuda_graph = False                     # enable_cuda_graph(): replay the whole semi-sup step
-        self._graph = None
-        self._static = None
+        # CUDA graphs of the step, one per batch geometry (multi-scale training pads every batch to its own size): key = image
+        # shapes of the four views -> {"static", "graph", "staged", "seen", ...}; all captures share one memory pool
+        self._graphs = {}
+        self._graph_pool = None
+        self._cur = None
         # gradient all-reduce overlapped with the last backward pass of a step (UT2_OVERLAP_ALLREDUCE=0: one call after it)
         self.overlap_allreduce = comm.get_world_size() > 1 and os.environ.get("UT2_OVERLAP_ALLREDUCE", "1") != "0"
         self._comm_stream = None
@@ -359,30 +361,45 @@ class UBTeacherTrainer:
     # ---------------------------------------------------------------- CUDA-graph replay of the step
     def enable_cuda_graph(self, flag=True):
         """The semi-supervised step has no host synchronisation and static shapes (fixed-capacity pseudo-label sets),
-        so after the first eager steps it is captured once and replayed: ~4000 launches per step cost one
-        cudaGraphLaunch. Inputs are copied into static buffers; the learning rate lives in device memory."""
+        so after the first eager steps it is captured and replayed: ~4000 launches per step cost one cudaGraphLaunch.
+        Inputs are copied into static buffers; the learning rate lives in device memory. One graph per batch geometry
+        (multi-scale training: INPUT.MIN_SIZE_TRAIN draws a size per image, so padded batches come in a few dozen shapes):
+        a geometry runs eagerly the first time it is seen (its lazily built per-shape buffers must exist before a capture), is
+        captured the second time, and replayed from then on; all captures share one memory pool (they never run
+        concurrently). UT2_GRAPH_CACHE caps the number of cached geometries (default 48); beyond it new ones stay eager."""
         self.use_cuda_graph = flag
         if not flag:
-            self._graph = self._static = None
+            self._graphs, self._graph_pool, self._cur = {}, None, None
 
-    def _stage_inputs(self, data):
+    @staticmethod
+    def _batch_key(data):
+        lq, lk, uq, uk = data
+        return tuple(tuple(d["image"].shape) for d in lq + lk + uq + uk)
+
+    def _graph_entry(self, data, create=True):
+        key = self._batch_key(data)
+        e = self._graphs.get(key)
+        if e is None and create and len(self._graphs) < int(os.environ.get("UT2_GRAPH_CACHE", "48")):
+            e = self._graphs[key] = {"key": key, "static": None, "graph": None, "staged": None, "seen": 0}
+        return e
+
+    def _stage_inputs(self, e, data):
         from ..modeling.fcos.fcos_outputs import BoxSet, as_boxset
         dev = self.model.device
         lq, lk, uq, uk = data
         lab = lq + lk
         gt = lab[0]["instances"] if isinstance(lab[0]["instances"], BoxSet) else as_boxset([d["instances"] for d in lab], dev)
         imgs = [d["image"] for d in lq + lk + uq + uk]
-        shapes = [tuple(i.shape) for i in imgs] + [tuple(gt.boxes.shape)]
-        if self._static is None:
-            st = {"shapes": shapes, "imgs": [torch.empty(i.shape, dtype=torch.uint8, device=dev) for i in imgs],
+        if e["static"] is None:
+            st = {"gt_shape": tuple(gt.boxes.shape), "imgs": [torch.empty(i.shape, dtype=torch.uint8, device=dev) for i in imgs],
                   "gt": BoxSet(torch.empty_like(gt.boxes), torch.empty_like(gt.classes), torch.empty_like(gt.counts))}
             n = [len(lq), len(lk), len(uq), len(uk)]
             o = [0, n[0], n[0] + n[1], n[0] + n[1] + n[2], sum(n)]
             mk = lambda a, b, with_gt: [dict({"image": t}, **({"instances": st["gt"]} if with_gt else {})) for t in st["imgs"][a:b]]
             st["data"] = (mk(o[0], o[1], True), mk(o[1], o[2], True), mk(o[2], o[3], False), mk(o[3], o[4], False))
-            self._static = st
-        st = self._static
-        if shapes != st["shapes"]:
+            e["static"] = st
+        st = e["static"]
+        if tuple(gt.boxes.shape) != st["gt_shape"]:
             return None
         for dst, src in zip(st["imgs"], imgs):
             dst.copy_(src, non_blocking=True)
@@ -392,9 +409,10 @@ class UBTeacherTrainer:
         return st["data"]
 
     def _prefetch_next(self):
-        """Called right after the graph launch of step i: fetch batch i+1 and, when it lives in (pinned) host memory, start
-        its host->device copies on a side stream into staging buffers so that they overlap step i's kernels; step i+1 then
-        only does device-to-device copies into the graph's static inputs. Device-resident batches are just fetched."""
+        """Called right after the graph launch of step i: fetch batch i+1 and, when it lives in (pinned) host memory and its
+        geometry already has static buffers, start its host->device copies on a side stream into staging buffers so that they
+        overlap step i's kernels; step i+1 then only does device-to-device copies into the graph's static inputs.
+        Device-resident batches are just fetched."""
         from ..modeling.fcos.fcos_outputs import BoxSet, as_boxset
         try:
             data = next(self._data_loader_iter)
@@ -403,15 +421,15 @@ class UBTeacherTrainer:
         self._prefetched = data
         lq, lk, uq, uk = data
         imgs = [d["image"] for d in lq + lk + uq + uk]
-        if self._static is None or any(i.is_cuda for i in imgs) or \
-                [tuple(i.shape) for i in imgs] != self._static["shapes"][:-1]:
+        e = self._graph_entry(data, create=False)
+        if e is None or e["static"] is None or any(i.is_cuda for i in imgs):
             return
         dev = self.model.device
-        if self._staged is None:
-            self._staged = {"imgs": [torch.empty_like(t) for t in self._static["imgs"]], "stream": torch.cuda.Stream(device=dev),
-                            "copied": torch.cuda.Event(), "consumed": torch.cuda.Event()}
-            self._staged["consumed"].record()
-        sg = self._staged
+        if e["staged"] is None:
+            e["staged"] = {"imgs": [torch.empty_like(t) for t in e["static"]["imgs"]], "stream": torch.cuda.Stream(device=dev),
+                           "copied": torch.cuda.Event(), "consumed": torch.cuda.Event()}
+            e["staged"]["consumed"].record()
+        sg = e["staged"]
         with torch.cuda.stream(sg["stream"]):
             sg["stream"].wait_event(sg["consumed"])          # the previous staging contents were copied out
             for dst, src in zip(sg["imgs"], imgs):
@@ -422,10 +440,10 @@ class UBTeacherTrainer:
             sg["copied"].record()
         sg["for"] = data
 
-    def _stage_prefetched(self, data):
+    def _stage_prefetched(self, e, data):
         """Static inputs <- staging buffers (device to device) for a batch whose H2D copies were started by _prefetch_next."""
-        sg, st = self._staged, self._static
-        if sg is None or sg.get("for") is not data or tuple(sg["gt"].boxes.shape) != st["shapes"][-1]:
+        sg, st = e["staged"], e["static"]
+        if sg is None or st is None or sg.get("for") is not data or tuple(sg["gt"].boxes.shape) != st["gt_shape"]:
             return None
         sg["for"] = None
         cur = torch.cuda.current_stream()
@@ -439,31 +457,39 @@ class UBTeacherTrainer:
         return st["data"]
 
     def _graph_step(self, data, data_time):
-        static = self._stage_prefetched(data) or self._stage_inputs(data)
-        if static is None:                      # a differently shaped batch: run it eagerly
+        e = self._graph_entry(data)
+        if e is None:                           # cache full: this geometry stays eager
+            return self._step_body(data, data_time)
+        if e["seen"] == 0:
+            e["seen"] = 1                       # a new geometry: one eager step builds its lazily allocated per-shape buffers
+            return self._step_body(data, data_time)
+        static = self._stage_prefetched(e, data) or self._stage_inputs(e, data)
+        if static is None:                      # a differently shaped label set: run it eagerly
             return self._step_body(data, data_time)
         self.optimizer.push_lr()
-        if self._graph is None:
+        if e["graph"] is None:
             from .. import _C
             torch.cuda.synchronize()
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
             g = torch.cuda.CUDAGraph()
             l0 = _C.launch_count
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, pool=self._graph_pool):
                 # fresh dict views for every capture: remove_label/add_label mutate the dicts
                 self._step_body(tuple([dict(d) for d in part] for part in static), 0.0, device_lr=True, bookkeeping=False)
-            self._graph = g
-            self._graph_launches = _C.launch_count - l0
+            e["graph"] = g
+            e["launches"] = _C.launch_count - l0
             _C.launch_count = l0
-            self._graph_names = self.last_losses[0]
-            self._graph_vec = self.last_losses[1]
+            e["names"], e["vec"] = self.last_losses
+        self._cur = e
         with nvtx_range("ut2.step.graph_replay"):
-            self._graph.replay()
+            e["graph"].replay()
         self._prefetch_next()
         from .. import _C
-        _C.launch_count += self._graph_launches      # kernels inside the replayed graph
+        _C.launch_count += e["launches"]      # kernels inside the replayed graph
         self.optimizer.steps += 1
-        self.last_losses = (self._graph_names, self._graph_vec)
-        self._host_metrics({"data_time": data_time}, self._graph_names, self._graph_vec)
+        self.last_losses = (e["names"], e["vec"])
+        self._host_metrics({"data_time": data_time}, e["names"], e["vec"])
 
     def _step_body(self, data, data_time, device_lr=False, bookkeeping=True):
         cfg, ss = self.cfg, self.cfg.SEMISUPNET
