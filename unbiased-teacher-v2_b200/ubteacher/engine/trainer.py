@@ -147,8 +147,9 @@ class UBTeacherTrainer:
         self._prefetched = None                         # next batch, when its H2D copy was started early (graph mode)
         self.use_cuda_graph = False                     # enable_cuda_graph(): replay the whole semi-sup step
         # CUDA graphs of the step, one per batch geometry (multi-scale training pads every batch to its own size): key = image
-        # shapes of the four views -> {"static", "graph", "staged", "seen", ...}; all captures share one memory pool
+        # shapes of the four views -> {"static", "graph", "staged", ...}; all captures share one memory pool
         self._graphs = {}
+        self._seen_once = {}
         self._graph_pool = None
         self._cur = None
         # gradient all-reduce overlapped with the last backward pass of a step (UT2_OVERLAP_ALLREDUCE=0: one call after it)
@@ -366,10 +367,13 @@ class UBTeacherTrainer:
         (multi-scale training: INPUT.MIN_SIZE_TRAIN draws a size per image, so padded batches come in a few dozen shapes):
         a geometry runs eagerly the first time it is seen (its lazily built per-shape buffers must exist before a capture), is
         captured the second time, and replayed from then on; all captures share one memory pool (they never run
-        concurrently). UT2_GRAPH_CACHE caps the number of cached geometries (default 48); beyond it new ones stay eager."""
+        concurrently). UT2_GRAPH_CACHE caps the number of cached geometries (default 48); beyond it new ones stay eager.
+        The key is the tuple of the images' own sizes (they are launch parameters of the stem / proposal kernels), so replay
+        needs batches whose sizes repeat — fixed-size inputs, or a dataset of uniform size with a handful of training scales;
+        batches of freely varying aspect ratios are all distinct and run eagerly (same results, more launch overhead)."""
         self.use_cuda_graph = flag
         if not flag:
-            self._graphs, self._graph_pool, self._cur = {}, None, None
+            self._graphs, self._seen_once, self._graph_pool, self._cur = {}, {}, None, None
 
     @staticmethod
     def _batch_key(data):
@@ -377,10 +381,21 @@ class UBTeacherTrainer:
         return tuple(tuple(d["image"].shape) for d in lq + lk + uq + uk)
 
     def _graph_entry(self, data, create=True):
+        """Entry of this batch's geometry, or None (first sight, or cache full). Geometries seen once are only remembered as
+        keys (a bounded LRU): batches of a dataset with free aspect ratios never repeat and must not fill the cache."""
         key = self._batch_key(data)
         e = self._graphs.get(key)
-        if e is None and create and len(self._graphs) < int(os.environ.get("UT2_GRAPH_CACHE", "48")):
-            e = self._graphs[key] = {"key": key, "static": None, "graph": None, "staged": None, "seen": 0}
+        if e is not None or not create:
+            return e
+        if key not in self._seen_once:
+            self._seen_once[key] = True
+            while len(self._seen_once) > 1024:
+                self._seen_once.pop(next(iter(self._seen_once)))
+            return None
+        if len(self._graphs) >= int(os.environ.get("UT2_GRAPH_CACHE", "48")):
+            return None
+        self._seen_once.pop(key, None)
+        e = self._graphs[key] = {"key": key, "static": None, "graph": None, "staged": None}
         return e
 
     def _stage_inputs(self, e, data):
@@ -458,10 +473,7 @@ class UBTeacherTrainer:
 
     def _graph_step(self, data, data_time):
         e = self._graph_entry(data)
-        if e is None:                           # cache full: this geometry stays eager
-            return self._step_body(data, data_time)
-        if e["seen"] == 0:
-            e["seen"] = 1                       # a new geometry: one eager step builds its lazily allocated per-shape buffers
+        if e is None:       # first sight of this geometry (the eager step also builds its lazily allocated buffers), or cache full
             return self._step_body(data, data_time)
         static = self._stage_prefetched(e, data) or self._stage_inputs(e, data)
         if static is None:                      # a differently shaped label set: run it eagerly
