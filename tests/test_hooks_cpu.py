@@ -66,3 +66,34 @@ def test_dataset_catalog_and_bbox_modes(tmp_path):
     assert bbox_xyxy({"bbox": [1, 2, 3, 4]}) == [1.0, 2.0, 3.0, 4.0] == bbox_xyxy({"bbox": [1, 2, 3, 4], "bbox_mode": 0})
     with pytest.raises(ValueError):
         bbox_xyxy({"bbox": [0, 0, 1, 1], "bbox_mode": 4})
+
+
+def test_graph_cache_policy_first_sight_eager_then_entry_and_bounded(monkeypatch):
+    """Trainer._graph_entry: a batch geometry gets a graph entry on its SECOND sight, geometries seen once are only keys in a
+    bounded LRU (a dataset with free aspect ratios never repeats a batch), and the number of entries is capped."""
+    import torch
+    from ubteacher.engine.trainer import UBTeacherTrainer
+
+    class Stub:
+        _graphs, _seen_once = {}, {}
+        _batch_key = staticmethod(UBTeacherTrainer._batch_key)
+
+    def batch(h, w):
+        img = {"image": torch.empty(3, h, w, dtype=torch.uint8)}
+        return ([img], [img], [img, img], [img, img])
+
+    st = Stub()
+    entry = lambda d, **kw: UBTeacherTrainer._graph_entry(st, d, **kw)
+    a = batch(128, 160)
+    assert entry(a) is None and len(st._seen_once) == 1 and not st._graphs          # first sight: eager
+    assert entry(a, create=False) is None
+    e = entry(a)
+    assert e is not None and e["graph"] is None and not st._seen_once                # second sight: an entry to capture into
+    assert entry(a) is e and entry(a, create=False) is e
+    for i in range(1500):                                                             # never-repeating geometries
+        assert entry(batch(64 + i, 96)) is None
+    assert len(st._seen_once) == 1024 and len(st._graphs) == 1
+    monkeypatch.setenv("UT2_GRAPH_CACHE", "2")
+    b, c = batch(160, 192), batch(192, 224)
+    entry(b); entry(c)
+    assert entry(b) is not None and entry(c) is None and len(st._graphs) == 2         # cap reached: c stays eager
