@@ -145,15 +145,17 @@ conv3x3_halo_kernel(const __grid_constant__ Halo3Maps tmaps_x, const __grid_cons
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sbs = sa + H3_A_BYTES;
+          // one descriptor pair per stage; taps and K steps only move the 14-bit start-address field (byte offset >> 4; shared
+          // memory addresses stay below 2^18, so the field cannot carry): the issuing thread is a serial resource
+          const uint64_t ad0 = umma_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bd0 = umma_smem_desc_sw128(sa + H3_A_BYTES, 16, 1024);
+          const uint32_t btap = (uint32_t)B_TAP_BYTES >> 4;
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = umma_smem_desc_sw128(sa + r * (H3_TW * 128) + k * 32, 16, 1024);
-              const uint64_t bd = umma_smem_desc_sw128(sbs + r * B_TAP_BYTES + k * 32, 16, 1024);
-              umma_bf16(d_tmem, ad, bd, idesc, (sb | r | k) != 0);
-            }
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, ad0 + (uint64_t)(r * (H3_TW * 128 / 16) + k * 2), bd0 + (uint64_t)(r * btap + k * 2), idesc,
+                        (sb | r | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
