@@ -76,11 +76,13 @@ int ut2_stem_conv_u8_tc_batched(const void* const* imgs, const int* hs, const in
 /* Fused stem + max-pool (uint8 CHW images -> [N, Hp/4, Wp/4, 64] bf16): normalise + space-to-depth scratch, then the 7x7 s2
  * convolution as a 4x4 s1 tcgen05 implicit GEMM with FrozenBN / ReLU / 3x3 s2 max-pool in the epilogue; the 64-channel stem
  * activation never reaches HBM. Replaces ut2_stem_conv_u8_tc_batched + ut2_maxpool3x3s2_nhwc ([D2] BasicStem). imgs / hs / ws:
- * HOST arrays; workspace: ut2_stem_pool_workspace_bytes(N, Hp, Wp) device bytes. */
+ * HOST arrays; hw_dev: optional DEVICE int[N][2] with the same (h, w), read by the kernel instead of hs / ws — the sizes are then
+ * data, and a captured CUDA graph of the step serves every batch of the same padded size; workspace:
+ * ut2_stem_pool_workspace_bytes(N, Hp, Wp) device bytes. */
 long long ut2_stem_pool_workspace_bytes(int N, int Hp, int Wp);
 int ut2_stem_pool_u8_batched(const void* const* imgs, const int* hs, const int* ws, int N, const float* wgt_rsck,
                              const float* scale, const float* shift, float m0, float m1, float m2, float s0, float s1, float s2,
-                             void* workspace, long long workspace_bytes, void* out, int Hp, int Wp, void* stream);
+                             void* workspace, long long workspace_bytes, void* out, int Hp, int Wp, const int* hw_dev, void* stream);
 int ut2_maxpool3x3s2_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream);          /* [D2] BasicStem max_pool2d */
 int ut2_upsample2x_add_nhwc(const void* lat, const void* top, void* out, int N, int H, int W, int C, void* stream); /* [D2] FPN top-down */
 int ut2_downsample2x_sum_nhwc(const void* g, const void* addend, void* gtop, int N, int Ht, int Wt, int C, void* stream);

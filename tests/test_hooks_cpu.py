@@ -75,8 +75,12 @@ def test_graph_cache_policy_first_sight_eager_then_entry_and_bounded(monkeypatch
     from ubteacher.engine.trainer import UBTeacherTrainer
 
     class Stub:
-        _graphs, _seen_once = {}, {}
-        _batch_key = staticmethod(UBTeacherTrainer._batch_key)
+        _graphs, _seen_once, graph_padded_key = {}, {}, True
+        _batch_key = UBTeacherTrainer._batch_key
+
+        class model:
+            class engine:
+                padded_size = staticmethod(lambda sizes: (max(s[0] for s in sizes) + 31 & ~31, max(s[1] for s in sizes) + 31 & ~31))
 
     def batch(h, w):
         img = {"image": torch.empty(3, h, w, dtype=torch.uint8)}
@@ -97,3 +101,12 @@ def test_graph_cache_policy_first_sight_eager_then_entry_and_bounded(monkeypatch
     b, c = batch(160, 192), batch(192, 224)
     entry(b); entry(c)
     assert entry(b) is not None and entry(c) is None and len(st._graphs) == 2         # cap reached: c stays eager
+    # batches of mixed image sizes are keyed by the padded size of their forward groups (sizes travel as device data)
+    def mixed(sizes):
+        im = [{"image": torch.empty(3, h, w, dtype=torch.uint8)} for h, w in sizes]
+        return ([im[0]], [im[1]], [im[2]], [im[3]])
+    k1 = st._batch_key(mixed([(120, 150), (128, 160), (100, 130), (90, 140)]))
+    k2 = st._batch_key(mixed([(128, 155), (110, 160), (97, 129), (96, 131)]))
+    assert k1 == k2 == ("padded", (2, 128, 160), (1, 128, 160), (1, 96, 160))
+    st.graph_padded_key = False
+    assert st._batch_key(mixed([(120, 150), (128, 160), (100, 130), (90, 140)]))[0] == (3, 120, 150)

@@ -485,6 +485,63 @@ def test_cuda_graph_cache_over_two_batch_geometries():
     assert all(torch.isfinite(v).all() for v in graph)
 
 
+def test_cuda_graph_padded_key_serves_mixed_image_sizes():
+    """Real datasets give every image its own size: the graph is keyed by the padded size of the three forward groups and the
+    images' sizes travel as device data (the stem reads them from memory), so ONE captured graph replays batches whose images
+    differ in size, and follows the eager schedule."""
+    import random
+    from util_cfg import fcos_cfg
+    from ubteacher.d2compat.events import EventStorage
+    from ubteacher.d2compat.structures import Boxes, Instances
+    from ubteacher.data.synthetic import SyntheticTwoCropLoader
+    from ubteacher.engine import UBTeacherTrainer
+
+    class MixedSizes:
+        """crops every image of a 128 x 160 batch to its own size in (97..128) x (129..160): the padded size stays 128 x 160"""
+
+        def __iter__(self):
+            rng = random.Random(7)
+            for batch in SyntheticTwoCropLoader(1, 2, h=128, w=160, boxes_per_image=3, pool=2):
+                out = []
+                for part in batch:
+                    new = []
+                    for d in part:
+                        h, w = rng.randint(97, 128), rng.randint(129, 160)
+                        d = dict(d)
+                        d["image"] = d["image"][:, :h, :w].contiguous()
+                        if "instances" in d:
+                            b = d["instances"].gt_boxes.tensor.clone()
+                            b[:, 0::2].clamp_(0, w)
+                            b[:, 1::2].clamp_(0, h)
+                            inst = Instances((h, w))
+                            inst.gt_boxes, inst.gt_classes = Boxes(b), d["instances"].gt_classes
+                            d["instances"] = inst
+                        new.append(d)
+                    out.append(new)
+                yield tuple(out)
+
+    def run(graph):
+        tr = UBTeacherTrainer(fcos_cfg(), data_loader=MixedSizes())
+        diversify(tr.model)
+        tr.enable_cuda_graph(graph)
+        out = []
+        with EventStorage(0) as tr.storage:
+            for it in range(6):
+                tr.iter = it
+                tr.run_step_full_semisup()
+                out.append(tr.last_losses[1].cpu().clone())
+                tr.scheduler.step()
+        return out, tr
+
+    eager, _ = run(False)
+    graph, tr = run(True)
+    assert len(tr._graphs) == 1, "all six batches share one padded geometry"
+    (key, e), = tr._graphs.items()
+    assert key == ("padded", (2, 128, 160), (2, 128, 160), (2, 128, 160)) and e["graph"] is not None
+    for i, (a, b) in enumerate(zip(eager, graph)):
+        torch.testing.assert_close(a, b, rtol=[1e-5, 2e-3, 2e-3, 2e-2, 1e-1, 1e-1][i], atol=1e-3)
+
+
 def test_checkpointer_roundtrip_and_c2_pickle(tmp_path):
     """DetectionTSCheckpointer (detection_checkpoint.py:10-89): save -> load restores teacher, student, momentum, LR
     schedule and the iteration; a Caffe2-style pickle initialises the STUDENT backbone only (name matching)."""

@@ -42,6 +42,8 @@ struct S2dBatch {
   const uint8_t* img[SP_MAX_IMG];
   int h[SP_MAX_IMG], w[SP_MAX_IMG];
   int n;
+  const int* hw_dev;       // optional DEVICE array [n][2] of (h, w): the sizes are data, not launch parameters (a captured graph of
+                           // the step then serves every batch with the same padded size)
 };
 
 // one thread per (padded) space-to-depth pixel: 12 byte loads, one 32-byte store
@@ -55,7 +57,7 @@ stem_s2d_kernel(const __grid_constant__ S2dBatch batch, float m0, float m1, floa
     const int ar = (int)(r % rows), n = (int)(r / rows);
     const int a = ar - SP_PADT, b = bc - SP_PADL;
     const uint8_t* img = batch.img[n];
-    const int h = batch.h[n], w = batch.w[n];
+    const int h = batch.hw_dev ? __ldg(batch.hw_dev + 2 * n) : batch.h[n], w = batch.hw_dev ? __ldg(batch.hw_dev + 2 * n + 1) : batch.w[n];
     uint32_t o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (a >= 0 && b >= 0 && 2 * a < h && 2 * b < w) {
       float v[12];
@@ -342,11 +344,13 @@ extern "C" long long ut2_stem_pool_workspace_bytes(int N, int Hp, int Wp) {
   return (long long)N * g.rows * g.pitch * 32;
 }
 
-// imgs / hs / ws: HOST arrays (N device pointers to uint8 CHW images and their sizes, each <= Hp x Wp); ws: device scratch of
+// imgs / hs / ws: HOST arrays (N device pointers to uint8 CHW images and their sizes, each <= Hp x Wp); hw_dev: optional DEVICE
+// int[N][2] with the same sizes, read by the kernel INSTEAD of hs / ws (sizes as data: CUDA-graph replay); ws: device scratch of
 // ut2_stem_pool_workspace_bytes(N, Hp, Wp); out: [N, Hp/4, Wp/4, 64] bf16.
 extern "C" int ut2_stem_pool_u8_batched(const void* const* imgs, const int* hs, const int* ws_, int N, const float* wgt_rsck,
                                         const float* scale, const float* shift, float m0, float m1, float m2, float s0, float s1,
-                                        float s2, void* ws, long long ws_bytes, void* out, int Hp, int Wp, void* stream) {
+                                        float s2, void* ws, long long ws_bytes, void* out, int Hp, int Wp, const int* hw_dev,
+                                        void* stream) {
   if (!imgs || !hs || !ws_ || !wgt_rsck || !scale || !shift || !ws || !out) return ut2_fail(-1, "stem_pool: null pointer");
   if (N <= 0) return 0;
   if (Hp % 4 || Wp % 4) return ut2_fail(-2, "stem_pool: padded size must be a multiple of 4");
@@ -364,6 +368,7 @@ extern "C" int ut2_stem_pool_u8_batched(const void* const* imgs, const int* hs, 
       b.img[i] = static_cast<const uint8_t*>(imgs[j]);
       b.h[i] = hs[j]; b.w[i] = ws_[j];
     }
+    b.hw_dev = hw_dev ? hw_dev + 2 * i0 : nullptr;
     const long long total = (long long)b.n * g.rows * g.pitch;
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     stem_s2d_kernel<<<blocks, 256, 0, st>>>(b, m0, m1, m2, 1.f / s0, 1.f / s1, 1.f / s2, x2 + (size_t)i0 * g.rows * g.pitch * 16, g.rows,

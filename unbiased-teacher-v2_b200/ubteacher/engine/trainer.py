@@ -19,6 +19,7 @@ import time
 import numpy as np
 import torch
 
+from .. import ops as ops_mod
 from ..checkpoint import DetectionTSCheckpointer
 from ..d2compat import comm
 from ..d2compat.events import EventStorage
@@ -368,17 +369,27 @@ class UBTeacherTrainer:
         a geometry runs eagerly the first time it is seen (its lazily built per-shape buffers must exist before a capture), is
         captured the second time, and replayed from then on; all captures share one memory pool (they never run
         concurrently). UT2_GRAPH_CACHE caps the number of cached geometries (default 48); beyond it new ones stay eager.
-        The key is the tuple of the images' own sizes (they are launch parameters of the stem / proposal kernels), so replay
-        needs batches whose sizes repeat — fixed-size inputs, or a dataset of uniform size with a handful of training scales;
-        batches of freely varying aspect ratios are all distinct and run eagerly (same results, more launch overhead)."""
+        Uniform batches are keyed by the image shape. FCOS batches of mixed image sizes are keyed by the padded size of their
+        three forward groups: the images' own sizes are device data there (ops.STATIC_SIZES -> hw_dev of the stem), so one graph
+        serves every batch of that padded size. The R-CNN step bakes the sizes into its anchor / clipping launches and keeps
+        exact keys: mixed-size batches of a real dataset never repeat there and run eagerly (same results, more overhead)."""
         self.use_cuda_graph = flag
         if not flag:
             self._graphs, self._seen_once, self._graph_pool, self._cur = {}, {}, None, None
+            ops_mod.STATIC_SIZES.clear()
 
-    @staticmethod
-    def _batch_key(data):
+    # True: batches of mixed image sizes are keyed by the PADDED size of their three forward groups, the images' own sizes travel
+    # as device data (the FCOS stem reads them from memory: ops.STATIC_SIZES). The R-CNN step also bakes the sizes into its anchor /
+    # clipping launches and keeps the exact key (UBRCNNTeacherTrainer sets this to False).
+    graph_padded_key = os.environ.get("UT2_GRAPH_PADDED_KEY", "1") != "0"
+
+    def _batch_key(self, data):
         lq, lk, uq, uk = data
-        return tuple(tuple(d["image"].shape) for d in lq + lk + uq + uk)
+        shapes = tuple(tuple(d["image"].shape) for d in lq + lk + uq + uk)
+        if not self.graph_padded_key or len(set(shapes)) == 1:
+            return shapes                       # uniform batches (and the R-CNN step): the images' own shapes
+        pad = self.model.engine.padded_size
+        return ("padded",) + tuple((len(g),) + pad([tuple(d["image"].shape[1:]) for d in g]) for g in (lq + lk, uq, uk))
 
     def _graph_entry(self, data, create=True):
         """Entry of this batch's geometry, or None (first sight, or cache full). Geometries seen once are only remembered as
@@ -405,17 +416,34 @@ class UBTeacherTrainer:
         lab = lq + lk
         gt = lab[0]["instances"] if isinstance(lab[0]["instances"], BoxSet) else as_boxset([d["instances"] for d in lab], dev)
         imgs = [d["image"] for d in lq + lk + uq + uk]
+        n = [len(lq), len(lk), len(uq), len(uk)]
+        o = [0, n[0], n[0] + n[1], n[0] + n[1] + n[2], sum(n)]
+        padded = e["key"][0] == "padded"
         if e["static"] is None:
-            st = {"gt_shape": tuple(gt.boxes.shape), "imgs": [torch.empty(i.shape, dtype=torch.uint8, device=dev) for i in imgs],
+            st = {"gt_shape": tuple(gt.boxes.shape),
                   "gt": BoxSet(torch.empty_like(gt.boxes), torch.empty_like(gt.classes), torch.empty_like(gt.counts))}
-            n = [len(lq), len(lk), len(uq), len(uk)]
-            o = [0, n[0], n[0] + n[1], n[0] + n[1] + n[2], sum(n)]
-            mk = lambda a, b, with_gt: [dict({"image": t}, **({"instances": st["gt"]} if with_gt else {})) for t in st["imgs"][a:b]]
-            st["data"] = (mk(o[0], o[1], True), mk(o[1], o[2], True), mk(o[2], o[3], False), mk(o[3], o[4], False))
+            if padded:
+                # flat buffers at the padded capacity of the image's forward group + one device int32 [n, 2] of (h, w) per group;
+                # the stem finds the sizes through the group's first buffer (ops.STATIC_SIZES)
+                caps = [e["key"][1][1:]] * (n[0] + n[1]) + [e["key"][2][1:]] * n[2] + [e["key"][3][1:]] * n[3]
+                st["flat"] = [torch.empty(3 * hp * wp, dtype=torch.uint8, device=dev) for hp, wp in caps]
+                st["sizes"] = [torch.empty((k, 2), dtype=torch.int32, device=dev) for k in (n[0] + n[1], n[2], n[3])]
+                for first, sz in zip((o[0], o[2], o[3]), st["sizes"]):
+                    ops_mod.STATIC_SIZES[st["flat"][first].data_ptr()] = sz
+            else:
+                st["imgs"] = [torch.empty(i.shape, dtype=torch.uint8, device=dev) for i in imgs]
             e["static"] = st
         st = e["static"]
         if tuple(gt.boxes.shape) != st["gt_shape"]:
             return None
+        if padded:
+            st["imgs"] = [f[:i.numel()].view(i.shape) for f, i in zip(st["flat"], imgs)]      # this batch's views of the buffers
+            hw = [[int(i.shape[1]), int(i.shape[2])] for i in imgs]
+            for sz, (a, b) in zip(st["sizes"], ((o[0], o[2]), (o[2], o[3]), (o[3], o[4]))):
+                sz.copy_(torch.tensor(hw[a:b], dtype=torch.int32))
+        if padded or "data" not in st:
+            mk = lambda a, b, with_gt: [dict({"image": t}, **({"instances": st["gt"]} if with_gt else {})) for t in st["imgs"][a:b]]
+            st["data"] = (mk(o[0], o[1], True), mk(o[1], o[2], True), mk(o[2], o[3], False), mk(o[3], o[4], False))
         for dst, src in zip(st["imgs"], imgs):
             dst.copy_(src, non_blocking=True)
         st["gt"].boxes.copy_(gt.boxes, non_blocking=True)
@@ -437,8 +465,8 @@ class UBTeacherTrainer:
         lq, lk, uq, uk = data
         imgs = [d["image"] for d in lq + lk + uq + uk]
         e = self._graph_entry(data, create=False)
-        if e is None or e["static"] is None or any(i.is_cuda for i in imgs):
-            return
+        if e is None or e["static"] is None or e["key"][0] == "padded" or any(i.is_cuda for i in imgs):
+            return      # (mixed-size batches are staged by _stage_inputs only: their views change with every batch)
         dev = self.model.device
         if e["staged"] is None:
             e["staged"] = {"imgs": [torch.empty_like(t) for t in e["static"]["imgs"]], "stream": torch.cuda.Stream(device=dev),
@@ -675,6 +703,8 @@ class UBRCNNTeacherTrainer(UBTeacherTrainer):
     ``UBTeacherTrainer``; ``run_step_full_semisup`` follows :786-912 (teacher on the weak views -> threshold_bbox at
     BBOX_THRESHOLD -> student on labeled (strong + weak) and on strongly augmented unlabeled images with the pseudo
     labels; loss weights :880-905). Teacher and student are ``RcnnEngine`` replicas; pseudo labels stay on the device."""
+
+    graph_padded_key = False   # the R-CNN step bakes the image sizes into its anchor-validity / clipping launches: exact graph keys
 
     def _make_pseudo_generator(self, cfg):
         return None           # the R-CNN trainer thresholds the ROI-head detections itself (trainer.py:727-769)

@@ -150,6 +150,12 @@ def stem_conv_batched(images, w_rsck, scale, shift, mean, std, out, P, Q):
                     f32(std[0]), f32(std[1]), f32(std[2]), out, P, Q)
 
 
+# data_ptr of the first image of a static input group -> device int32 [n, 2] with the (h, w) of the group's images. Filled by the
+# trainer's CUDA-graph staging for batches of mixed image sizes: the stem then reads the sizes from device memory, and one
+# captured graph serves every batch with the same padded size (engine/trainer.py: _stage_inputs).
+STATIC_SIZES = {}
+
+
 def stem_pool_batched(images, w_rsck, scale, shift, mean, std, Hp, Wp):
     """Fused stem + max-pool: list of uint8 CHW device images -> [N, Hp/4, Wp/4, 64] bf16 (csrc/stem_pool.cu)."""
     n = len(images)
@@ -165,7 +171,7 @@ def stem_pool_batched(images, w_rsck, scale, shift, mean, std, Hp, Wp):
     hs = (ctypes.c_int * n)(*[int(im.shape[1]) for im in images])
     ws_ = (ctypes.c_int * n)(*[int(im.shape[2]) for im in images])
     _C.counted_call("ut2_stem_pool_u8_batched", ptrs, hs, ws_, n, w_rsck, scale, shift, f32(mean[0]), f32(mean[1]), f32(mean[2]),
-                    f32(std[0]), f32(std[1]), f32(std[2]), ws, i64(wsb), out, Hp, Wp)
+                    f32(std[0]), f32(std[1]), f32(std[2]), ws, i64(wsb), out, Hp, Wp, STATIC_SIZES.get(images[0].data_ptr()))
     _C.launch_count += 1  # two kernels
     return out
 
