@@ -369,18 +369,18 @@ class UBTeacherTrainer:
         a geometry runs eagerly the first time it is seen (its lazily built per-shape buffers must exist before a capture), is
         captured the second time, and replayed from then on; all captures share one memory pool (they never run
         concurrently). UT2_GRAPH_CACHE caps the number of cached geometries (default 48); beyond it new ones stay eager.
-        Uniform batches are keyed by the image shape. FCOS batches of mixed image sizes are keyed by the padded size of their
-        three forward groups: the images' own sizes are device data there (ops.STATIC_SIZES -> hw_dev of the stem), so one graph
-        serves every batch of that padded size. The R-CNN step bakes the sizes into its anchor / clipping launches and keeps
-        exact keys: mixed-size batches of a real dataset never repeat there and run eagerly (same results, more overhead)."""
+        Uniform batches are keyed by the image shape. Batches of mixed image sizes are keyed by the padded size of their three
+        forward groups: the images' own sizes are device data (ops.STATIC_SIZES -> hw_dev of the stem, ops.STATIC_HW -> image_hw
+        of the R-CNN clipping kernels), so one graph serves every batch of that padded size."""
         self.use_cuda_graph = flag
         if not flag:
             self._graphs, self._seen_once, self._graph_pool, self._cur = {}, {}, None, None
             ops_mod.STATIC_SIZES.clear()
+            ops_mod.STATIC_HW.clear()
 
     # True: batches of mixed image sizes are keyed by the PADDED size of their three forward groups, the images' own sizes travel
-    # as device data (the FCOS stem reads them from memory: ops.STATIC_SIZES). The R-CNN step also bakes the sizes into its anchor /
-    # clipping launches and keeps the exact key (UBRCNNTeacherTrainer sets this to False).
+    # as device data (the fused stem reads them from memory: ops.STATIC_SIZES; the R-CNN proposal / detection clipping reads
+    # ops.STATIC_HW). UT2_GRAPH_PADDED_KEY=0: exact image shapes only.
     graph_padded_key = os.environ.get("UT2_GRAPH_PADDED_KEY", "1") != "0"
 
     def _batch_key(self, data):
@@ -428,8 +428,10 @@ class UBTeacherTrainer:
                 caps = [e["key"][1][1:]] * (n[0] + n[1]) + [e["key"][2][1:]] * n[2] + [e["key"][3][1:]] * n[3]
                 st["flat"] = [torch.empty(3 * hp * wp, dtype=torch.uint8, device=dev) for hp, wp in caps]
                 st["sizes"] = [torch.empty((k, 2), dtype=torch.int32, device=dev) for k in (n[0] + n[1], n[2], n[3])]
-                for first, sz in zip((o[0], o[2], o[3]), st["sizes"]):
+                st["hw_f"] = [torch.empty((k, 2), dtype=torch.float32, device=dev) for k in (n[0] + n[1], n[2], n[3])]
+                for first, sz, hwf in zip((o[0], o[2], o[3]), st["sizes"], st["hw_f"]):
                     ops_mod.STATIC_SIZES[st["flat"][first].data_ptr()] = sz
+                    ops_mod.STATIC_HW[st["flat"][first].data_ptr()] = hwf
             else:
                 st["imgs"] = [torch.empty(i.shape, dtype=torch.uint8, device=dev) for i in imgs]
             e["static"] = st
@@ -439,8 +441,9 @@ class UBTeacherTrainer:
         if padded:
             st["imgs"] = [f[:i.numel()].view(i.shape) for f, i in zip(st["flat"], imgs)]      # this batch's views of the buffers
             hw = [[int(i.shape[1]), int(i.shape[2])] for i in imgs]
-            for sz, (a, b) in zip(st["sizes"], ((o[0], o[2]), (o[2], o[3]), (o[3], o[4]))):
+            for sz, hwf, (a, b) in zip(st["sizes"], st["hw_f"], ((o[0], o[2]), (o[2], o[3]), (o[3], o[4]))):
                 sz.copy_(torch.tensor(hw[a:b], dtype=torch.int32))
+                hwf.copy_(sz)
         if padded or "data" not in st:
             mk = lambda a, b, with_gt: [dict({"image": t}, **({"instances": st["gt"]} if with_gt else {})) for t in st["imgs"][a:b]]
             st["data"] = (mk(o[0], o[1], True), mk(o[1], o[2], True), mk(o[2], o[3], False), mk(o[3], o[4], False))
@@ -703,8 +706,6 @@ class UBRCNNTeacherTrainer(UBTeacherTrainer):
     ``UBTeacherTrainer``; ``run_step_full_semisup`` follows :786-912 (teacher on the weak views -> threshold_bbox at
     BBOX_THRESHOLD -> student on labeled (strong + weak) and on strongly augmented unlabeled images with the pseudo
     labels; loss weights :880-905). Teacher and student are ``RcnnEngine`` replicas; pseudo labels stay on the device."""
-
-    graph_padded_key = False   # the R-CNN step bakes the image sizes into its anchor-validity / clipping launches: exact graph keys
 
     def _make_pseudo_generator(self, cfg):
         return None           # the R-CNN trainer thresholds the ROI-head detections itself (trainer.py:727-769)

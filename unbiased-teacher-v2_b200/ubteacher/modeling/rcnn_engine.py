@@ -130,7 +130,7 @@ class RcnnEngine(EngineBase):
         feat, levels = self.fpn_forward(feats, geom, N, tape)
         rpn_out = self.rpn_head_forward(feat, geom, N, tape)
         return {"rpn_out": rpn_out, "levels": levels, "geom": geom, "rgeom": rgeom, "N": N, "image_sizes": sizes,
-                "image_hw": self.image_hw(sizes), "tape": tape, "padded": (Hp, Wp), "feat": feat}
+                "image_hw": self.image_hw(sizes, images), "tape": tape, "padded": (Hp, Wp), "feat": feat}
 
     @staticmethod
     def level_views(buf, geom, N, C):
@@ -166,7 +166,11 @@ class RcnnEngine(EngineBase):
             tape["feat"] = feat
         return rpn_out
 
-    def image_hw(self, sizes):
+    def image_hw(self, sizes, images=None):
+        if images is not None:                      # static inputs of a CUDA-graph step: the sizes live in device memory
+            hw = ops.STATIC_HW.get(images[0].data_ptr())
+            if hw is not None:
+                return hw
         key = tuple(map(tuple, sizes))
         if key not in self._image_hw:               # cached: no pinned temporary inside a graph capture
             self._image_hw[key] = torch.tensor(sizes, dtype=torch.float32).pin_memory().to(self.device, non_blocking=True)

@@ -154,6 +154,7 @@ def stem_conv_batched(images, w_rsck, scale, shift, mean, std, out, P, Q):
 # trainer's CUDA-graph staging for batches of mixed image sizes: the stem then reads the sizes from device memory, and one
 # captured graph serves every batch with the same padded size (engine/trainer.py: _stage_inputs).
 STATIC_SIZES = {}
+STATIC_HW = {}       # the same sizes as float32 [n, 2] (the R-CNN proposal / detection clipping kernels read image_hw)
 
 
 def stem_pool_batched(images, w_rsck, scale, shift, mean, std, Hp, Wp):
