@@ -110,3 +110,20 @@ def test_graph_cache_policy_first_sight_eager_then_entry_and_bounded(monkeypatch
     assert k1 == k2 == ("padded", (2, 128, 160), (1, 128, 160), (1, 96, 160))
     st.graph_padded_key = False
     assert st._batch_key(mixed([(120, 150), (128, 160), (100, 130), (90, 140)]))[0] == (3, 120, 150)
+
+
+def test_static_size_table_dies_with_its_buffer():
+    """ops.STATIC_SIZES maps the address of a static input buffer to its device-side image sizes; the entry must not outlive the
+    buffer (the allocator may hand the address to an unrelated image)."""
+    import gc
+    import torch
+    from ubteacher import ops
+    buf, sizes = torch.empty(64, dtype=torch.uint8), torch.zeros(2, 2, dtype=torch.int32)
+    ops.register_static(ops.STATIC_SIZES, buf, sizes)
+    ptr = buf.data_ptr()
+    assert ops.lookup_static(ops.STATIC_SIZES, ptr) is sizes
+    assert ops.lookup_static(ops.STATIC_SIZES, buf[:12].view(3, 2, 2).data_ptr()) is sizes      # this batch's view of the buffer
+    assert ops.lookup_static(ops.STATIC_SIZES, ptr + 1) is None
+    del buf
+    gc.collect()
+    assert ops.lookup_static(ops.STATIC_SIZES, ptr) is None and ptr not in ops.STATIC_SIZES

@@ -375,8 +375,7 @@ class UBTeacherTrainer:
         self.use_cuda_graph = flag
         if not flag:
             self._graphs, self._seen_once, self._graph_pool, self._cur = {}, {}, None, None
-            ops_mod.STATIC_SIZES.clear()
-            ops_mod.STATIC_HW.clear()
+            # (entries of the dropped static buffers die with them: ops.lookup_static checks the weak reference)
 
     # True: batches of mixed image sizes are keyed by the PADDED size of their three forward groups, the images' own sizes travel
     # as device data (the fused stem reads them from memory: ops.STATIC_SIZES; the R-CNN proposal / detection clipping reads
@@ -430,8 +429,8 @@ class UBTeacherTrainer:
                 st["sizes"] = [torch.empty((k, 2), dtype=torch.int32, device=dev) for k in (n[0] + n[1], n[2], n[3])]
                 st["hw_f"] = [torch.empty((k, 2), dtype=torch.float32, device=dev) for k in (n[0] + n[1], n[2], n[3])]
                 for first, sz, hwf in zip((o[0], o[2], o[3]), st["sizes"], st["hw_f"]):
-                    ops_mod.STATIC_SIZES[st["flat"][first].data_ptr()] = sz
-                    ops_mod.STATIC_HW[st["flat"][first].data_ptr()] = hwf
+                    ops_mod.register_static(ops_mod.STATIC_SIZES, st["flat"][first], sz)
+                    ops_mod.register_static(ops_mod.STATIC_HW, st["flat"][first], hwf)
             else:
                 st["imgs"] = [torch.empty(i.shape, dtype=torch.uint8, device=dev) for i in imgs]
             e["static"] = st

@@ -168,7 +168,7 @@ class RcnnEngine(EngineBase):
 
     def image_hw(self, sizes, images=None):
         if images is not None:                      # static inputs of a CUDA-graph step: the sizes live in device memory
-            hw = ops.STATIC_HW.get(images[0].data_ptr())
+            hw = ops.lookup_static(ops.STATIC_HW, images[0].data_ptr())
             if hw is not None:
                 return hw
         key = tuple(map(tuple, sizes))

@@ -153,8 +153,25 @@ def stem_conv_batched(images, w_rsck, scale, shift, mean, std, out, P, Q):
 # data_ptr of the first image of a static input group -> device int32 [n, 2] with the (h, w) of the group's images. Filled by the
 # trainer's CUDA-graph staging for batches of mixed image sizes: the stem then reads the sizes from device memory, and one
 # captured graph serves every batch with the same padded size (engine/trainer.py: _stage_inputs).
+# Entries are (weak reference to the static buffer, tensor): once the trainer that owns the buffer is gone its address may be
+# handed to an unrelated image, so a dead reference invalidates the entry.
 STATIC_SIZES = {}
 STATIC_HW = {}       # the same sizes as float32 [n, 2] (the R-CNN proposal / detection clipping kernels read image_hw)
+
+
+def register_static(table, buf, value):
+    import weakref
+    table[buf.data_ptr()] = (weakref.ref(buf), value)
+
+
+def lookup_static(table, ptr):
+    hit = table.get(ptr)
+    if hit is None:
+        return None
+    if hit[0]() is None:
+        del table[ptr]
+        return None
+    return hit[1]
 
 
 def stem_pool_batched(images, w_rsck, scale, shift, mean, std, Hp, Wp):
@@ -172,7 +189,7 @@ def stem_pool_batched(images, w_rsck, scale, shift, mean, std, Hp, Wp):
     hs = (ctypes.c_int * n)(*[int(im.shape[1]) for im in images])
     ws_ = (ctypes.c_int * n)(*[int(im.shape[2]) for im in images])
     _C.counted_call("ut2_stem_pool_u8_batched", ptrs, hs, ws_, n, w_rsck, scale, shift, f32(mean[0]), f32(mean[1]), f32(mean[2]),
-                    f32(std[0]), f32(std[1]), f32(std[2]), ws, i64(wsb), out, Hp, Wp, STATIC_SIZES.get(images[0].data_ptr()))
+                    f32(std[0]), f32(std[1]), f32(std[2]), ws, i64(wsb), out, Hp, Wp, lookup_static(STATIC_SIZES, images[0].data_ptr()))
     _C.launch_count += 1  # two kernels
     return out
 
